@@ -1,0 +1,125 @@
+/* strotss_b200 -- C ABI of the B200-native STROTSS loss hot path.
+ *
+ * Drop-in boundary for the per-iteration loss (+gradient) evaluation of
+ * interaction-lab-uh/STROTSS-tensorflow.  Every entry point names the reference interface it
+ * replaces (file:line are relative to the reference tree).  Plain pointers and sizes only; all
+ * matrix arguments are DEVICE pointers to dense row-major fp32 unless the name ends in _host.
+ * Work is enqueued on the CUDA stream passed as `stream` (a cudaStream_t cast to void*); nothing
+ * synchronises with the host except the *_host entry points.  The caller owns every input/output
+ * buffer; the handle owns a grow-only device workspace (no N x M / N x N / full-size temporaries
+ * other than one L2-sized row panel).  There is no CPU fallback: every call fails with
+ * STROTSS_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Return value: 0 on success, negative STROTSS_ERR_* otherwise; strotss_last_error() gives text.
+ */
+#ifndef STROTSS_B200_H
+#define STROTSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct strotss_ctx* strotss_handle;
+
+enum {
+    STROTSS_OK = 0,
+    STROTSS_ERR_ARG = -1,          /* bad argument (null pointer, non-positive size, ...)          */
+    STROTSS_ERR_DISTANCE = -2,     /* unknown distance name: wrappers raise KeyError (losses.py:74) */
+    STROTSS_ERR_CUDA = -3,         /* CUDA runtime / driver failure, or no sm_100 device           */
+    STROTSS_ERR_STATE = -4,        /* call order violated (e.g. no style target set)               */
+    STROTSS_ERR_UNSUPPORTED = -5   /* combination outside the hot path (l2/both with D != 3)       */
+};
+
+/* distance codes == keys of dist_metrics (nn/losses.py:27-28) */
+enum { STROTSS_DIST_COSINE = 0, STROTSS_DIST_L2 = 1, STROTSS_DIST_BOTH = 2 };
+
+/* slots of the scalar block written by strotss_eval* (device or host float[16]) */
+enum {
+    STROTSS_S_TOTAL = 0,        /* (alpha*loss_c + loss_s)/loss_denom        run_strotss.py:140 */
+    STROTSS_S_LOSS_C = 1,       /* ContentLoss                                run_strotss.py:21-24 */
+    STROTSS_S_LOSS_S = 2,       /* StyleLoss                                  run_strotss.py:33-40 */
+    STROTSS_S_L_M = 3,          /* moment_matching                            nn/losses.py:39-52 */
+    STROTSS_S_L_REMD = 4,       /* relaxed_emd cosine                         nn/losses.py:69-80 */
+    STROTSS_S_L_PALETTE = 5,    /* relaxed_emd 'both' on YUV                  run_strotss.py:37-39 */
+    STROTSS_S_REMD_RX = 6, STROTSS_S_REMD_RY = 7,
+    STROTSS_S_L_COV = 8, STROTSS_S_L_MEAN = 9,
+    STROTSS_S_PAL_RX = 10, STROTSS_S_PAL_RY = 11,
+    STROTSS_S_REMD_BRANCH = 12, /* 1.0 if R_X >= R_Y (gradient flows through the target->pred minima) */
+    STROTSS_S_PAL_BRANCH = 13,
+    STROTSS_NUM_SCALARS = 16
+};
+
+/* Library / handle life cycle.  Replaces nothing in the reference (TensorFlow owns its runtime);
+ * `device` plays the role of --gpu_id (run_strotss.py:176,179, nn/utils.py:73-85). */
+int strotss_create(int device, strotss_handle* out);
+void strotss_destroy(strotss_handle h);
+const char* strotss_last_error(strotss_handle h);
+const char* strotss_version(void);
+/* bytes of device workspace currently held by the handle */
+size_t strotss_workspace_bytes(strotss_handle h);
+/* kernels launched by this handle since creation (the bench's gpu_launches counter) */
+long long strotss_launch_count(strotss_handle h);
+
+/* StyleLoss.__init__(target, alpha) (run_strotss.py:28-31): fix the style target for a scale.
+ * Caches what the reference recomputes every iteration (nn/losses.py:43,49; run_strotss.py:37):
+ * normalised bf16 operand, column mean, covariance, YUV records.  style: M x D, row stride ld. */
+int strotss_set_style_target(strotss_handle h, const float* style, int M, int D, long long ld, void* stream);
+
+/* One train_step loss evaluation (run_strotss.py:136-141 without VGG/sampling):
+ *   loss_c = self_similarity(pred, content)                     run_strotss.py:24
+ *   loss_s = moment_matching(style, pred) + relaxed_emd(style, pred)
+ *            + relaxed_emd(yuv(style), yuv(pred), 'both') / max(alpha, 1)      run_strotss.py:33-40
+ *   loss   = (alpha*loss_c + loss_s) / (2 + alpha + 1/max(alpha,1))            run_strotss.py:92,140
+ * pred, content: N x D (D as given to strotss_set_style_target), row strides ld_pred / ld_content.
+ * scalars: device float[STROTSS_NUM_SCALARS].  grad_pred: device N x D (row stride ld_grad) or NULL.
+ * remd_row_argmin (M int32) / remd_col_argmin (N int32): optional device outputs (may be NULL):
+ * the prediction index matched to each style sample and the style index matched to each
+ * prediction sample. */
+int strotss_eval(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,
+                 int N, float alpha, float* scalars, float* grad_pred, long long ld_grad,
+                 int32_t* remd_row_argmin, int32_t* remd_col_argmin, void* stream);
+
+/* Same evaluation with HOST buffers (pinned memory recommended): copies pred and content to the
+ * device, runs strotss_eval, copies scalars (and grad if non-NULL) back and synchronises the stream.
+ * This is the call bench.py times as `e2e`. */
+int strotss_eval_host(strotss_handle h, const float* pred_host, const float* content_host, int N, float alpha,
+                      float* scalars_host, float* grad_host, void* stream);
+
+/* StyleLoss.__call__(prediction) alone (run_strotss.py:33-40): scalars slots L_M, L_REMD, L_PALETTE,
+ * LOSS_S are written; grad (if non-NULL) is d loss_s / d pred. */
+int strotss_style_loss(strotss_handle h, const float* pred, long long ld_pred, int N, float alpha,
+                       float* scalars, float* grad_pred, long long ld_grad, void* stream);
+
+/* relaxed_emd(x, y, distance) (nn/losses.py:69-80).  x: M x D target, y: N x D prediction.
+ * loss: device float[4] = {loss, R_X, R_Y, branch}.  grad_y: device N x D or NULL (d loss / d y).
+ * D == 3 runs the CUDA-core palette kernel for all three distances; D > 3 supports 'cosine' on the
+ * tcgen05 path (the only combination on the reference's hot path, run_strotss.py:36,39). */
+int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, const float* y, long long ldy, int N,
+                        int D, int distance, float* loss, float* grad_y, long long ld_grad,
+                        int32_t* row_argmin, int32_t* col_argmin, void* stream);
+
+/* moment_matching(x, y) (nn/losses.py:39-52).  loss: device float[3] = {loss, l_cov, l_mean};
+ * grad_y: device N x D or NULL. */
+int strotss_moment_matching(strotss_handle h, const float* x, long long ldx, int M, const float* y, long long ldy, int N,
+                            int D, float* loss, float* grad_y, long long ld_grad, void* stream);
+
+/* self_similarity(x, y) (nn/losses.py:55-66).  x, y: N x D.  loss: device float[1];
+ * grad_x: device N x D or NULL (the reference calls it with x = prediction, run_strotss.py:24). */
+int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, const float* y, long long ldy, int N,
+                            int D, float* loss, float* grad_x, long long ld_grad, void* stream);
+
+/* convert_rgb_to_yuv(x) (nn/strotss_utils.py:166-167): out[n][3] = x[n][0:3] . K_yuv. */
+int strotss_convert_rgb_to_yuv(strotss_handle h, const float* x, long long ldx, int n, float* out, void* stream);
+
+/* Test hook: C[m][n] = alpha * sum_k bf16(A[m][k]) * bf16(B[n][k]) through the tcgen05 GEMM core
+ * (fp32 in, fp32 out; tile_n is 128 or 256).  Not part of the reference interface. */
+int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha,
+                       float* C, int tile_n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STROTSS_B200_H */

@@ -1,0 +1,339 @@
+"""CPU oracle for the STROTSS per-iteration loss hot path.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: the reference (interaction-lab-uh/STROTSS-tensorflow) ships no tests, golden
+vectors or fixtures for this path, and TensorFlow cannot be imported in this environment, so
+this restatement cannot be checked against reference outputs.  It is pinned only by the
+analytic known-answer cases, invariances and fp64 finite-difference checks in tests/.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module, and only as the checker.  The product path (strotss_tensorflow_b200) never
+imports it and has no CPU fallback.
+
+This is a NumPy restatement, op by op, of
+  nn/losses.py:8-9    mae
+  nn/losses.py:12-15  cosine_distance
+  nn/losses.py:18-24  l2_distance
+  nn/losses.py:27-28  dist_metrics
+  nn/losses.py:31-36  reshape_2d
+  nn/losses.py:39-52  moment_matching
+  nn/losses.py:55-66  self_similarity
+  nn/losses.py:69-80  relaxed_emd
+  nn/strotss_utils.py:166-167  convert_rgb_to_yuv
+  run_strotss.py:21-40         ContentLoss / StyleLoss
+  run_strotss.py:65,92,140,155 alpha schedule, loss_denom, total loss
+with hand-written reverse-mode gradients that encode TensorFlow's op semantics
+(third-party, unpinned `tensorflow` in requirements.txt:1; README.md:11 says >= 2.6.0):
+  * tf.nn.l2_normalize(x, axis, epsilon=1e-12) = x * rsqrt(max(sum(x^2), epsilon))
+  * tf.reduce_min gradient is shared equally among tied minima
+  * tf.maximum(a, b) gradient goes entirely to `a` when a >= b
+  * tf.abs gradient is sign(x) (0 at 0); tf.sqrt gradient is 0.5 / sqrt(x)
+  * tf.image.rgb_to_yuv uses the fixed 3x3 kernel below.
+Every function takes a `dtype` so the same code runs as fp64 (truth) or fp32 (what a
+TF fp32 run would roughly give).  Matrices are materialised exactly like the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# tf.image.rgb_to_yuv kernel (rows = R, G, B inputs; columns = Y, U, V outputs).
+RGB_TO_YUV = np.array(
+    [[0.299, -0.14714119, 0.61497538],
+     [0.587, -0.28886916, -0.51496512],
+     [0.114, 0.43601035, -0.10001026]], dtype=np.float64)
+
+L2N_EPS = 1e-12      # tf.nn.l2_normalize default epsilon (nn/losses.py:13-14)
+L2D_CLAMP = 1e-06    # nn/losses.py:23
+COLSUM_CLAMP = 1e-12  # nn/losses.py:60,63
+
+
+# --------------------------------------------------------------------------------------
+# forward building blocks
+# --------------------------------------------------------------------------------------
+def reshape_2d(x, channel_axis: int = -1):
+    """nn/losses.py:31-36.  The rank test at :32 never fires, so always squeeze+reshape."""
+    x = np.asarray(x)
+    x = np.squeeze(x)
+    if x.ndim == 0:
+        x = x.reshape(1, 1)
+    if x.ndim == 1:
+        # tf.reshape(x, (-1, shape[-1])) of a rank-1 tensor gives one row
+        return x.reshape(1, x.shape[0])
+    return x.reshape(-1, x.shape[channel_axis])
+
+
+def mae(x, y):
+    """nn/losses.py:8-9."""
+    return np.mean(np.abs(x - y))
+
+
+def l2_normalize(x, dtype=np.float64):
+    x = np.asarray(x, dtype=dtype)
+    ss = np.sum(x * x, axis=1, keepdims=True)
+    r = 1.0 / np.sqrt(np.maximum(ss, dtype(L2N_EPS)))
+    return x * r, ss, r
+
+
+def _l2_normalize_bwd(x, ss, r, g):
+    """Reverse of x * rsqrt(max(ss, eps)).  tf.maximum sends the gradient to ss when ss >= eps."""
+    gx = g * r
+    live = (ss >= L2N_EPS)
+    dot = np.sum(g * x, axis=1, keepdims=True)
+    gx = gx - np.where(live, x * dot * r ** 3, 0.0)
+    return gx
+
+
+def cosine_distance(x, y, dtype=np.float64):
+    """nn/losses.py:12-15."""
+    xh, _, _ = l2_normalize(x, dtype)
+    yh, _, _ = l2_normalize(y, dtype)
+    return 1 - xh @ yh.T
+
+
+def l2_distance(x, y, dtype=np.float64):
+    """nn/losses.py:18-24."""
+    x = np.asarray(x, dtype=dtype)
+    y = np.asarray(y, dtype=dtype)
+    x_sq = np.sum(x ** 2, axis=1).reshape(-1, 1)
+    y_sq = np.sum(y ** 2, axis=1).reshape(1, -1)
+    matrix = x_sq + y_sq - dtype(2.0) * (x @ y.T)
+    matrix = np.maximum(matrix, dtype(L2D_CLAMP)) / dtype(x.shape[1])
+    return np.sqrt(matrix)
+
+
+dist_metrics = {
+    'cosine': cosine_distance,
+    'l2': l2_distance,
+    'both': lambda x, y, dtype=np.float64: cosine_distance(x, y, dtype) + l2_distance(x, y, dtype),
+}
+
+
+def convert_rgb_to_yuv(x, dtype=np.float64):
+    """nn/strotss_utils.py:166-167."""
+    x = np.asarray(x, dtype=dtype)
+    return x[:, :3] @ RGB_TO_YUV.astype(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# distance matrices with their reverse pass w.r.t. the SECOND argument
+# --------------------------------------------------------------------------------------
+def _cosine_fwd(x, y, dtype):
+    xh, xss, xr = l2_normalize(x, dtype)
+    yh, yss, yr = l2_normalize(y, dtype)
+    C = 1 - xh @ yh.T
+    return C, (xh, np.asarray(y, dtype=dtype), yh, yss, yr)
+
+
+def _cosine_bwd_y(ctx, dC):
+    xh, y, yh, yss, yr = ctx
+    gyh = -(dC.T @ xh)
+    return _l2_normalize_bwd(y, yss, yr, gyh)
+
+
+def _l2_fwd(x, y, dtype):
+    x = np.asarray(x, dtype=dtype)
+    y = np.asarray(y, dtype=dtype)
+    x_sq = np.sum(x ** 2, axis=1).reshape(-1, 1)
+    y_sq = np.sum(y ** 2, axis=1).reshape(1, -1)
+    m = x_sq + y_sq - dtype(2.0) * (x @ y.T)
+    mc = np.maximum(m, dtype(L2D_CLAMP)) / dtype(x.shape[1])
+    out = np.sqrt(mc)
+    return out, (x, y, m, out)
+
+
+def _l2_bwd_y(ctx, dC):
+    x, y, m, out = ctx
+    D = x.shape[1]
+    dm = dC * (0.5 / out) / D
+    dm = np.where(m >= L2D_CLAMP, dm, 0.0)      # tf.maximum(matrix, 1e-6): grad to matrix iff >=
+    # m_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  ->  dm/dy_j = 2 y_j - 2 x_i
+    gy = 2.0 * y * np.sum(dm, axis=0).reshape(-1, 1) - 2.0 * (dm.T @ x)
+    return gy
+
+
+def _dist_fwd(x, y, distance, dtype):
+    if distance not in dist_metrics:
+        raise KeyError(distance)          # nn/losses.py:74: dict lookup raises KeyError
+    if distance == 'cosine':
+        C, ctx = _cosine_fwd(x, y, dtype)
+        return C, ('cosine', ctx)
+    if distance == 'l2':
+        C, ctx = _l2_fwd(x, y, dtype)
+        return C, ('l2', ctx)
+    C1, c1 = _cosine_fwd(x, y, dtype)
+    C2, c2 = _l2_fwd(x, y, dtype)
+    return C1 + C2, ('both', (c1, c2))
+
+
+def _dist_bwd_y(tagged, dC):
+    tag, ctx = tagged
+    if tag == 'cosine':
+        return _cosine_bwd_y(ctx, dC)
+    if tag == 'l2':
+        return _l2_bwd_y(ctx, dC)
+    return _cosine_bwd_y(ctx[0], dC) + _l2_bwd_y(ctx[1], dC)
+
+
+# --------------------------------------------------------------------------------------
+# the three losses (value, gradient w.r.t. the prediction operand, diagnostics)
+# --------------------------------------------------------------------------------------
+def relaxed_emd(x, y, distance: str = 'cosine', dtype=np.float64, want_grad: bool = False):
+    """nn/losses.py:69-80.  x = target (rows of C), y = prediction (columns of C).
+
+    Returns loss, or (loss, dL/dy, info) when want_grad.  info carries the observables the
+    CUDA path is compared on: R_X, R_Y, the argmins and the fp gap to each runner-up.
+    """
+    x = reshape_2d(x)
+    y = reshape_2d(y)
+    C, ctx = _dist_fwd(x, y, distance, dtype)
+    row_min = C.min(axis=1)
+    col_min = C.min(axis=0)
+    R_X = row_min.mean()
+    R_Y = col_min.mean()
+    loss = np.maximum(R_X, R_Y)
+    if not want_grad:
+        return loss
+    M, N = C.shape
+    dC = np.zeros_like(C)
+    if R_X >= R_Y:        # tf.maximum: ties go to the first argument
+        sel = (C == row_min[:, None])
+        dC = sel / sel.sum(axis=1, keepdims=True) / M
+    else:
+        sel = (C == col_min[None, :])
+        dC = sel / sel.sum(axis=0, keepdims=True) / N
+    gy = _dist_bwd_y(ctx, dC.astype(dtype))
+
+    def _gap(Cm):
+        if Cm.shape[1] < 2:
+            return np.full(Cm.shape[0], np.inf)
+        part = np.partition(Cm, 1, axis=1)
+        return part[:, 1] - part[:, 0]
+
+    info = dict(R_X=R_X, R_Y=R_Y, branch_x=bool(R_X >= R_Y),
+                row_argmin=C.argmin(axis=1), col_argmin=C.argmin(axis=0),
+                row_gap=_gap(C), col_gap=_gap(C.T), row_min=row_min, col_min=col_min)
+    return loss, gy, info
+
+
+def moment_matching(x, y, dtype=np.float64, want_grad: bool = False):
+    """nn/losses.py:39-52.  Gradient w.r.t. y (the prediction; run_strotss.py:35)."""
+    x = reshape_2d(x).astype(dtype)
+    y = reshape_2d(y).astype(dtype)
+    xm = x.mean(axis=0, keepdims=True)
+    ym = y.mean(axis=0, keepdims=True)
+    cx = x - xm
+    cy = y - ym
+    xv = cx.T @ cx / dtype(x.shape[0])
+    yv = cy.T @ cy / dtype(y.shape[0])
+    loss = mae(xv, yv) + mae(xm, ym)
+    if not want_grad:
+        return loss
+    N, D = y.shape
+    gV = np.sign(yv - xv) / (D * D)      # d mean|xv - yv| / d yv
+    gm = np.sign(ym - xm) / D
+    gcy = cy @ (gV + gV.T) / N
+    gy = gcy - gcy.mean(axis=0, keepdims=True) + gm / N
+    info = dict(l_cov=mae(xv, yv), l_mean=mae(xm, ym))
+    return loss, gy.astype(dtype), info
+
+
+def self_similarity(x, y, dtype=np.float64, want_grad: bool = False):
+    """nn/losses.py:55-66.  Gradient w.r.t. x (the prediction; run_strotss.py:24)."""
+    x = reshape_2d(x).astype(dtype)
+    y = reshape_2d(y).astype(dtype)
+    xh, xss, xr = l2_normalize(x, dtype)
+    yh, _, _ = l2_normalize(y, dtype)
+    Xd = 1 - xh @ xh.T
+    s = Xd.sum(axis=0)
+    sc = np.maximum(s, dtype(COLSUM_CLAMP))
+    Xn = Xd / sc
+    Yd = 1 - yh @ yh.T
+    t = np.maximum(Yd.sum(axis=0), dtype(COLSUM_CLAMP))
+    Yn = Yd / t
+    Ny = y.shape[0]
+    loss = mae(Xn, Yn) * dtype(Ny)
+    if not want_grad:
+        return loss
+    N = x.shape[0]
+    gXn = np.sign(Xn - Yn) * (Ny / (N * N))
+    gXd = gXn / sc
+    gsc = -(gXn * Xd).sum(axis=0) / sc ** 2
+    gs = np.where(s >= COLSUM_CLAMP, gsc, 0.0)
+    gXd = gXd + gs[None, :]
+    # Xd = 1 - a b^T with a = b = xh (x is normalised twice at nn/losses.py:13-14; same values)
+    gxh = -(gXd @ xh) - (gXd.T @ xh)
+    gx = _l2_normalize_bwd(x, xss, xr, gxh)
+    info = dict(s=s, t=t)
+    return loss, gx.astype(dtype), info
+
+
+# --------------------------------------------------------------------------------------
+# wrappers (run_strotss.py:21-40) and the total (run_strotss.py:92,140)
+# --------------------------------------------------------------------------------------
+def content_loss(target, prediction, dtype=np.float64, want_grad: bool = False):
+    """ContentLoss.__call__(target, prediction) -> self_similarity(prediction, target)."""
+    return self_similarity(prediction, target, dtype=dtype, want_grad=want_grad)
+
+
+def style_loss(target, prediction, alpha: float, dtype=np.float64, want_grad: bool = False):
+    """StyleLoss(target, alpha)(prediction): l_m + l_remd + l_palette / max(alpha, 1)."""
+    inv_alpha = 1.0 / max(alpha, 1.0)
+    if not want_grad:
+        l_m = moment_matching(target, prediction, dtype)
+        l_r = relaxed_emd(target, prediction, 'cosine', dtype)
+        l_p = relaxed_emd(convert_rgb_to_yuv(target, dtype), convert_rgb_to_yuv(prediction, dtype), 'both', dtype)
+        return l_m + l_r + inv_alpha * l_p
+    l_m, g_m, i_m = moment_matching(target, prediction, dtype, True)
+    l_r, g_r, i_r = relaxed_emd(target, prediction, 'cosine', dtype, True)
+    l_p, g_pyuv, i_p = relaxed_emd(convert_rgb_to_yuv(target, dtype), convert_rgb_to_yuv(prediction, dtype),
+                                   'both', dtype, True)
+    g = g_m + g_r
+    g[:, :3] += inv_alpha * (g_pyuv @ RGB_TO_YUV.astype(dtype).T)
+    info = dict(l_m=l_m, l_remd=l_r, l_palette=l_p, moment=i_m, remd=i_r, palette=i_p)
+    return l_m + l_r + inv_alpha * l_p, g, info
+
+
+def loss_denom(alpha: float) -> float:
+    """run_strotss.py:92."""
+    return 2.0 + alpha + 1.0 / max(alpha, 1.0)
+
+
+def total_loss(style, content, pred, alpha: float = 16.0, dtype=np.float64, want_grad: bool = False):
+    """run_strotss.py:138-140: (alpha * loss_c + loss_s) / loss_denom and d/d pred."""
+    den = loss_denom(alpha)
+    if not want_grad:
+        l_c = content_loss(content, pred, dtype)
+        l_s = style_loss(style, pred, alpha, dtype)
+        return (alpha * l_c + l_s) / den
+    l_c, g_c, i_c = content_loss(content, pred, dtype, True)
+    l_s, g_s, i_s = style_loss(style, pred, alpha, dtype, True)
+    loss = (alpha * l_c + l_s) / den
+    grad = (alpha * g_c + g_s) / den
+    info = dict(loss_c=l_c, loss_s=l_s, **i_s)
+    return loss, grad, info
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs (seed-0 convention of nn/rand.py:12-21)
+# --------------------------------------------------------------------------------------
+def synth_features(n: int, d: int, rng: np.random.Generator, sigma=None):
+    """Channels 0-2: U[0,1) 'RGB'.  Channels 3..: ReLU-like heavy-tailed 'VGG' activations."""
+    out = np.empty((n, d), dtype=np.float32)
+    k = min(3, d)
+    out[:, :k] = rng.random((n, k), dtype=np.float32)
+    if d > 3:
+        if sigma is None:
+            sigma = np.exp(rng.standard_normal(d - 3)).astype(np.float32)
+        z = rng.standard_normal((n, d - 3), dtype=np.float32)
+        out[:, 3:] = np.maximum(0.0, sigma[None, :] * (z + 0.3))
+    return out
+
+
+def synth_problem(N: int, M: int, D: int = 2179, eps: float = 1.0, seed: int = 0):
+    """style (M,D), content (N,D), pred (N,D) = max(0, content + eps*mean|content|*noise)."""
+    rng = np.random.default_rng(seed)
+    sigma = np.exp(rng.standard_normal(max(D - 3, 0))).astype(np.float32)
+    style = synth_features(M, D, rng, sigma)
+    content = synth_features(N, D, rng, sigma)
+    noise = rng.standard_normal((N, D), dtype=np.float32)
+    pred = np.maximum(0.0, content + np.float32(eps) * np.mean(np.abs(content)) * noise).astype(np.float32)
+    return style, content, pred

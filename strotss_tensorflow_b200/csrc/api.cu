@@ -1,0 +1,710 @@
+// C ABI of the B200-native STROTSS loss hot path (see include/strotss_b200.h).
+// Host side: workspace management, TMA tensor maps, launch sequencing.  No torch, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/strotss_b200.h"
+#include "gemm_core.cuh"
+#include "kernels.cuh"
+
+using namespace sb;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// cast fp32 -> bf16 with zero padding of the K dimension (debug GEMM only)
+__global__ void cast_pad_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst, int ldp) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(rows) * ldp;
+    if (idx >= total) return;
+    const int r = static_cast<int>(idx / ldp), c = static_cast<int>(idx % ldp);
+    dst[idx] = __float2bfloat16(c < cols ? src[static_cast<long long>(r) * cols + c] : 0.f);
+}
+
+__global__ void yuv_kernel(const float* __restrict__ x, long long ld, int n, float* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float* xr = x + static_cast<long long>(r) * ld;
+    const float R = xr[0], G = xr[1], B = xr[2];
+    out[3 * r + 0] = R * c_rgb2yuv[0] + G * c_rgb2yuv[3] + B * c_rgb2yuv[6];
+    out[3 * r + 1] = R * c_rgb2yuv[1] + G * c_rgb2yuv[4] + B * c_rgb2yuv[7];
+    out[3 * r + 2] = R * c_rgb2yuv[2] + G * c_rgb2yuv[5] + B * c_rgb2yuv[8];
+}
+
+__global__ void copy_scalars_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, float* __restrict__ dst) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[idx[threadIdx.x]];
+}
+
+}  // namespace
+
+// Prepared operands of one (n x D) fp32 feature matrix.
+struct Feat {
+    const float* x = nullptr; long long ld = 0; int n = 0; int np = 0;
+    float* inv = nullptr; float* mean = nullptr; float* sumhat = nullptr;
+    bf16* xh = nullptr; bf16* cen = nullptr; bf16* dlt = nullptr; bf16* xhT = nullptr; bf16* cenT = nullptr;
+    float* rec = nullptr;
+};
+
+struct strotss_ctx {
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    PFN_tmapEncodeTiled encode = nullptr;
+    std::map<std::string, std::pair<void*, size_t>> bufs;
+    size_t ws_bytes = 0;
+    long long launches = 0;
+    // style target
+    bool has_style = false;
+    int M = 0, D = 0, Dp = 0, Mp = 0;
+    Feat style;
+    float* Vx = nullptr;
+    // host pinned staging for scalar read-back
+    float* h_scalars = nullptr;
+
+    ~strotss_ctx() {
+        for (auto& kv : bufs) cudaFree(kv.second.first);
+        if (h_scalars) cudaFreeHost(h_scalars);
+    }
+};
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            h->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                                 \
+            return STROTSS_ERR_CUDA;                                                                     \
+        }                                                                                                \
+    } while (0)
+#define CKL()                                                                                            \
+    do {                                                                                                 \
+        ++h->launches;                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                             \
+        if (_e != cudaSuccess) {                                                                         \
+            h->err = std::string("kernel launch (") + __FILE__ + ":" + std::to_string(__LINE__) + "): " + \
+                     cudaGetErrorString(_e);                                                             \
+            return STROTSS_ERR_CUDA;                                                                     \
+        }                                                                                                \
+    } while (0)
+#define RET(expr)                                                                                        \
+    do { int _r = (expr); if (_r != 0) return _r; } while (0)
+
+namespace {
+
+// grow-only named device buffer
+template <class T>
+int ensure(strotss_ctx* h, const char* name, size_t count, T** out, bool zero_on_alloc = false) {
+    const size_t bytes = count * sizeof(T);
+    auto it = h->bufs.find(name);
+    if (it != h->bufs.end() && it->second.second >= bytes) { *out = static_cast<T*>(it->second.first); return 0; }
+    if (it != h->bufs.end()) { CK(cudaDeviceSynchronize()); cudaFree(it->second.first); h->ws_bytes -= it->second.second; h->bufs.erase(it); }
+    void* p = nullptr;
+    const size_t alloc = (bytes + 255) / 256 * 256;
+    CK(cudaMalloc(&p, alloc));
+    if (zero_on_alloc) CK(cudaMemset(p, 0, alloc));
+    h->bufs[name] = std::make_pair(p, alloc);
+    h->ws_bytes += alloc;
+    *out = static_cast<T*>(p);
+    return 0;
+}
+
+int make_tmap(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int rows, int kcols, long long ld_elems, int box_rows) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kcols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * sizeof(bf16)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        h->err = "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)) + " (rows=" +
+                 std::to_string(rows) + " k=" + std::to_string(kcols) + " ld=" + std::to_string(ld_elems) + ")";
+        return STROTSS_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <int BN, int NACC, int STAGES, class Epi>
+int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
+    using Cfg = TileCfg<BN, NACC>;
+    constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
+    auto kern = gemm_kernel<BN, NACC, STAGES, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    if (tiles <= 0) return 0;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    kern<<<grid, kGemmThreads, smem, st>>>(p);
+    CKL();
+    return 0;
+}
+
+// ---- operand preparation --------------------------------------------------------------
+struct PrepWant { bool mean, sumhat, xh, cen, dlt, xhT, cenT, rec; };
+
+int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long ld, int n, int D, int Dp,
+                  const PrepWant& w, const Feat* other /* for dlt */, int rec_convert, cudaStream_t st) {
+    f.x = x; f.ld = ld; f.n = n; f.np = round_up(n, 64);
+    const std::string t(tag);
+    const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+    float *part_raw = nullptr, *part_hat = nullptr;
+    RET(ensure(h, (t + ".inv").c_str(), n, &f.inv));
+    if (w.mean) { RET(ensure(h, (t + ".mean").c_str(), D, &f.mean)); RET(ensure(h, (t + ".praw").c_str(), (size_t)nblk * D, &part_raw)); }
+    if (w.sumhat) { RET(ensure(h, (t + ".sumhat").c_str(), D, &f.sumhat)); RET(ensure(h, (t + ".phat").c_str(), (size_t)nblk * D, &part_hat)); }
+    row_stats_kernel<<<nblk, 256, 0, st>>>(x, ld, n, D, f.inv, part_raw, part_hat);
+    CKL();
+    if (w.mean) { colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(part_raw, nblk, D, 1.f / n, f.mean); CKL(); }
+    if (w.sumhat) { colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(part_hat, nblk, D, 1.f, f.sumhat); CKL(); }
+    EmitArgs a{};
+    a.x = x; a.ldx = ld; a.n = n; a.D = D; a.Dp = Dp; a.np = f.np; a.inv = f.inv; a.mean = f.mean;
+    if (w.xh) { RET(ensure(h, (t + ".xh").c_str(), (size_t)n * Dp, &f.xh)); a.xh = f.xh; }
+    if (w.cen) { RET(ensure(h, (t + ".cen").c_str(), (size_t)n * Dp, &f.cen)); a.cen = f.cen; }
+    if (w.dlt) {
+        RET(ensure(h, (t + ".dlt").c_str(), (size_t)n * Dp, &f.dlt)); a.dlt = f.dlt;
+        a.y = other->x; a.ldy = other->ld; a.inv_y = other->inv;
+    }
+    if (w.xhT) { RET(ensure(h, (t + ".xhT").c_str(), (size_t)D * f.np, &f.xhT)); a.xhT = f.xhT; }
+    if (w.cenT) { RET(ensure(h, (t + ".cenT").c_str(), (size_t)D * f.np, &f.cenT)); a.cenT = f.cenT; }
+    if (w.xh || w.cen || w.dlt || w.xhT || w.cenT) {
+        dim3 grid(Dp / 64, f.np / 64);
+        emit_operands_kernel<<<grid, 256, 0, st>>>(a);
+        CKL();
+    }
+    if (w.rec) {
+        RET(ensure(h, (t + ".rec").c_str(), (size_t)n * 8, &f.rec));
+        pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, rec_convert, f.rec);
+        CKL();
+    }
+    return 0;
+}
+
+// ---- covariance of a prepared feature set:  V = cenT . cenT^T / n  ---------------------
+int cov_store(strotss_ctx* h, const Feat& f, int D, int Dp, float* V, cudaStream_t st) {
+    GemmParams<EpiStoreT<256>> p{};
+    RET(make_tmap(h, &p.tmA[0], f.cenT, D, f.np, f.np, BM));
+    RET(make_tmap(h, &p.tmB[0], f.cenT, D, f.np, f.np, 256));
+    p.nseg = 1; p.seg_kblocks[0] = f.np / BK; p.seg_acc[0] = 0;
+    p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
+    p.epi.C = V; p.epi.ldc = Dp; p.epi.rows = D; p.epi.cols = D; p.epi.alpha = 1.f / f.n; p.epi.row_off = 0;
+    return launch_gemm<256, 1, 4>(h, p, st);
+}
+
+// ---- the three loss terms, each leaving its gradient contribution in workspace buffers --
+struct RemdOut { unsigned long long* rowbest; unsigned long long* colbest; float* g; long long ldg; };
+
+int remd_cosine(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int N, int D, int Dp, float* scalars,
+                int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, RemdOut& out,
+                int32_t* row_arg, int32_t* col_arg, cudaStream_t st) {
+    RET(ensure(h, "remd.rowbest", (size_t)M, &out.rowbest));
+    RET(ensure(h, "remd.colbest", (size_t)N, &out.colbest));
+    CK(cudaMemsetAsync(out.rowbest, 0, sizeof(unsigned long long) * M, st));
+    CK(cudaMemsetAsync(out.colbest, 0, sizeof(unsigned long long) * N, st));
+    GemmParams<EpiRemd<256>> p{};
+    RET(make_tmap(h, &p.tmA[0], target.xh, M, Dp, Dp, BM));
+    RET(make_tmap(h, &p.tmB[0], pred.xh, N, Dp, Dp, 256));
+    p.nseg = 1; p.seg_kblocks[0] = Dp / BK; p.seg_acc[0] = 0;
+    p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + 255) / 256;
+    p.epi.rowbest = out.rowbest; p.epi.colbest = out.colbest; p.epi.M = M; p.epi.N = N;
+    RET((launch_gemm<256, 1, 4>(h, p, st)));
+    remd_finish_kernel<<<1, 1024, 0, st>>>(out.rowbest, M, out.colbest, N, 1.f, scalars, slot_loss, slot_rx, slot_ry,
+                                           slot_branch, row_arg, col_arg);
+    CKL();
+    out.g = nullptr; out.ldg = 0;
+    if (want_grad) {
+        RET(ensure(h, "remd.g", (size_t)N * D, &out.g));
+        out.ldg = D;
+        CK(cudaMemsetAsync(out.g, 0, sizeof(float) * (size_t)N * D, st));
+        const int rows = M > N ? M : N;
+        remd_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(out.rowbest, M, out.colbest, N, target.x, target.ld, target.inv, D,
+                                                             scalars, slot_branch, out.g, out.ldg);
+        CKL();
+    }
+    return 0;
+}
+
+int remd_small(strotss_ctx* h, const float* arec, int M, const float* brec, int N, int mode, int convert, float* scalars,
+               int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, float** gpal,
+               int32_t* row_arg, int32_t* col_arg, cudaStream_t st) {
+    unsigned long long *rowbest, *colbest;
+    RET(ensure(h, "pal.rowbest", (size_t)M, &rowbest));
+    RET(ensure(h, "pal.colbest", (size_t)N, &colbest));
+    CK(cudaMemsetAsync(rowbest, 0, sizeof(unsigned long long) * M, st));
+    CK(cudaMemsetAsync(colbest, 0, sizeof(unsigned long long) * N, st));
+    auto launch = [&](const float* q, int nq, const float* k, int nk, int swap, unsigned long long* best) -> int {
+        const int qblocks = (nq + 127) / 128;
+        int ks = (2 * h->num_sms + qblocks - 1) / qblocks;        // aim for >= 2 waves of blocks
+        const int maxks = (nk + 255) / 256;
+        if (ks > maxks) ks = maxks;
+        if (ks < 1) ks = 1;
+        int kchunk = round_up((nk + ks - 1) / ks, 256);
+        ks = (nk + kchunk - 1) / kchunk;
+        dim3 grid(qblocks, ks);
+        pal_min_kernel<<<grid, 128, 0, st>>>(q, nq, k, nk, kchunk, mode, swap, best);
+        CKL();
+        return 0;
+    };
+    RET(launch(arec, M, brec, N, 0, rowbest));
+    RET(launch(brec, N, arec, M, 1, colbest));
+    remd_finish_kernel<<<1, 1024, 0, st>>>(rowbest, M, colbest, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
+                                           row_arg, col_arg);
+    CKL();
+    if (want_grad) {
+        RET(ensure(h, "pal.g", (size_t)N * 4, gpal));
+        CK(cudaMemsetAsync(*gpal, 0, sizeof(float) * (size_t)N * 4, st));
+        const int rows = M > N ? M : N;
+        pal_backward_kernel<<<(rows + 127) / 128, 128, 0, st>>>(rowbest, M, colbest, N, arec, brec, mode, convert, scalars,
+                                                                slot_branch, *gpal);
+        CKL();
+    }
+    return 0;
+}
+
+struct MomOut { float* Q; long long ldq; float q_scale; float* gmu; };
+
+// target mean / covariance given explicitly (mu_x, Vx with row stride Dp)
+int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred, int N, int D, int Dp, float* scalars,
+            bool want_grad, MomOut& out, cudaStream_t st) {
+    bf16* Sg; float* part;
+    RET(ensure(h, "mom.Sg", (size_t)Dp * Dp, &Sg, /*zero_on_alloc=*/true));
+    GemmParams<EpiCovFwd<256>> p{};
+    RET(make_tmap(h, &p.tmA[0], pred.cenT, D, pred.np, pred.np, BM));
+    RET(make_tmap(h, &p.tmB[0], pred.cenT, D, pred.np, pred.np, 256));
+    p.nseg = 1; p.seg_kblocks[0] = pred.np / BK; p.seg_acc[0] = 0;
+    p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
+    const int npart = p.tiles_m * p.tiles_n * 4;
+    RET(ensure(h, "mom.part", (size_t)npart, &part));
+    p.epi.Vx = Vx; p.epi.ldv = Dp; p.epi.Sg = Sg; p.epi.lds = Dp; p.epi.part = part; p.epi.inv_n = 1.f / N; p.epi.D = D;
+    p.epi.tiles_n = p.tiles_n;
+    RET((launch_gemm<256, 1, 4>(h, p, st)));
+    RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
+    moment_finish_kernel<<<1, 1024, 0, st>>>(pred.mean, mu_x, D, part, npart, out.gmu, scalars);
+    CKL();
+    out.Q = nullptr; out.ldq = 0; out.q_scale = 0.f;
+    if (want_grad) {
+        // Q = cen . (G + G^T) / N with G = sign(V_y - V_x)/D^2 symmetric  ->  q_scale * (cen . Sg^T)
+        RET(ensure(h, "mom.Q", (size_t)N * Dp, &out.Q));
+        out.ldq = Dp; out.q_scale = 2.f / (static_cast<float>(N) * static_cast<float>(D) * static_cast<float>(D));
+        GemmParams<EpiStoreT<256>> q{};
+        RET(make_tmap(h, &q.tmA[0], pred.cen, N, Dp, Dp, BM));
+        RET(make_tmap(h, &q.tmB[0], Sg, D, Dp, Dp, 256));
+        q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
+        q.tiles_m = (N + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
+        q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = N; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = 0;
+        RET((launch_gemm<256, 1, 4>(h, q, st)));
+    }
+    return 0;
+}
+
+struct SsOut { float* ss2; long long ld; float* v; float* coef; };
+
+// x = prediction (gradient side), y = content.  Needs x.{xh,xhT,dlt,sumhat}, y.{xh,sumhat}.
+int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp, float* loss_out, bool want_grad, SsOut& out,
+             cudaStream_t st) {
+    float *u, *w, *sclamp, *loss_part, *r_part, *rowloss;
+    RET(ensure(h, "ss.u", (size_t)N, &u));
+    RET(ensure(h, "ss.w", (size_t)N, &w));
+    RET(ensure(h, "ss.sclamp", (size_t)N, &sclamp));
+    ss_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
+    CKL();
+    const int tiles_n = (N + 127) / 128;
+    RET(ensure(h, "ss.loss_part", (size_t)tiles_n * N, &loss_part));
+    RET(ensure(h, "ss.r_part", (size_t)tiles_n * N, &r_part));
+    RET(ensure(h, "ss.rowloss", (size_t)N, &rowloss));
+    RET(ensure(h, "ss.coef", (size_t)N, &out.coef));
+    const int np = x.np;
+    // row panel of P (bf16), sized to stay L2-resident between its producer and consumer GEMMs
+    int panel = 2048;
+    if (panel > round_up(N, BM)) panel = round_up(N, BM);
+    bf16* P = nullptr;
+    out.ss2 = nullptr; out.ld = 0; out.v = nullptr;
+    if (want_grad) {
+        RET(ensure(h, "ss.P", (size_t)panel * np, &P));
+        RET(ensure(h, "ss.ss2", (size_t)N * Dp, &out.ss2));
+        out.ld = Dp;
+    }
+    for (int r0 = 0; r0 < N; r0 += panel) {
+        const int rows = (N - r0 < panel) ? (N - r0) : panel;
+        GemmParams<EpiSS1> p{};
+        // segment 0: delta_I . x^_J ; segment 1: y^_I . delta_J  (both into acc 0) ; segment 2: y^_I . y^_J (acc 1)
+        RET(make_tmap(h, &p.tmA[0], x.dlt, N, Dp, Dp, BM));
+        RET(make_tmap(h, &p.tmB[0], x.xh, N, Dp, Dp, 128));
+        RET(make_tmap(h, &p.tmA[1], y.xh, N, Dp, Dp, BM));
+        RET(make_tmap(h, &p.tmB[1], x.dlt, N, Dp, Dp, 128));
+        RET(make_tmap(h, &p.tmA[2], y.xh, N, Dp, Dp, BM));
+        RET(make_tmap(h, &p.tmB[2], y.xh, N, Dp, Dp, 128));
+        p.nseg = 3;
+        for (int s = 0; s < 3; ++s) p.seg_kblocks[s] = Dp / BK;
+        p.seg_acc[0] = 0; p.seg_acc[1] = 0; p.seg_acc[2] = 1;
+        p.tiles_m = (rows + BM - 1) / BM; p.tiles_n = tiles_n;
+        p.a_row0 = r0; p.b_row0 = 0;
+        p.epi.u = u; p.epi.w = w; p.epi.P = P; p.epi.ldp = np; p.epi.panel_row0 = r0;
+        p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.write_p = want_grad ? 1 : 0;
+        RET((launch_gemm<128, 2, 6>(h, p, st)));
+        if (want_grad) {
+            GemmParams<EpiStoreT<256>> q{};
+            RET(make_tmap(h, &q.tmA[0], P, rows, np, np, BM));
+            RET(make_tmap(h, &q.tmB[0], x.xhT, D, np, np, 256));
+            q.nseg = 1; q.seg_kblocks[0] = np / BK; q.seg_acc[0] = 0;
+            q.tiles_m = (rows + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
+            q.a_row0 = 0; q.b_row0 = 0;
+            q.epi.C = out.ss2 + static_cast<long long>(r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
+            q.epi.alpha = 1.f; q.epi.row_off = 0;
+            RET((launch_gemm<256, 1, 4>(h, q, st)));
+        }
+    }
+    ss_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(loss_part, r_part, tiles_n, N, u, sclamp, out.coef, rowloss);
+    CKL();
+    reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss, N, 1.f / N, loss_out);
+    CKL();
+    if (want_grad) {
+        const int nblk = (N + kRowsPerBlock - 1) / kRowsPerBlock;
+        float* vpart;
+        RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
+        RET(ensure(h, "ss.v", (size_t)D, &out.v));
+        weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x, x.ld, N, D, x.inv, out.coef, vpart);
+        CKL();
+        colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(vpart, nblk, D, 1.f, out.v);
+        CKL();
+    }
+    return 0;
+}
+
+int finalize(strotss_ctx* h, const FinalizeArgs& a, cudaStream_t st) {
+    finalize_grad_kernel<<<a.N, 256, sizeof(float) * a.D, st>>>(a);
+    CKL();
+    return 0;
+}
+
+int check_handle(strotss_handle h) { return h ? 0 : STROTSS_ERR_ARG; }
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+const char* strotss_version(void) { return "strotss_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+
+int strotss_create(int device, strotss_handle* out) {
+    if (!out) return STROTSS_ERR_ARG;
+    *out = nullptr;
+    strotss_ctx* h = new strotss_ctx();
+    h->device = device;
+    *out = h;     // returned even on failure so the caller can read the error text
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { h->err = "invalid device index " + std::to_string(device); return STROTSS_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        h->err = std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                 "; this library contains sm_100a code only (no fallback)";
+        return STROTSS_ERR_CUDA;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled not available"; return STROTSS_ERR_CUDA; }
+    h->encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+    CK(cudaMallocHost(&h->h_scalars, sizeof(float) * STROTSS_NUM_SCALARS));
+    return 0;
+}
+
+void strotss_destroy(strotss_handle h) { delete h; }
+
+const char* strotss_last_error(strotss_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+size_t strotss_workspace_bytes(strotss_handle h) { return h ? h->ws_bytes : 0; }
+
+long long strotss_launch_count(strotss_handle h) { return h ? h->launches : 0; }
+
+int strotss_set_style_target(strotss_handle h, const float* style, int M, int D, long long ld, void* stream) {
+    RET(check_handle(h));
+    if (!style || M <= 0 || D < 3 || ld < D) { h->err = "set_style_target: bad argument"; return STROTSS_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    h->has_style = false;
+    h->M = M; h->D = D; h->Dp = round_up(D, BK); h->Mp = round_up(M, 64);
+    // private copy: later evaluations must not depend on the caller keeping `style` alive
+    float* copy;
+    RET(ensure(h, "style.x", (size_t)M * D, &copy));
+    CK(cudaMemcpy2DAsync(copy, sizeof(float) * D, style, sizeof(float) * ld, sizeof(float) * D, M, cudaMemcpyDeviceToDevice, st));
+    PrepWant w{}; w.mean = true; w.xh = true; w.cenT = true; w.rec = true;
+    RET(prep_features(h, "style", h->style, copy, D, M, D, h->Dp, w, nullptr, 1, st));
+    RET(ensure(h, "style.Vx", (size_t)h->Dp * h->Dp, &h->Vx, true));
+    RET(cov_store(h, h->style, D, h->Dp, h->Vx, st));
+    h->has_style = true;
+    return 0;
+}
+
+static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,
+                     int N, float alpha, float* scalars, float* grad, long long ld_grad, int32_t* row_arg, int32_t* col_arg,
+                     bool with_content, cudaStream_t st) {
+    const int D = h->D, Dp = h->Dp, M = h->M;
+    const bool want_grad = grad != nullptr;
+    const float inv_alpha = 1.f / (alpha > 1.f ? alpha : 1.f);
+    const float denom = with_content ? (2.f + alpha + inv_alpha) : 1.f;
+    CK(cudaMemsetAsync(scalars, 0, sizeof(float) * STROTSS_NUM_SCALARS, st));
+    Feat fp, fc;
+    if (with_content) {
+        PrepWant wc{}; wc.sumhat = true; wc.xh = true;
+        RET(prep_features(h, "content", fc, content, ld_content, N, D, Dp, wc, nullptr, 0, st));
+    }
+    PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true; wp.rec = true;
+    wp.cen = want_grad; wp.sumhat = with_content; wp.dlt = with_content; wp.xhT = with_content && want_grad;
+    RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, with_content ? &fc : nullptr, 1, st));
+
+    RemdOut ro{}; MomOut mo{}; SsOut so{}; float* gpal = nullptr;
+    RET(remd_cosine(h, h->style, M, fp, N, D, Dp, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad, ro, row_arg,
+                    col_arg, st));
+    RET(remd_small(h, h->style.rec, M, fp.rec, N, STROTSS_DIST_BOTH, 1, scalars, S_LPAL, S_PAL_RX, S_PAL_RY, S_PAL_BRANCH,
+                   want_grad, &gpal, nullptr, nullptr, st));
+    RET(moments(h, h->style.mean, h->Vx, fp, N, D, Dp, scalars, want_grad, mo, st));
+    if (with_content) RET(self_sim(h, fp, fc, N, D, Dp, scalars + S_LOSS_C, want_grad, so, st));
+    combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom);
+    CKL();
+    if (want_grad) {
+        FinalizeArgs a{};
+        a.x = pred; a.ldx = ld_pred; a.inv = fp.inv; a.N = N; a.D = D;
+        if (with_content) { a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = so.v; a.coef = so.coef; a.sumhat = fp.sumhat; a.w_ss = alpha / denom; }
+        a.gremd = ro.g; a.ld_gremd = ro.ldg; a.w_remd = 1.f / denom;
+        a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = 1.f / denom;
+        a.gpal = gpal; a.w_pal = inv_alpha / denom;
+        a.grad = grad; a.ldg = ld_grad;
+        RET(finalize(h, a, st));
+    }
+    return 0;
+}
+
+int strotss_eval(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content, int N,
+                 float alpha, float* scalars, float* grad_pred, long long ld_grad, int32_t* remd_row_argmin,
+                 int32_t* remd_col_argmin, void* stream) {
+    RET(check_handle(h));
+    if (!h->has_style) { h->err = "strotss_eval: call strotss_set_style_target first"; return STROTSS_ERR_STATE; }
+    if (!pred || !content || !scalars || N <= 0 || ld_pred < h->D || ld_content < h->D || (grad_pred && ld_grad < h->D)) {
+        h->err = "strotss_eval: bad argument"; return STROTSS_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->device));
+    return eval_impl(h, pred, ld_pred, content, ld_content, N, alpha, scalars, grad_pred, ld_grad, remd_row_argmin,
+                     remd_col_argmin, true, static_cast<cudaStream_t>(stream));
+}
+
+int strotss_style_loss(strotss_handle h, const float* pred, long long ld_pred, int N, float alpha, float* scalars,
+                       float* grad_pred, long long ld_grad, void* stream) {
+    RET(check_handle(h));
+    if (!h->has_style) { h->err = "strotss_style_loss: call strotss_set_style_target first"; return STROTSS_ERR_STATE; }
+    if (!pred || !scalars || N <= 0 || ld_pred < h->D || (grad_pred && ld_grad < h->D)) {
+        h->err = "strotss_style_loss: bad argument"; return STROTSS_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->device));
+    return eval_impl(h, pred, ld_pred, nullptr, 0, N, alpha, scalars, grad_pred, ld_grad, nullptr, nullptr, false,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int strotss_eval_host(strotss_handle h, const float* pred_host, const float* content_host, int N, float alpha,
+                      float* scalars_host, float* grad_host, void* stream) {
+    RET(check_handle(h));
+    if (!h->has_style) { h->err = "strotss_eval_host: call strotss_set_style_target first"; return STROTSS_ERR_STATE; }
+    if (!pred_host || !content_host || !scalars_host || N <= 0) { h->err = "strotss_eval_host: bad argument"; return STROTSS_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const size_t elems = (size_t)N * h->D;
+    float *dp, *dc, *dg = nullptr, *ds;
+    RET(ensure(h, "host.pred", elems, &dp));
+    RET(ensure(h, "host.content", elems, &dc));
+    RET(ensure(h, "host.scalars", (size_t)STROTSS_NUM_SCALARS, &ds));
+    if (grad_host) RET(ensure(h, "host.grad", elems, &dg));
+    CK(cudaMemcpyAsync(dp, pred_host, elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dc, content_host, elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    RET(eval_impl(h, dp, h->D, dc, h->D, N, alpha, ds, dg, h->D, nullptr, nullptr, true, st));
+    CK(cudaMemcpyAsync(h->h_scalars, ds, sizeof(float) * STROTSS_NUM_SCALARS, cudaMemcpyDeviceToHost, st));
+    if (grad_host) CK(cudaMemcpyAsync(grad_host, dg, elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(scalars_host, h->h_scalars, sizeof(float) * STROTSS_NUM_SCALARS);
+    return 0;
+}
+
+int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, const float* y, long long ldy, int N, int D,
+                        int distance, float* loss, float* grad_y, long long ld_grad, int32_t* row_argmin, int32_t* col_argmin,
+                        void* stream) {
+    RET(check_handle(h));
+    if (distance < 0 || distance > 2) { h->err = "relaxed_emd: unknown distance"; return STROTSS_ERR_DISTANCE; }
+    if (!x || !y || !loss || M <= 0 || N <= 0 || D <= 0 || ldx < D || ldy < D || (grad_y && ld_grad < D)) {
+        h->err = "relaxed_emd: bad argument"; return STROTSS_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    float* sc;
+    RET(ensure(h, "fn.scalars", (size_t)S_COUNT, &sc));
+    CK(cudaMemsetAsync(sc, 0, sizeof(float) * S_COUNT, st));
+    const bool want_grad = grad_y != nullptr;
+    if (D == 3) {
+        Feat fx, fy;
+        PrepWant w{}; w.rec = true;
+        RET(prep_features(h, "fn.x", fx, x, ldx, M, D, round_up(D, BK), w, nullptr, 0, st));
+        RET(prep_features(h, "fn.y", fy, y, ldy, N, D, round_up(D, BK), w, nullptr, 0, st));
+        float* gpal = nullptr;
+        RET(remd_small(h, fx.rec, M, fy.rec, N, distance, 0, sc, S_LPAL, S_PAL_RX, S_PAL_RY, S_PAL_BRANCH, want_grad, &gpal,
+                       row_argmin, col_argmin, st));
+        if (want_grad) {
+            CK(cudaMemcpy2DAsync(grad_y, sizeof(float) * ld_grad, gpal, sizeof(float) * 4, sizeof(float) * 3, N,
+                                 cudaMemcpyDeviceToDevice, st));
+        }
+        int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
+        const int hidx[4] = {S_LPAL, S_PAL_RX, S_PAL_RY, S_PAL_BRANCH};
+        CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
+        copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, 4, loss);
+        CKL();
+        return 0;
+    }
+    if (distance != STROTSS_DIST_COSINE) {
+        h->err = "relaxed_emd: 'l2'/'both' are implemented for D == 3 only (the palette call, run_strotss.py:39)";
+        return STROTSS_ERR_UNSUPPORTED;
+    }
+    const int Dp = round_up(D, BK);
+    Feat fx, fy;
+    PrepWant w{}; w.xh = true;
+    RET(prep_features(h, "fn.x", fx, x, ldx, M, D, Dp, w, nullptr, 0, st));
+    RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, w, nullptr, 0, st));
+    RemdOut ro{};
+    RET(remd_cosine(h, fx, M, fy, N, D, Dp, sc, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad, ro, row_argmin,
+                    col_argmin, st));
+    if (want_grad) {
+        FinalizeArgs a{};
+        a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D;
+        a.gremd = ro.g; a.ld_gremd = ro.ldg; a.w_remd = 1.f;
+        a.grad = grad_y; a.ldg = ld_grad;
+        RET(finalize(h, a, st));
+    }
+    int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
+    const int hidx[4] = {S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH};
+    CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
+    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, 4, loss);
+    CKL();
+    return 0;
+}
+
+int strotss_moment_matching(strotss_handle h, const float* x, long long ldx, int M, const float* y, long long ldy, int N, int D,
+                            float* loss, float* grad_y, long long ld_grad, void* stream) {
+    RET(check_handle(h));
+    if (!x || !y || !loss || M <= 0 || N <= 0 || D <= 0 || ldx < D || ldy < D || (grad_y && ld_grad < D)) {
+        h->err = "moment_matching: bad argument"; return STROTSS_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int Dp = round_up(D, BK);
+    const bool want_grad = grad_y != nullptr;
+    float* sc;
+    RET(ensure(h, "fn.scalars", (size_t)S_COUNT, &sc));
+    CK(cudaMemsetAsync(sc, 0, sizeof(float) * S_COUNT, st));
+    Feat fx, fy;
+    PrepWant wx{}; wx.mean = true; wx.cenT = true;
+    RET(prep_features(h, "fn.x", fx, x, ldx, M, D, Dp, wx, nullptr, 0, st));
+    float* Vx;
+    RET(ensure(h, "fn.Vx", (size_t)Dp * Dp, &Vx, true));
+    RET(cov_store(h, fx, D, Dp, Vx, st));
+    PrepWant wy{}; wy.mean = true; wy.cenT = true; wy.cen = want_grad;
+    RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, wy, nullptr, 0, st));
+    MomOut mo{};
+    RET(moments(h, fx.mean, Vx, fy, N, D, Dp, sc, want_grad, mo, st));
+    if (want_grad) {
+        FinalizeArgs a{};
+        a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D;
+        a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = 1.f;
+        a.grad = grad_y; a.ldg = ld_grad;
+        RET(finalize(h, a, st));
+    }
+    int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
+    const int hidx[4] = {S_LM, S_LCOV, S_LMEAN, S_LMEAN};
+    CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
+    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, 3, loss);
+    CKL();
+    return 0;
+}
+
+int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, const float* y, long long ldy, int N, int D,
+                            float* loss, float* grad_x, long long ld_grad, void* stream) {
+    RET(check_handle(h));
+    if (!x || !y || !loss || N <= 0 || D <= 0 || ldx < D || ldy < D || (grad_x && ld_grad < D)) {
+        h->err = "self_similarity: bad argument"; return STROTSS_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int Dp = round_up(D, BK);
+    const bool want_grad = grad_x != nullptr;
+    Feat fx, fy;
+    PrepWant wy{}; wy.sumhat = true; wy.xh = true;
+    RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, wy, nullptr, 0, st));
+    PrepWant wx{}; wx.sumhat = true; wx.xh = true; wx.dlt = true; wx.xhT = want_grad;
+    RET(prep_features(h, "fn.x", fx, x, ldx, N, D, Dp, wx, &fy, 0, st));
+    SsOut so{};
+    RET(self_sim(h, fx, fy, N, D, Dp, loss, want_grad, so, st));
+    if (want_grad) {
+        FinalizeArgs a{};
+        a.x = x; a.ldx = ldx; a.inv = fx.inv; a.N = N; a.D = D;
+        a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = so.v; a.coef = so.coef; a.sumhat = fx.sumhat; a.w_ss = 1.f;
+        a.grad = grad_x; a.ldg = ld_grad;
+        RET(finalize(h, a, st));
+    }
+    return 0;
+}
+
+int strotss_convert_rgb_to_yuv(strotss_handle h, const float* x, long long ldx, int n, float* out, void* stream) {
+    RET(check_handle(h));
+    if (!x || !out || n <= 0 || ldx < 3) { h->err = "convert_rgb_to_yuv: bad argument"; return STROTSS_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    yuv_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, n, out);
+    CKL();
+    return 0;
+}
+
+int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha, float* C, int tile_n,
+                       void* stream) {
+    RET(check_handle(h));
+    if (!A || !B || !C || m <= 0 || n <= 0 || k <= 0 || (tile_n != 128 && tile_n != 256)) {
+        h->err = "debug_gemm: bad argument"; return STROTSS_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int kp = round_up(k, BK);
+    bf16 *a16, *b16;
+    RET(ensure(h, "dbg.a", (size_t)m * kp, &a16));
+    RET(ensure(h, "dbg.b", (size_t)n * kp, &b16));
+    cast_pad_kernel<<<(unsigned)(((long long)m * kp + 255) / 256), 256, 0, st>>>(A, m, k, a16, kp); CKL();
+    cast_pad_kernel<<<(unsigned)(((long long)n * kp + 255) / 256), 256, 0, st>>>(B, n, k, b16, kp); CKL();
+    if (tile_n == 256) {
+        GemmParams<EpiStoreT<256>> p{};
+        RET(make_tmap(h, &p.tmA[0], a16, m, kp, kp, BM));
+        RET(make_tmap(h, &p.tmB[0], b16, n, kp, kp, 256));
+        p.nseg = 1; p.seg_kblocks[0] = kp / BK; p.seg_acc[0] = 0;
+        p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + 255) / 256;
+        p.epi.C = C; p.epi.ldc = n; p.epi.rows = m; p.epi.cols = n; p.epi.alpha = alpha; p.epi.row_off = 0;
+        return launch_gemm<256, 1, 4>(h, p, st);
+    }
+    GemmParams<EpiStoreT<128>> p{};
+    RET(make_tmap(h, &p.tmA[0], a16, m, kp, kp, BM));
+    RET(make_tmap(h, &p.tmB[0], b16, n, kp, kp, 128));
+    p.nseg = 1; p.seg_kblocks[0] = kp / BK; p.seg_acc[0] = 0;
+    p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + 127) / 128;
+    p.epi.C = C; p.epi.ldc = n; p.epi.rows = m; p.epi.cols = n; p.epi.alpha = alpha; p.epi.row_off = 0;
+    return launch_gemm<128, 1, 6>(h, p, st);
+}
+
+}  // extern "C"

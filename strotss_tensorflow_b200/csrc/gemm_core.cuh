@@ -1,0 +1,409 @@
+// Persistent, warp-specialised tcgen05 GEMM core for sm_100a:  acc[a] (+)= A_seg * B_seg^T
+//
+//   * operands are bf16, K-major (row-major with K contiguous), staged by TMA with 128-byte swizzle
+//   * a launch is a list of up to three "segments"; each segment is one (A, B) tensor-map pair with
+//     its own K extent and the index of the TMEM accumulator it adds into (that is how the
+//     self-similarity kernel forms  delta.x^T + y.delta^T  in one accumulator and  y.y^T  in a second)
+//   * tile = 128 (rows of A) x BN (rows of B), fp32 accumulators in TMEM, double-buffered when
+//     2 * BN * NACC <= 512 columns so the epilogue of tile t overlaps the MMAs of tile t+1
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//     warps 4..7 = epilogue (warp q owns TMEM lanes 32q..32q+31, one accumulator row per thread)
+//   * the epilogue is a policy class; no tile of the product is written to HBM unless the policy
+//     stores it.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxSeg = 3;
+constexpr int kSmemBudget = 232448 - 1024;   // 227 KB minus alignment slack
+
+template <int BN, int NACC>
+struct TileCfg {
+    static constexpr int ACC_COLS = BN * NACC;
+    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+};
+
+template <class Epi>
+struct GemmParams {
+    CUtensorMap tmA[kMaxSeg];
+    CUtensorMap tmB[kMaxSeg];
+    int nseg;
+    int seg_kblocks[kMaxSeg];
+    int seg_acc[kMaxSeg];
+    int tiles_m, tiles_n;
+    int a_row0, b_row0;          // element row where tile (0,0) starts in A / B
+    typename Epi::Params epi;
+};
+
+struct TileInfo {
+    int tm, tn;                  // tile indices
+    int row0, col0;              // a_row0 + tm*BM, b_row0 + tn*BN  (global element coordinates)
+    int q, lane;                 // epilogue warp (TMEM lane quadrant) and lane
+    uint32_t taddr;              // TMEM address of accumulator 0, this warp's lane quadrant
+    int tile_seq;                // running count of tiles processed by this CTA
+};
+
+__device__ __forceinline__ void epi_bar_sync() {
+    asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+}
+
+template <int BN, int NACC, int STAGES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
+    using Cfg = TileCfg<BN, NACC>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::SMEM_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + Cfg::ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) { tma_prefetch_desc(&p.tmA[s]); tma_prefetch_desc(&p.tmB[s]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < Cfg::ACC_STAGES; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+                const int arow = p.a_row0 + tm * BM, brow = p.b_row0 + tn * BN;
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sB = sA + Cfg::A_BYTES;
+                        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sA, &p.tmA[s], &full[stage], kb * BK, arow);
+                        tma_load_2d(sB, &p.tmB[s], &full[stage], kb * BK, brow);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                uint32_t touched = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int acc = p.seg_acc[s];
+                    const uint32_t d_addr = tmem_base + as * Cfg::ACC_COLS + acc * BN;
+                    for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom
+                            umma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                      ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
+                        }
+                        touched |= (1u << acc);
+                        umma_commit(&empty[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(&tfull[as]);
+                if (++as == Cfg::ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        int as = 0; uint32_t aphase = 0;
+        int seq = 0;
+        typename Epi::State st;
+        Epi::init(st, p.epi, q, lane);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++seq) {
+            TileInfo ti;
+            ti.tm = t / p.tiles_n; ti.tn = t % p.tiles_n;
+            ti.row0 = p.a_row0 + ti.tm * BM; ti.col0 = p.b_row0 + ti.tn * BN;
+            ti.q = q; ti.lane = lane; ti.tile_seq = seq;
+            ti.taddr = tmem_base + as * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            Epi::prologue(st, p.epi, ti, epi_smem);      // may overlap the MMAs of this tile
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            Epi::run(st, p.epi, ti, epi_smem);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (++as == Cfg::ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+        Epi::finish(st, p.epi, q, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ======================================================================================
+// Epilogue policies
+// ======================================================================================
+
+// ---- plain store:  C[row][col] = alpha * acc   (fp32, row stride ldc) -----------------
+struct EpiStore {
+    static constexpr int SMEM_BYTES = 0;
+    struct Params { float* C; long long ldc; int rows, cols; float alpha; int row_off; };
+    struct State {};
+    __device__ static void init(State&, const Params&, int, int) {}
+    __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
+    __device__ static void finish(State&, const Params&, int, int) {}
+    template <int BN>
+    __device__ static void run_bn(State&, const Params& P, const TileInfo& ti, uint8_t*) {
+        const int row = ti.row0 + ti.q * 32 + ti.lane;
+        const bool rvalid = row < P.rows;
+        float* crow = P.C + static_cast<long long>(row - P.row_off) * P.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(ti.taddr + c * 32, r);
+            tmem_ld_wait();
+            const int col = ti.col0 + c * 32;
+            if (rvalid) {
+                if (col + 32 <= P.cols && (P.ldc & 3) == 0) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        float4 v = make_float4(__uint_as_float(r[e]) * P.alpha, __uint_as_float(r[e + 1]) * P.alpha,
+                                               __uint_as_float(r[e + 2]) * P.alpha, __uint_as_float(r[e + 3]) * P.alpha);
+                        *reinterpret_cast<float4*>(crow + col + e) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (col + e < P.cols) crow[col + e] = __uint_as_float(r[e]) * P.alpha;
+                }
+            }
+        }
+    }
+};
+template <int BN> struct EpiStoreT : EpiStore {
+    __device__ static void run(State& s, const Params& P, const TileInfo& ti, uint8_t* sm) { run_bn<BN>(s, P, ti, sm); }
+};
+
+// ---- relaxed EMD: best (max dot = min cosine distance) per A row and per B row ---------
+// A rows = target/style samples i (M of them), B rows = prediction samples j (N of them).
+// rowbest[i] = max_j (dot_ij, lowest j on ties);  colbest[j] = max_i (dot_ij, lowest i on ties).
+// Phantom rows/columns produced by TMA zero fill are masked out (SURVEY "OOB / ragged tiles").
+template <int BN>
+struct EpiRemd {
+    static constexpr int SMEM_BYTES = 0;
+    struct Params { unsigned long long* rowbest; unsigned long long* colbest; int M, N; };
+    struct State {};
+    __device__ static void init(State&, const Params&, int, int) {}
+    __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
+    __device__ static void finish(State&, const Params&, int, int) {}
+    __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t*) {
+        const int row = ti.row0 + ti.q * 32 + ti.lane;
+        const bool rvalid = row < P.M;
+        float best_v = -INFINITY;
+        int best_j = 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(ti.taddr + c * 32, r);
+            tmem_ld_wait();
+            const int colbase = ti.col0 + c * 32;
+            uint32_t my_key = 0; int my_src = 0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float v = __uint_as_float(r[e]);
+                const int col = colbase + e;
+                if (col < P.N && v > best_v) { best_v = v; best_j = col; }
+                const uint32_t key = rvalid ? f2ord(v) : 0u;
+                const uint32_t m = __reduce_max_sync(0xffffffffu, key);
+                const uint32_t ball = __ballot_sync(0xffffffffu, key == m);
+                if (ti.lane == e) { my_key = m; my_src = __ffs(ball) - 1; }
+            }
+            const int mycol = colbase + ti.lane;
+            if (mycol < P.N && my_key != 0u) {
+                const uint32_t src_row = static_cast<uint32_t>(ti.row0 + ti.q * 32 + my_src);
+                const unsigned long long packed = (static_cast<unsigned long long>(my_key) << 32) |
+                                                  static_cast<unsigned long long>(~src_row);
+                atomicMax(P.colbest + mycol, packed);
+            }
+        }
+        if (rvalid && best_v > -INFINITY) atomicMax(P.rowbest + row, pack_best(best_v, static_cast<uint32_t>(best_j)));
+    }
+};
+
+// ---- self-similarity, stage 1 ----------------------------------------------------------
+// acc0 = delta_i.x^_j + y^_i.delta_j = -(Xd_ij - Yd_ij)      (delta = x^ - y^; x^ pred, y^ content)
+// acc1 = y^_i.y^_j                   = 1 - Yd_ij
+// column form  term_ij  = Xd_ij/s_j - Yd_ij/t_j = diff*u_j + Yd*w_j      (u = 1/s, w = 1/s - 1/t)
+// row form     term'_ij = term_ji               = diff*u_i + Yd*w_i      (Xd, Yd symmetric)
+// loss_i += |term'_ij|,  r_i += sign(term'_ij) * Xd_ij,  P_ij = sign(term_ij)*u_j + sign(term'_ij)*u_i
+// P (bf16) goes to the L2-resident row panel that stage 2 multiplies with x^.
+struct EpiSS1 {
+    static constexpr int BN = 128;
+    static constexpr int SMEM_BYTES = 2 * 2 * BN * sizeof(float);
+    struct Params {
+        const float* u; const float* w;       // per sample, length N
+        __nv_bfloat16* P; long long ldp;      // panel, row stride (elements), panel starts at row panel_row0
+        int panel_row0;
+        float* loss_part; float* r_part;      // [tiles_n_total][N]
+        int N;
+        int write_p;
+    };
+    struct State {};
+    __device__ static void init(State&, const Params&, int, int) {}
+    __device__ static void finish(State&, const Params&, int, int) {}
+    __device__ static void prologue(State&, const Params& P, const TileInfo& ti, uint8_t* sm) {
+        float* buf = reinterpret_cast<float*>(sm) + (ti.tile_seq & 1) * 2 * BN;
+        const int t = ti.q * 32 + ti.lane;
+        const int col = ti.col0 + t;
+        buf[t] = (col < P.N) ? P.u[col] : 0.f;
+        buf[BN + t] = (col < P.N) ? P.w[col] : 0.f;
+        epi_bar_sync();
+    }
+    __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t* sm) {
+        const float* su = reinterpret_cast<const float*>(sm) + (ti.tile_seq & 1) * 2 * BN;
+        const float* sw = su + BN;
+        const int row = ti.row0 + ti.q * 32 + ti.lane;
+        const bool rvalid = row < P.N;
+        const float ui = rvalid ? P.u[row] : 0.f;
+        const float wi = rvalid ? P.w[row] : 0.f;
+        float loss = 0.f, racc = 0.f;
+        __nv_bfloat16* prow = P.P + static_cast<long long>(row - P.panel_row0) * P.ldp;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t a0[32], a1[32];
+            tmem_ld32(ti.taddr + c * 32, a0);
+            tmem_ld32(ti.taddr + BN + c * 32, a1);
+            tmem_ld_wait();
+            const int colbase = ti.col0 + c * 32;
+            uint32_t packed[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                float pv[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = colbase + e + h;
+                    const bool live = rvalid && (col < P.N) && (col != row);
+                    const float diff = -__uint_as_float(a0[e + h]);
+                    const float yd = 1.f - __uint_as_float(a1[e + h]);
+                    const float uj = su[c * 32 + e + h], wj = sw[c * 32 + e + h];
+                    const float tc = fmaf(diff, uj, yd * wj);
+                    const float tr = fmaf(diff, ui, yd * wi);
+                    const float sc = live ? ((tc > 0.f) ? 1.f : ((tc < 0.f) ? -1.f : 0.f)) : 0.f;
+                    const float sr = live ? ((tr > 0.f) ? 1.f : ((tr < 0.f) ? -1.f : 0.f)) : 0.f;
+                    loss += live ? fabsf(tr) : 0.f;
+                    racc = fmaf(sr, yd + diff, racc);
+                    pv[h] = fmaf(sc, uj, sr * ui);
+                }
+                packed[e >> 1] = pack_bf16x2(pv[0], pv[1]);
+            }
+            if (P.write_p && rvalid && colbase < P.ldp) {
+                // ldp is a multiple of 64 and colbase a multiple of 32, so a 32-wide chunk is
+                // either fully inside the padded row or fully outside it.
+                uint4* dst = reinterpret_cast<uint4*>(prow + colbase);
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+            }
+        }
+        if (rvalid) {
+            P.loss_part[static_cast<long long>(ti.tn) * P.N + row] = loss;
+            P.r_part[static_cast<long long>(ti.tn) * P.N + row] = racc;
+        }
+    }
+};
+
+// ---- covariance forward:  V = acc/n ; loss partial = sum |V - Vx| ; Sg = sign(V - Vx) (bf16) ---
+template <int BN>
+struct EpiCovFwd {
+    static constexpr int SMEM_BYTES = 0;
+    struct Params {
+        const float* Vx; long long ldv;        // target covariance (fp32)
+        __nv_bfloat16* Sg; long long lds;      // sign matrix out (bf16, zero-padded by the owner)
+        float* part;                           // [num_tiles * 4] partial sums of |V - Vx|
+        float inv_n; int D;
+        int tiles_n;
+    };
+    struct State {};
+    __device__ static void init(State&, const Params&, int, int) {}
+    __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
+    __device__ static void finish(State&, const Params&, int, int) {}
+    __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t*) {
+        const int row = ti.row0 + ti.q * 32 + ti.lane;
+        const bool rvalid = row < P.D;
+        const float* vrow = P.Vx + static_cast<long long>(row) * P.ldv;
+        __nv_bfloat16* srow = P.Sg + static_cast<long long>(row) * P.lds;
+        float part = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(ti.taddr + c * 32, r);
+            tmem_ld_wait();
+            const int colbase = ti.col0 + c * 32;
+            if (rvalid && colbase < P.D) {
+                if (colbase + 32 <= P.D) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        const float4 vx = *reinterpret_cast<const float4*>(vrow + colbase + e);
+                        const float d0 = fmaf(__uint_as_float(r[e]), P.inv_n, -vx.x);
+                        const float d1 = fmaf(__uint_as_float(r[e + 1]), P.inv_n, -vx.y);
+                        const float d2 = fmaf(__uint_as_float(r[e + 2]), P.inv_n, -vx.z);
+                        const float d3 = fmaf(__uint_as_float(r[e + 3]), P.inv_n, -vx.w);
+                        part += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+                        auto sg = [](float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); };
+                        packed[e >> 1] = pack_bf16x2(sg(d0), sg(d1));
+                        packed[(e >> 1) + 1] = pack_bf16x2(sg(d2), sg(d3));
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(srow + colbase);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        if (colbase + e < P.D) {
+                            const float d = fmaf(__uint_as_float(r[e]), P.inv_n, -vrow[colbase + e]);
+                            part += fabsf(d);
+                            srow[colbase + e] = __float2bfloat16((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
+                        }
+                    }
+                }
+            }
+        }
+        part = warp_sum(part);
+        if (ti.lane == 0) P.part[(static_cast<long long>(ti.tm) * P.tiles_n + ti.tn) * 4 + ti.q] = part;
+    }
+};
+
+}  // namespace sb

@@ -1,0 +1,494 @@
+// HBM-bound / CUDA-core kernels of the STROTSS loss path: operand preparation (row norms, column
+// sums, bf16 operand emission incl. transposes), the K=3 palette distance, the sparse relaxed-EMD
+// backward, the small reductions and the final gradient assembly.  All reductions that feed a
+// reported loss are fixed-order (two-stage partials), so results are run-to-run deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+constexpr float kL2NEps = 1e-12f;      // tf.nn.l2_normalize epsilon       (nn/losses.py:13-14)
+constexpr float kL2DClamp = 1e-6f;     // l2_distance clamp               (nn/losses.py:23)
+constexpr float kColsumClamp = 1e-12f; // self_similarity column-sum clamp (nn/losses.py:60,63)
+constexpr int kRowsPerBlock = 32;      // rows per block in the column-partial kernels
+
+// scalar slots written by the library (device float array, see include/strotss_b200.h)
+enum Scalar {
+    S_TOTAL = 0, S_LOSS_C = 1, S_LOSS_S = 2, S_LM = 3, S_LREMD = 4, S_LPAL = 5,
+    S_REMD_RX = 6, S_REMD_RY = 7, S_LCOV = 8, S_LMEAN = 9, S_PAL_RX = 10, S_PAL_RY = 11,
+    S_REMD_BRANCH = 12, S_PAL_BRANCH = 13, S_COUNT = 16
+};
+
+// --------------------------------------------------------------------------------------
+// row statistics + per-block column partial sums
+//   inv[r]            = rsqrt(max(sum_d x[r][d]^2, 1e-12))
+//   part_raw[b][d]    = sum_{r in block b} x[r][d]              (-> column mean)
+//   part_hat[b][d]    = sum_{r in block b} x[r][d] * inv[r]     (-> sum of normalised rows)
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, long long ld, int n, int D,
+                                                        float* __restrict__ inv, float* __restrict__ part_raw,
+                                                        float* __restrict__ part_hat) {
+    __shared__ float s_inv[kRowsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * kRowsPerBlock;
+    for (int rr = warp; rr < kRowsPerBlock; rr += 8) {
+        const int r = r0 + rr;
+        float ss = 0.f;
+        if (r < n) {
+            const float* xr = x + static_cast<long long>(r) * ld;
+            for (int d = lane; d < D; d += 32) { const float v = xr[d]; ss = fmaf(v, v, ss); }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            const float iv = rsqrtf(fmaxf(ss, kL2NEps));
+            s_inv[rr] = (r < n) ? iv : 0.f;
+            if (r < n) inv[r] = iv;
+        }
+    }
+    __syncthreads();
+    const int rows = min(kRowsPerBlock, n - r0);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float a = 0.f, h = 0.f;
+        for (int rr = 0; rr < rows; ++rr) {
+            const float v = x[static_cast<long long>(r0 + rr) * ld + d];
+            a += v;
+            h = fmaf(v, s_inv[rr], h);
+        }
+        if (part_raw) part_raw[static_cast<long long>(blockIdx.x) * D + d] = a;
+        if (part_hat) part_hat[static_cast<long long>(blockIdx.x) * D + d] = h;
+    }
+}
+
+// weighted sum of normalised rows: part[b][d] = sum_{r in block b} coef[r] * inv[r] * x[r][d]
+__global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __restrict__ x, long long ld, int n, int D,
+                                                              const float* __restrict__ inv, const float* __restrict__ coef,
+                                                              float* __restrict__ part) {
+    __shared__ float s_w[kRowsPerBlock];
+    const int r0 = blockIdx.x * kRowsPerBlock;
+    if (threadIdx.x < kRowsPerBlock) {
+        const int r = r0 + threadIdx.x;
+        s_w[threadIdx.x] = (r < n) ? coef[r] * inv[r] : 0.f;
+    }
+    __syncthreads();
+    const int rows = min(kRowsPerBlock, n - r0);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float a = 0.f;
+        for (int rr = 0; rr < rows; ++rr) a = fmaf(x[static_cast<long long>(r0 + rr) * ld + d], s_w[rr], a);
+        part[static_cast<long long>(blockIdx.x) * D + d] = a;
+    }
+}
+
+// out[d] = scale * sum_b part[b][d]   (fixed order)
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int nblocks, int D, float scale,
+                                     float* __restrict__ out) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float a = 0.f;
+    for (int b = 0; b < nblocks; ++b) a += part[static_cast<long long>(b) * D + d];
+    out[d] = a * scale;
+}
+
+// --------------------------------------------------------------------------------------
+// bf16 operand emission, 64x64 tiles through shared memory.
+//   xh  [r][d]  = x*inv                 (row-major, ld = Dp, zero in the K padding)
+//   cen [r][d]  = x - mean[d]           (row-major, ld = Dp)
+//   dlt [r][d]  = x*inv - y*inv_y       (row-major, ld = Dp)          (self-similarity delta form)
+//   xhT [d][r]  = x*inv                 (transposed, ld = np, zero for r >= n)
+//   cenT[d][r]  = x - mean[d]           (transposed, ld = np)
+// Any output pointer may be null.
+// --------------------------------------------------------------------------------------
+struct EmitArgs {
+    const float* x; long long ldx; int n, D, Dp, np;
+    const float* inv; const float* mean;
+    const float* y; long long ldy; const float* inv_y;      // only for dlt
+    __nv_bfloat16* xh; __nv_bfloat16* cen; __nv_bfloat16* dlt;
+    __nv_bfloat16* xhT; __nv_bfloat16* cenT;
+};
+
+__global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
+    __shared__ float sx[64][65];
+    __shared__ float sy[64][65];
+    __shared__ float s_inv[64], s_invy[64], s_mean[64];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int col0 = blockIdx.x * 64, row0 = blockIdx.y * 64;
+    if (threadIdx.x < 64) {
+        const int r = row0 + threadIdx.x;
+        s_inv[threadIdx.x] = (r < a.n) ? a.inv[r] : 0.f;
+        s_invy[threadIdx.x] = (a.dlt && r < a.n) ? a.inv_y[r] : 0.f;
+        const int c = col0 + threadIdx.x;
+        s_mean[threadIdx.x] = (a.mean && c < a.D) ? a.mean[c] : 0.f;
+    }
+    for (int rr = grp * 8; rr < grp * 8 + 8; ++rr) {
+        const int r = row0 + rr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cc = lane + 32 * h, c = col0 + cc;
+            const bool ok = (r < a.n) && (c < a.D);
+            sx[rr][cc] = ok ? a.x[static_cast<long long>(r) * a.ldx + c] : 0.f;
+            sy[rr][cc] = (ok && a.dlt) ? a.y[static_cast<long long>(r) * a.ldy + c] : 0.f;
+        }
+    }
+    __syncthreads();
+    // row-major outputs: thread (grp, lane) -> rows grp*8.., columns 2*lane, 2*lane+1
+    for (int rr = grp * 8; rr < grp * 8 + 8; ++rr) {
+        const int r = row0 + rr;
+        if (r >= a.n) continue;
+        const int cc = 2 * lane, c = col0 + cc;
+        const float x0 = sx[rr][cc], x1 = sx[rr][cc + 1];
+        const float iv = s_inv[rr];
+        const long long off = static_cast<long long>(r) * a.Dp + c;
+        if (a.xh) *reinterpret_cast<uint32_t*>(a.xh + off) = pack_bf16x2(x0 * iv, x1 * iv);
+        if (a.cen) {
+            const float c0 = (c < a.D) ? x0 - s_mean[cc] : 0.f;
+            const float c1 = (c + 1 < a.D) ? x1 - s_mean[cc + 1] : 0.f;
+            *reinterpret_cast<uint32_t*>(a.cen + off) = pack_bf16x2(c0, c1);
+        }
+        if (a.dlt) {
+            const float ivy = s_invy[rr];
+            *reinterpret_cast<uint32_t*>(a.dlt + off) =
+                pack_bf16x2(fmaf(x0, iv, -sy[rr][cc] * ivy), fmaf(x1, iv, -sy[rr][cc + 1] * ivy));
+        }
+    }
+    // transposed outputs: thread (grp, lane) -> columns grp*8.., rows 2*lane, 2*lane+1
+    if (a.xhT || a.cenT) {
+        for (int cc = grp * 8; cc < grp * 8 + 8; ++cc) {
+            const int c = col0 + cc;
+            if (c >= a.D) continue;
+            const int rr = 2 * lane, r = row0 + rr;
+            if (r >= a.np) continue;
+            const long long off = static_cast<long long>(c) * a.np + r;
+            if (a.xhT)
+                *reinterpret_cast<uint32_t*>(a.xhT + off) = pack_bf16x2(sx[rr][cc] * s_inv[rr], sx[rr + 1][cc] * s_inv[rr + 1]);
+            if (a.cenT) {
+                const float m = s_mean[cc];
+                const float c0 = (r < a.n) ? sx[rr][cc] - m : 0.f;
+                const float c1 = (r + 1 < a.n) ? sx[rr + 1][cc] - m : 0.f;
+                *reinterpret_cast<uint32_t*>(a.cenT + off) = pack_bf16x2(c0, c1);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// self-similarity per-sample vectors (one warp per sample j):
+//   s_j = N - x^_j . sum_i x^_i,  t_j = N - y^_j . sum_i y^_i      (column sums of Xd, Yd)
+//   u_j = 1/max(s_j,1e-12),  w_j = 1/max(s_j,..) - 1/max(t_j,..)
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ss_vectors_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ invx,
+                                                         const float* __restrict__ sumhx,
+                                                         const float* __restrict__ y, long long ldy, const float* __restrict__ invy,
+                                                         const float* __restrict__ sumhy,
+                                                         int N, int D, float* __restrict__ u, float* __restrict__ w,
+                                                         float* __restrict__ sclamp) {
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= N) return;
+    const float* xr = x + static_cast<long long>(j) * ldx;
+    const float* yr = y + static_cast<long long>(j) * ldy;
+    float dx = 0.f, dy = 0.f;
+    for (int d = lane; d < D; d += 32) { dx = fmaf(xr[d], sumhx[d], dx); dy = fmaf(yr[d], sumhy[d], dy); }
+    dx = warp_sum(dx) * invx[j];
+    dy = warp_sum(dy) * invy[j];
+    if (lane == 0) {
+        const float s = static_cast<float>(N) - dx, t = static_cast<float>(N) - dy;
+        const float sc = fmaxf(s, kColsumClamp), tcl = fmaxf(t, kColsumClamp);
+        const bool plain = (s >= kColsumClamp) && (t >= kColsumClamp);
+        const float tms = plain ? (dx - dy) : (tcl - sc);       // t - s without the N - N cancellation
+        u[j] = 1.f / sc;
+        w[j] = tms / (sc * tcl);
+        sclamp[j] = (s >= kColsumClamp) ? 1.f : 0.f;             // tf.maximum passes the gradient iff s >= clamp
+    }
+}
+
+// r_i = (1/N) sum_tn r_part[tn][i];  coef_i = r_i u_i^2 [s_i >= clamp];  rowloss_i = sum_tn loss_part[tn][i]
+__global__ void ss_rows_kernel(const float* __restrict__ loss_part, const float* __restrict__ r_part, int ntn, int N,
+                               const float* __restrict__ u, const float* __restrict__ sclamp,
+                               float* __restrict__ coef, float* __restrict__ rowloss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float l = 0.f, r = 0.f;
+    for (int t = 0; t < ntn; ++t) {
+        l += loss_part[static_cast<long long>(t) * N + i];
+        r += r_part[static_cast<long long>(t) * N + i];
+    }
+    rowloss[i] = l;
+    const float ui = u[i];
+    coef[i] = (r / static_cast<float>(N)) * ui * ui * sclamp[i];
+}
+
+// out[slot] = scale * sum_i in[i]      (single block, fixed order)
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out) {
+    __shared__ float sh[32];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += in[i];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float b = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+        b = warp_sum(b);
+        if (threadIdx.x == 0) *out = b * scale;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// relaxed EMD finish:  R_X = mean_i cost(rowbest_i), R_Y = mean_j cost(colbest_j), L = max(R_X,R_Y)
+// cost = offset - value  (cosine: offset 1, value = max dot;  palette: offset 0, value = -min cost)
+// tf.maximum sends the gradient to its FIRST argument (R_X) on ties -> branch = (R_X >= R_Y).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long long* __restrict__ rowbest, int M,
+                                                           const unsigned long long* __restrict__ colbest, int N,
+                                                           float offset, float* __restrict__ scalars, int slot_loss,
+                                                           int slot_rx, int slot_ry, int slot_branch,
+                                                           int* __restrict__ row_arg, int* __restrict__ col_arg) {
+    __shared__ float sh[2][32];
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const unsigned long long k = rowbest[i];
+        a += offset - best_val(k);
+        if (row_arg) row_arg[i] = static_cast<int>(best_idx(k));
+    }
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const unsigned long long k = colbest[j];
+        b += offset - best_val(k);
+        if (col_arg) col_arg[j] = static_cast<int>(best_idx(k));
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float aa = sh[0][threadIdx.x], bb = sh[1][threadIdx.x];
+        aa = warp_sum(aa); bb = warp_sum(bb);
+        if (threadIdx.x == 0) {
+            const float rx = aa / static_cast<float>(M), ry = bb / static_cast<float>(N);
+            scalars[slot_rx] = rx; scalars[slot_ry] = ry;
+            scalars[slot_loss] = fmaxf(rx, ry);
+            scalars[slot_branch] = (rx >= ry) ? 1.f : 0.f;
+        }
+    }
+}
+
+// Sparse backward of the cosine relaxed EMD into g (gradient w.r.t. the NORMALISED prediction rows):
+//   branch X: g[argmin_i][:] += -(1/M) x^_i   for every target row i   (scatter, atomics)
+//   branch Y: g[j][:]        += -(1/N) x^_{argmin_j}                    (gather)
+// One warp per row of max(M, N); the branch flag is read from device memory (no host sync).
+__global__ void __launch_bounds__(256) remd_backward_kernel(const unsigned long long* __restrict__ rowbest, int M,
+                                                            const unsigned long long* __restrict__ colbest, int N,
+                                                            const float* __restrict__ xs, long long ldxs,
+                                                            const float* __restrict__ inv_s, int D,
+                                                            const float* __restrict__ scalars, int slot_branch,
+                                                            float* __restrict__ g, long long ldg) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const bool bx = scalars[slot_branch] != 0.f;
+    if (bx) {
+        if (row >= M) return;
+        const int j = static_cast<int>(best_idx(rowbest[row]));
+        const float sc = -inv_s[row] / static_cast<float>(M);
+        const float* src = xs + static_cast<long long>(row) * ldxs;
+        float* dst = g + static_cast<long long>(j) * ldg;
+        for (int d = lane; d < D; d += 32) atomicAdd(dst + d, src[d] * sc);
+    } else {
+        if (row >= N) return;
+        const int i = static_cast<int>(best_idx(colbest[row]));
+        const float sc = -inv_s[i] / static_cast<float>(N);
+        const float* src = xs + static_cast<long long>(i) * ldxs;
+        float* dst = g + static_cast<long long>(row) * ldg;
+        for (int d = lane; d < D; d += 32) dst[d] += src[d] * sc;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// palette (nn/strotss_utils.py:166-167 + nn/losses.py:12-28 'both' on 3 channels)
+// rec = { y,u,v, y^,u^,v^, |yuv|^2, inv_norm }
+// --------------------------------------------------------------------------------------
+__constant__ float c_rgb2yuv[9] = {0.299f, -0.14714119f, 0.61497538f,
+                                   0.587f, -0.28886916f, -0.51496512f,
+                                   0.114f, 0.43601035f, -0.10001026f};
+
+__global__ void pal_prep_kernel(const float* __restrict__ x, long long ld, int n, int convert, float* __restrict__ rec) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float* xr = x + static_cast<long long>(r) * ld;
+    const float R = xr[0], G = xr[1], B = xr[2];
+    float y, u, v;
+    if (convert) {
+        y = R * c_rgb2yuv[0] + G * c_rgb2yuv[3] + B * c_rgb2yuv[6];
+        u = R * c_rgb2yuv[1] + G * c_rgb2yuv[4] + B * c_rgb2yuv[7];
+        v = R * c_rgb2yuv[2] + G * c_rgb2yuv[5] + B * c_rgb2yuv[8];
+    } else { y = R; u = G; v = B; }
+    const float sq = y * y + u * u + v * v;
+    const float iv = rsqrtf(fmaxf(sq, kL2NEps));
+    float* o = rec + static_cast<long long>(r) * 8;
+    o[0] = y; o[1] = u; o[2] = v; o[3] = y * iv; o[4] = u * iv; o[5] = v * iv; o[6] = sq; o[7] = iv;
+}
+
+// cost of one (a, b) pair for distance mode: 0 cosine, 1 l2, 2 both   (3 channels)
+__device__ __forceinline__ float pal_cost(const float* a, const float* b, int mode) {
+    float c = 0.f;
+    if (mode != 1) c = 1.f - (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
+    if (mode != 0) {
+        const float m = a[6] + b[6] - 2.f * (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+        c += sqrtf(fmaxf(m, kL2DClamp) / 3.f);
+    }
+    return c;
+}
+
+// best[q] = max over keys of -cost(q, key)  (packed; ties -> lowest key index).
+// swap = 1 evaluates cost(key, query) so both directions see the same operand order as the reference.
+__global__ void __launch_bounds__(128) pal_min_kernel(const float* __restrict__ qrec, int nq, const float* __restrict__ krec, int nk,
+                                                      int kchunk, int mode, int swap, unsigned long long* __restrict__ best) {
+    __shared__ float sk[256 * 8];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = (q < nq) ? qrec[static_cast<long long>(q) * 8 + e] : 0.f;
+    const int k0 = blockIdx.y * kchunk, k1 = min(nk, k0 + kchunk);
+    float bv = INFINITY; int bi = 0;
+    for (int kb = k0; kb < k1; kb += 256) {
+        const int cnt = min(256, k1 - kb);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * 8; e += blockDim.x) sk[e] = krec[static_cast<long long>(kb) * 8 + e];
+        __syncthreads();
+        for (int k = 0; k < cnt; ++k) {
+            const float c = swap ? pal_cost(sk + k * 8, a, mode) : pal_cost(a, sk + k * 8, mode);
+            if (c < bv) { bv = c; bi = kb + k; }
+        }
+    }
+    if (q < nq && k1 > k0) atomicMax(best + q, pack_best(-bv, static_cast<uint32_t>(bi)));
+}
+
+// Sparse backward of the 3-channel relaxed EMD w.r.t. the prediction's RGB (through the YUV matrix).
+// gpal[j][0..2] += weight-less gradient; one thread per selected pair.
+__global__ void pal_backward_kernel(const unsigned long long* __restrict__ rowbest, int M,
+                                    const unsigned long long* __restrict__ colbest, int N,
+                                    const float* __restrict__ arec, const float* __restrict__ brec, int mode, int convert,
+                                    const float* __restrict__ scalars, int slot_branch, float* __restrict__ gpal) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bx = scalars[slot_branch] != 0.f;
+    int i, j; float wgt;
+    if (bx) { if (t >= M) return; i = t; j = static_cast<int>(best_idx(rowbest[t])); wgt = 1.f / static_cast<float>(M); }
+    else    { if (t >= N) return; j = t; i = static_cast<int>(best_idx(colbest[t])); wgt = 1.f / static_cast<float>(N); }
+    const float* a = arec + static_cast<long long>(i) * 8;
+    const float* b = brec + static_cast<long long>(j) * 8;
+    float g[3] = {0.f, 0.f, 0.f};
+    if (mode != 1) {
+        // d(1 - a^.b^)/db = -(a^ - b^ (a^.b^)) / |b|   (no projection when |b|^2 < 1e-12)
+        const float dot = a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+        const bool live = b[6] >= kL2NEps;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) g[e] += -(a[3 + e] - (live ? b[3 + e] * dot : 0.f)) * b[7];
+    }
+    if (mode != 0) {
+        const float m = a[6] + b[6] - 2.f * (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+        if (m >= kL2DClamp) {
+            const float l2 = sqrtf(m / 3.f);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) g[e] += (b[e] - a[e]) / (3.f * l2);
+        }
+    }
+    float o[3];
+    if (convert) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = g[0] * c_rgb2yuv[3 * c] + g[1] * c_rgb2yuv[3 * c + 1] + g[2] * c_rgb2yuv[3 * c + 2];
+    } else { o[0] = g[0]; o[1] = g[1]; o[2] = g[2]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(gpal + static_cast<long long>(j) * 4 + c, o[c] * wgt);
+}
+
+// --------------------------------------------------------------------------------------
+// moment matching, mean part + covariance partial sum (single block):
+//   l_mean = mean_d |mu_y - mu_x|,  gmu[d] = sign(mu_y - mu_x) / D
+//   l_cov  = sum(part) / D^2 ;  l_m = l_cov + l_mean
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) moment_finish_kernel(const float* __restrict__ mu_y, const float* __restrict__ mu_x, int D,
+                                                             const float* __restrict__ part, int npart,
+                                                             float* __restrict__ gmu, float* __restrict__ scalars) {
+    __shared__ float sh[2][32];
+    float a = 0.f, b = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float df = mu_y[d] - mu_x[d];
+        a += fabsf(df);
+        gmu[d] = ((df > 0.f) ? 1.f : ((df < 0.f) ? -1.f : 0.f)) / static_cast<float>(D);
+    }
+    for (int i = threadIdx.x; i < npart; i += blockDim.x) b += part[i];
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float aa = warp_sum(sh[0][threadIdx.x]), bb = warp_sum(sh[1][threadIdx.x]);
+        if (threadIdx.x == 0) {
+            const float lmean = aa / static_cast<float>(D);
+            const float lcov = bb / (static_cast<float>(D) * static_cast<float>(D));
+            scalars[S_LMEAN] = lmean; scalars[S_LCOV] = lcov; scalars[S_LM] = lmean + lcov;
+        }
+    }
+}
+
+// loss_s = l_m + l_remd + inv_alpha*l_pal ; total = (alpha*loss_c + loss_s)/denom   (run_strotss.py:40,140)
+__global__ void combine_scalars_kernel(float* __restrict__ s, float alpha, float inv_alpha, float denom) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const float ls = s[S_LM] + s[S_LREMD] + inv_alpha * s[S_LPAL];
+        s[S_LOSS_S] = ls;
+        s[S_TOTAL] = (alpha * s[S_LOSS_C] + ls) / denom;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// final gradient assembly, one block per prediction row i:
+//   g^[d]  = w_ss * ( -ss2[i][d]/N + v[d] + coef_i * sumhat[d] )  +  w_remd * gremd[i][d]
+//   grad   = (g^ - x^ (x^ . g^)) * inv_i                     (through l2_normalize; no projection if clamped)
+//          + w_mom * ( q_scale * Q[i][d] + gmu[d]/N )
+//          + w_pal * gpal[i][d]  for d < 3
+// Any term whose pointer is null is skipped.  All weights already include 1/loss_denom.
+// --------------------------------------------------------------------------------------
+struct FinalizeArgs {
+    const float* x; long long ldx; const float* inv; int N, D;
+    const float* ss2; long long ld_ss2; const float* v; const float* coef; const float* sumhat; float w_ss;
+    const float* gremd; long long ld_gremd; float w_remd;
+    const float* Q; long long ldq; float q_scale; const float* gmu; float w_mom;
+    const float* gpal; float w_pal;
+    float* grad; long long ldg;
+};
+
+__global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a) {
+    extern __shared__ float sg[];       // D floats: g^
+    __shared__ float sh[8];
+    __shared__ float s_dot;
+    const int i = blockIdx.x;
+    const float* xr = a.x + static_cast<long long>(i) * a.ldx;
+    const float iv = a.inv[i];
+    const float invN = 1.f / static_cast<float>(a.N);
+    const float ci = a.ss2 ? a.coef[i] : 0.f;
+    float dot = 0.f, ssq = 0.f;
+    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+        float g = 0.f;
+        if (a.ss2) g += a.w_ss * (-a.ss2[static_cast<long long>(i) * a.ld_ss2 + d] * invN + a.v[d] + ci * a.sumhat[d]);
+        if (a.gremd) g += a.w_remd * a.gremd[static_cast<long long>(i) * a.ld_gremd + d];
+        sg[d] = g;
+        const float xv = xr[d];
+        dot = fmaf(g, xv, dot);
+        ssq = fmaf(xv, xv, ssq);
+    }
+    dot = warp_sum(dot); ssq = warp_sum(ssq);
+    __shared__ float sh2[8];
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = dot; sh2[threadIdx.x >> 5] = ssq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f, q = 0.f;
+        for (int k = 0; k < 8; ++k) { t += sh[k]; q += sh2[k]; }
+        // g^.x^ = (g^.x) * inv ; the projection term is x^ (x^.g^) * inv = x * (g^.x) * inv^3
+        s_dot = (q >= kL2NEps) ? t * iv * iv * iv : 0.f;
+    }
+    __syncthreads();
+    const float pd = s_dot;
+    float* gr = a.grad + static_cast<long long>(i) * a.ldg;
+    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+        float o = sg[d] * iv - xr[d] * pd;
+        if (a.Q) o += a.w_mom * (a.q_scale * a.Q[static_cast<long long>(i) * a.ldq + d] + a.gmu[d] * invN);
+        if (a.gpal && d < 3) o += a.w_pal * a.gpal[static_cast<long long>(i) * 4 + d];
+        gr[d] = o;
+    }
+}
+
+}  // namespace sb

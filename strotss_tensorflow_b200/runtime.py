@@ -1,0 +1,203 @@
+"""Handle management: one library handle per (owner, CUDA device); torch supplies device memory and
+the current stream, nothing else."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_features(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the STROTSS loss path runs on a B200 only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (the reference computes in fp32), got {t.dtype}")
+    return t
+
+
+def reshape_2d(x: torch.Tensor, channel_axis: int = -1) -> torch.Tensor:
+    """nn/losses.py:31-36: squeeze, then reshape to (-1, C).  (The rank test at :32 never fires.)"""
+    x = torch.squeeze(x)
+    if x.dim() == 0:
+        x = x.reshape(1, 1)
+    return x.reshape(-1, x.shape[channel_axis])
+
+
+class Handle:
+    """Owns one strotss_handle (device workspace + cached style target)."""
+
+    def __init__(self, device: torch.device):
+        self.lib = _lib.load()
+        if device.type != "cuda":
+            raise RuntimeError("strotss_tensorflow_b200 needs a CUDA (sm_100) device; there is no CPU path")
+        self.device = device
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.index = idx
+        h = C.c_void_p()
+        code = self.lib.strotss_create(idx, C.byref(h))
+        self._h = h
+        if code != 0:
+            msg = self.lib.strotss_last_error(h).decode() if h else "allocation failed"
+            if h:
+                self.lib.strotss_destroy(h)
+            self._h = None
+            raise _lib.StrotssError(f"strotss_create(device={idx}) failed (code {code}): {msg}")
+        self.style_shape = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:
+                pass
+            self.lib.strotss_destroy(h)
+            self._h = None
+
+    def _ck(self, code, what):
+        _lib.check(self.lib, self._h, code, what)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.strotss_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.strotss_workspace_bytes(self._h))
+
+    # ---- fused path -----------------------------------------------------------------
+    def set_style_target(self, style: torch.Tensor):
+        style = _check_features("style target", reshape_2d(style)).contiguous()
+        M, D = style.shape
+        self._ck(self.lib.strotss_set_style_target(self._h, _ptr(style), M, D, style.stride(0), _stream(style.device)),
+                 "strotss_set_style_target")
+        self.style_shape = (M, D)
+
+    def eval(self, pred: torch.Tensor, content: torch.Tensor, alpha: float, want_grad: bool = True, want_argmin: bool = False):
+        pred = _check_features("prediction", reshape_2d(pred)).contiguous()
+        content = _check_features("content", reshape_2d(content)).contiguous()
+        if pred.shape != content.shape:
+            raise ValueError(f"prediction {tuple(pred.shape)} and content {tuple(content.shape)} must have the same shape")
+        N, D = pred.shape
+        if self.style_shape is None or self.style_shape[1] != D:
+            raise ValueError("style target not set or feature width differs from the prediction's")
+        scalars = torch.empty(_lib.NUM_SCALARS, device=pred.device, dtype=torch.float32)
+        grad = torch.empty_like(pred) if want_grad else None
+        ra = torch.empty(self.style_shape[0], device=pred.device, dtype=torch.int32) if want_argmin else None
+        ca = torch.empty(N, device=pred.device, dtype=torch.int32) if want_argmin else None
+        self._ck(self.lib.strotss_eval(self._h, _ptr(pred), pred.stride(0), _ptr(content), content.stride(0), N, float(alpha),
+                                       _ptr(scalars), _ptr(grad), D, _ptr(ra), _ptr(ca), _stream(pred.device)),
+                 "strotss_eval")
+        return scalars, grad, ra, ca
+
+    def eval_host(self, pred_host: torch.Tensor, content_host: torch.Tensor, alpha: float, grad_host: Optional[torch.Tensor],
+                  scalars_host: torch.Tensor):
+        """Host-buffer evaluation (bench e2e): tensors are CPU float32, ideally pinned."""
+        N, D = pred_host.shape
+        dev = self.device
+        self._ck(self.lib.strotss_eval_host(self._h, _ptr(pred_host), _ptr(content_host), N, float(alpha), _ptr(scalars_host),
+                                            _ptr(grad_host), _stream(dev)), "strotss_eval_host")
+
+    def style_loss(self, pred: torch.Tensor, alpha: float, want_grad: bool = True):
+        pred = _check_features("prediction", reshape_2d(pred)).contiguous()
+        N, D = pred.shape
+        if self.style_shape is None or self.style_shape[1] != D:
+            raise ValueError("style target not set or feature width differs from the prediction's")
+        scalars = torch.empty(_lib.NUM_SCALARS, device=pred.device, dtype=torch.float32)
+        grad = torch.empty_like(pred) if want_grad else None
+        self._ck(self.lib.strotss_style_loss(self._h, _ptr(pred), pred.stride(0), N, float(alpha), _ptr(scalars), _ptr(grad), D,
+                                             _stream(pred.device)), "strotss_style_loss")
+        return scalars, grad
+
+    # ---- per-function entry points ----------------------------------------------------
+    def relaxed_emd(self, x, y, distance: str, want_grad: bool, want_argmin: bool = False):
+        if distance not in _lib.DIST_CODES:
+            raise KeyError(distance)                      # nn/losses.py:74
+        x = _check_features("x", x).contiguous()
+        y = _check_features("y", y).contiguous()
+        if x.shape[1] != y.shape[1]:
+            raise ValueError("x and y must have the same number of channels")
+        M, D = x.shape
+        N = y.shape[0]
+        out = torch.empty(4, device=y.device, dtype=torch.float32)
+        grad = torch.empty_like(y) if want_grad else None
+        ra = torch.empty(M, device=y.device, dtype=torch.int32) if want_argmin else None
+        ca = torch.empty(N, device=y.device, dtype=torch.int32) if want_argmin else None
+        self._ck(self.lib.strotss_relaxed_emd(self._h, _ptr(x), x.stride(0), M, _ptr(y), y.stride(0), N, D,
+                                              _lib.DIST_CODES[distance], _ptr(out), _ptr(grad), D, _ptr(ra), _ptr(ca),
+                                              _stream(y.device)), "strotss_relaxed_emd")
+        return out, grad, ra, ca
+
+    def moment_matching(self, x, y, want_grad: bool):
+        x = _check_features("x", x).contiguous()
+        y = _check_features("y", y).contiguous()
+        if x.shape[1] != y.shape[1]:
+            raise ValueError("x and y must have the same number of channels")
+        M, D = x.shape
+        N = y.shape[0]
+        out = torch.empty(3, device=y.device, dtype=torch.float32)
+        grad = torch.empty_like(y) if want_grad else None
+        self._ck(self.lib.strotss_moment_matching(self._h, _ptr(x), x.stride(0), M, _ptr(y), y.stride(0), N, D, _ptr(out),
+                                                  _ptr(grad), D, _stream(y.device)), "strotss_moment_matching")
+        return out, grad
+
+    def self_similarity(self, x, y, want_grad: bool):
+        x = _check_features("x", x).contiguous()
+        y = _check_features("y", y).contiguous()
+        if x.shape != y.shape:
+            raise ValueError("self_similarity needs x and y of the same shape")
+        N, D = x.shape
+        out = torch.empty(1, device=x.device, dtype=torch.float32)
+        grad = torch.empty_like(x) if want_grad else None
+        self._ck(self.lib.strotss_self_similarity(self._h, _ptr(x), x.stride(0), _ptr(y), y.stride(0), N, D, _ptr(out),
+                                                  _ptr(grad), D, _stream(x.device)), "strotss_self_similarity")
+        return out, grad
+
+    def convert_rgb_to_yuv(self, x):
+        x = _check_features("x", x)
+        if x.dim() != 2 or x.shape[1] < 3:
+            raise ValueError("convert_rgb_to_yuv expects (n, >=3)")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        out = torch.empty(x.shape[0], 3, device=x.device, dtype=torch.float32)
+        self._ck(self.lib.strotss_convert_rgb_to_yuv(self._h, _ptr(x), x.stride(0), x.shape[0], _ptr(out), _stream(x.device)),
+                 "strotss_convert_rgb_to_yuv")
+        return out
+
+    def debug_gemm(self, A, B, alpha=1.0, tile_n=256):
+        A = _check_features("A", A).contiguous()
+        B = _check_features("B", B).contiguous()
+        m, k = A.shape
+        n = B.shape[0]
+        Cm = torch.empty(m, n, device=A.device, dtype=torch.float32)
+        self._ck(self.lib.strotss_debug_gemm(self._h, _ptr(A), m, _ptr(B), n, k, float(alpha), _ptr(Cm), tile_n, _stream(A.device)),
+                 "strotss_debug_gemm")
+        return Cm
+
+
+_shared: Dict[int, Handle] = {}
+
+
+def shared_handle(device: torch.device) -> Handle:
+    """Per-device handle used by the stateless functions of losses.py."""
+    if device.type != "cuda":
+        raise RuntimeError(f"tensor is on {device}: strotss_tensorflow_b200 runs on CUDA sm_100 only (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = _shared.get(idx)
+    if h is None:
+        h = Handle(torch.device("cuda", idx))
+        _shared[idx] = h
+    return h
