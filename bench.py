@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the STROTSS loss hot path (BASELINE.json metric: loss+grad evals/sec at
+N=M=16384, D=2179) on B200, with the CPU restatement of the reference timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload large|default]
+
+One "step" = one evaluation: total loss (self-similarity + moment matching + relaxed EMD + palette)
+and its gradient w.r.t. the (N, 2179) prediction hypercolumns, style-side preparation excluded
+(constant per scale, run_strotss.py:100,128).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_FEAT = 2179
+ALPHA = 16.0
+WORKLOADS = {
+    # name: (N, M)
+    "large": (16384, 16384),     # BASELINE.json configs[3]: large-sample loss microbench (the metric's config)
+    "default": (1024, 1024),     # reference default sample count (run_strotss.py:68)
+}
+
+
+def f_alg(N, M, D=D_FEAT):
+    """Algorithmic FLOPs per evaluation: no recompute / padding credit."""
+    return 2.0 * M * N * D + 2 * (2.0 * N * N * D) + 2.0 * N * N * D + 2 * (2.0 * N * D * D)
+
+
+def f_ref(N, M, D=D_FEAT):
+    """Dense FLOPs the reference's framework autodiff executes (5 fwd + 5 bwd GEMMs)."""
+    return 2 * (2.0 * M * N * D) + 4 * (2.0 * N * N * D) + 4 * (2.0 * N * D * D)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+def synth_torch(N, M, D, eps, seed, device):
+    """Synthetic hypercolumns of SURVEY.md section 8d (RGB in [0,1), ReLU-like heavy-tailed VGG channels)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    sigma = torch.exp(torch.randn(D - 3, generator=g, device=device))
+
+    def feats(n):
+        out = torch.empty(n, D, device=device, dtype=torch.float32)
+        out[:, :3] = torch.rand(n, 3, generator=g, device=device)
+        out[:, 3:] = torch.clamp_min(sigma[None, :] * (torch.randn(n, D - 3, generator=g, device=device) + 0.3), 0.0)
+        return out
+
+    style = feats(M)
+    content = feats(N)
+    noise = torch.randn(N, D, generator=g, device=device)
+    pred = torch.clamp_min(content + eps * content.abs().mean() * noise, 0.0)
+    return style, content, pred
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return None
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the torch-CPU port of the reference op sequence (oracle/torch_port.py)
+# ------------------------------------------------------------------------------------------
+def cpu_eval_seconds(n_sample, reps, warmup, threads):
+    import torch
+    from oracle import torch_port as T
+    torch.set_num_threads(threads)
+    st, co, pr = synth_torch(n_sample, n_sample, D_FEAT, 1.0, 0, torch.device("cpu"))
+    for _ in range(warmup):
+        T.total_loss_and_grad(st, co, pr, ALPHA)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        T.total_loss_and_grad(st, co, pr, ALPHA)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, N, M):
+    """`--impl reference`: the reference's own CPU path.  TensorFlow is not installable here, so this
+    times the CPU restatement of the reference op sequence (materialised matrices + framework
+    autodiff), all host threads, each step a bounded sample scaled by the reference FLOP ratio."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0))
+    n_s = min(N, 2048)
+    scale = f_ref(N, M) / f_ref(n_s, n_s)
+    times = cpu_eval_seconds(n_s, args.steps, args.warmup, threads)
+    t_step = sum(times) / len(times)
+    value = 1.0 / (t_step * scale)
+    sample = (f"torch-CPU port of nn/losses.py (fp32, materialised matrices, autograd), N=M={n_s} full evaluation per step, "
+              f"{threads} threads; evals/s scaled to N=M={N} by the reference FLOP ratio {scale:.2f}")
+    line = {
+        "impl": "reference", "metric": f"loss+grad evals/sec at N=M={N}, D={D_FEAT}", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA}", "sampled_as": f"N=M={n_s}"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
+    ap.add_argument("--eps", type=float, default=1.0, help="pred = content + eps*noise (SURVEY 8d)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    N, M = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference(args, N, M)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import strotss_tensorflow_b200 as S
+    from strotss_tensorflow_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # Replica mode: every rank evaluates its own (seeded per rank) problem of the full size.
+    style, content, pred = synth_torch(N, M, D_FEAT, args.eps, rank, dev)
+    h = S.Handle(dev)
+    h.set_style_target(style)
+    scalars = None
+    for _ in range(max(args.warmup, 3)):
+        scalars, grad, _, _ = h.eval(pred, content, ALPHA, True, False)
+    barrier()
+
+    # ---- device-resident timed region ------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    h.profile_enable(True)
+    h.profile_read()
+    l0 = h.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        scalars, grad, _, _ = h.eval(pred, content, ALPHA, True, False)
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = h.launch_count - l0
+    phases = h.profile_read()
+    h.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    total = float(scalars[_lib.S_TOTAL].item())
+
+    # ---- end to end through the host-buffer entry point ---------------------------------
+    ph = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory(); ph.copy_(pred)
+    ch = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory(); ch.copy_(content)
+    gh = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory()
+    sh = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32)
+    for _ in range(2):
+        h.eval_host(ph, ch, ALPHA, gh, sh)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h.eval_host(ph, ch, ALPHA, gh, sh)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    value = world * 1000.0 / ms_step
+    # dominant kernel: self-similarity stage 1 (one launch per 2048-row panel)
+    ss1_ms, ss1_n = phases.get("ss_stage1_gemm", (0.0, 0))
+    panel_rows = min(2048, N)
+    alg_flops_launch = 2 * (2.0 * panel_rows * N * D_FEAT)          # Xd and Yd tiles of one row panel
+    ach = alg_flops_launch / (ss1_ms / max(ss1_n, 1) * 1e-3) / 1e12 if ss1_n else None
+    roof = {"bound": "tensor", "kernel": "gemm_kernel<128,2,6,EpiSS1> (self-similarity stage 1)",
+            "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
+            "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+            "executed_over_algorithmic": 1.5,
+            "note": "algorithmic = 2 GEMMs (Xd, Yd) per panel; the delta form executes 3 bf16 K passes"}
+    line = {
+        "metric": f"loss+grad evals/sec at N=M={N}, D={D_FEAT}", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}"
+                   if args.workload == "large" else f"default sample count N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one problem per GPU)",
+                   "l2": "inputs (3 x %.0f MB fp32) exceed the 126 MB L2; no flush" % (N * D_FEAT * 4 / 1e6)
+                   if N * D_FEAT * 4 * 3 > 126e6 else "inputs fit in L2 (launch-bound regime)",
+                   "precision": "bf16 operands (delta-form self-similarity), fp32 accumulate/reductions"},
+        "clocks": clocks,
+        "e2e": {"value": world * 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 2 * N * D_FEAT * 4, "d2h_bytes_per_step": N * D_FEAT * 4 + _lib.NUM_SCALARS * 4},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "whole_eval": {"f_alg": f_alg(N, M), "tflops_alg": f_alg(N, M) / (ms_step * 1e-3) / 1e12,
+                       "frac_of_burst_peak": f_alg(N, M) / (ms_step * 1e-3) / 1e12 / pk["tf_burst"],
+                       "frac_of_sustained_peak": f_alg(N, M) / (ms_step * 1e-3) / 1e12 / pk["tf_sust"]},
+        "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in phases.items()},
+        "loss": total,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        n_s = min(N, 2048)
+        t_probe = cpu_eval_seconds(n_s, 1, 1, threads)[0]
+        if N >= 4096 and t_probe * (f_ref(4096, 4096) / f_ref(n_s, n_s)) < 12.0:
+            n_s = 4096
+        reps = 2 if n_s == 4096 else 5
+        times = cpu_eval_seconds(n_s, reps, 0, threads)
+        t = sum(times) / len(times)
+        scale = f_ref(N, M) / f_ref(n_s, n_s)
+        line["cpu_baseline"] = {
+            "value": 1.0 / (t * scale), "unit": "evals/s", "cores": threads, "kind": "port",
+            "sample": f"torch-CPU port of the reference op sequence (fp32, materialised matrices, autograd), {reps} evaluations at "
+                      f"N=M={n_s} ({t:.2f} s each), scaled to N=M={N} by the reference FLOP ratio {scale:.2f}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,15 @@ size_t strotss_workspace_bytes(strotss_handle h);
 /* kernels launched by this handle since creation (the bench's gpu_launches counter) */
 long long strotss_launch_count(strotss_handle h);
 
+/* Optional per-phase timing (the reference has only a whole-run wall clock, nn/utils.py:97-114):
+ * when enabled, every launch group is bracketed by CUDA events on the launching stream.
+ * strotss_profile_read synchronises on them, fills ms_sum[i] / counts[i] for
+ * i < strotss_profile_num_phases() and clears the records. */
+int strotss_profile_enable(strotss_handle h, int on);
+int strotss_profile_num_phases(void);
+const char* strotss_profile_phase_name(int i);
+int strotss_profile_read(strotss_handle h, double* ms_sum, long long* counts);
+
 /* StyleLoss.__init__(target, alpha) (run_strotss.py:28-31): fix the style target for a scale.
  * Caches what the reference recomputes every iteration (nn/losses.py:43,49; run_strotss.py:37):
  * normalised bf16 operand, column mean, covariance, YUV records.  style: M x D, row stride ld. */

@@ -25,6 +25,10 @@ SIGNATURES = {
     "strotss_version": (C.c_char_p, []),
     "strotss_workspace_bytes": (C.c_size_t, [_vp]),
     "strotss_launch_count": (_ll, [_vp]),
+    "strotss_profile_enable": (_i, [_vp, _i]),
+    "strotss_profile_num_phases": (_i, []),
+    "strotss_profile_phase_name": (C.c_char_p, [_i]),
+    "strotss_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll)]),
     "strotss_set_style_target": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "strotss_eval": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _f, _vp, _vp, _ll, _vp, _vp, _vp]),
     "strotss_eval_host": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),

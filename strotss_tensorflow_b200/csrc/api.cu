@@ -48,6 +48,13 @@ __global__ void copy_scalars_kernel(const float* __restrict__ src, const int* __
 
 }  // namespace
 
+// Phases timed with CUDA events on the launching stream when profiling is enabled.
+enum Phase { PH_PREP = 0, PH_REMD_GEMM, PH_REMD_MISC, PH_PALETTE, PH_COV_FWD, PH_COV_BWD, PH_MOM_MISC, PH_SS_VEC, PH_SS1, PH_SS2,
+             PH_SS_MISC, PH_FINALIZE, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"prep", "remd_gemm", "remd_misc", "palette", "cov_fwd_gemm", "cov_bwd_gemm", "moment_misc",
+                                            "ss_vectors", "ss_stage1_gemm", "ss_stage2_gemm", "ss_misc", "finalize"};
+struct PhaseRec { int id; cudaEvent_t a, b; };
+
 // Prepared operands of one (n x D) fp32 feature matrix.
 struct Feat {
     const float* x = nullptr; long long ld = 0; int n = 0; int np = 0;
@@ -71,10 +78,16 @@ struct strotss_ctx {
     float* Vx = nullptr;
     // host pinned staging for scalar read-back
     float* h_scalars = nullptr;
+    // optional per-phase CUDA-event timing
+    bool profiling = false;
+    std::vector<PhaseRec> recs;
+    std::vector<cudaEvent_t> pool;
 
     ~strotss_ctx() {
         for (auto& kv : bufs) cudaFree(kv.second.first);
         if (h_scalars) cudaFreeHost(h_scalars);
+        for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto& e : pool) cudaEventDestroy(e);
     }
 };
 
@@ -100,6 +113,18 @@ struct strotss_ctx {
     do { int _r = (expr); if (_r != 0) return _r; } while (0)
 
 namespace {
+
+struct PhaseTimer {
+    strotss_ctx* h; cudaStream_t st; PhaseRec r; bool on;
+    static cudaEvent_t get(strotss_ctx* h) {
+        if (!h->pool.empty()) { cudaEvent_t e = h->pool.back(); h->pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    PhaseTimer(strotss_ctx* h_, int id, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling) {
+        if (on) { r.id = id; r.a = get(h); r.b = get(h); cudaEventRecord(r.a, st); }
+    }
+    ~PhaseTimer() { if (on) { cudaEventRecord(r.b, st); h->recs.push_back(r); } }
+};
 
 // grow-only named device buffer
 template <class T>
@@ -158,6 +183,7 @@ struct PrepWant { bool mean, sumhat, xh, cen, dlt, xhT, cenT, rec; };
 
 int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long ld, int n, int D, int Dp,
                   const PrepWant& w, const Feat* other /* for dlt */, int rec_convert, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_PREP, st);
     f.x = x; f.ld = ld; f.n = n; f.np = round_up(n, 64);
     const std::string t(tag);
     const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
@@ -194,6 +220,7 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
 
 // ---- covariance of a prepared feature set:  V = cenT . cenT^T / n  ---------------------
 int cov_store(strotss_ctx* h, const Feat& f, int D, int Dp, float* V, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_COV_FWD, st);
     GemmParams<EpiStoreT<256>> p{};
     RET(make_tmap(h, &p.tmA[0], f.cenT, D, f.np, f.np, BM));
     RET(make_tmap(h, &p.tmB[0], f.cenT, D, f.np, f.np, 256));
@@ -219,7 +246,8 @@ int remd_cosine(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int
     p.nseg = 1; p.seg_kblocks[0] = Dp / BK; p.seg_acc[0] = 0;
     p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + 255) / 256;
     p.epi.rowbest = out.rowbest; p.epi.colbest = out.colbest; p.epi.M = M; p.epi.N = N;
-    RET((launch_gemm<256, 1, 4>(h, p, st)));
+    { PhaseTimer _pt(h, PH_REMD_GEMM, st); RET((launch_gemm<256, 1, 4>(h, p, st))); }
+    PhaseTimer _pm(h, PH_REMD_MISC, st);
     remd_finish_kernel<<<1, 1024, 0, st>>>(out.rowbest, M, out.colbest, N, 1.f, scalars, slot_loss, slot_rx, slot_ry,
                                            slot_branch, row_arg, col_arg);
     CKL();
@@ -239,6 +267,7 @@ int remd_cosine(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int
 int remd_small(strotss_ctx* h, const float* arec, int M, const float* brec, int N, int mode, int convert, float* scalars,
                int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, float** gpal,
                int32_t* row_arg, int32_t* col_arg, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_PALETTE, st);
     unsigned long long *rowbest, *colbest;
     RET(ensure(h, "pal.rowbest", (size_t)M, &rowbest));
     RET(ensure(h, "pal.colbest", (size_t)N, &colbest));
@@ -289,10 +318,13 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     RET(ensure(h, "mom.part", (size_t)npart, &part));
     p.epi.Vx = Vx; p.epi.ldv = Dp; p.epi.Sg = Sg; p.epi.lds = Dp; p.epi.part = part; p.epi.inv_n = 1.f / N; p.epi.D = D;
     p.epi.tiles_n = p.tiles_n;
-    RET((launch_gemm<256, 1, 4>(h, p, st)));
+    { PhaseTimer _pt(h, PH_COV_FWD, st); RET((launch_gemm<256, 1, 4>(h, p, st))); }
     RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
-    moment_finish_kernel<<<1, 1024, 0, st>>>(pred.mean, mu_x, D, part, npart, out.gmu, scalars);
-    CKL();
+    {
+        PhaseTimer _pt(h, PH_MOM_MISC, st);
+        moment_finish_kernel<<<1, 1024, 0, st>>>(pred.mean, mu_x, D, part, npart, out.gmu, scalars);
+        CKL();
+    }
     out.Q = nullptr; out.ldq = 0; out.q_scale = 0.f;
     if (want_grad) {
         // Q = cen . (G + G^T) / N with G = sign(V_y - V_x)/D^2 symmetric  ->  q_scale * (cen . Sg^T)
@@ -304,6 +336,7 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
         q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
         q.tiles_m = (N + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
         q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = N; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = 0;
+        PhaseTimer _pt(h, PH_COV_BWD, st);
         RET((launch_gemm<256, 1, 4>(h, q, st)));
     }
     return 0;
@@ -318,8 +351,11 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
     RET(ensure(h, "ss.u", (size_t)N, &u));
     RET(ensure(h, "ss.w", (size_t)N, &w));
     RET(ensure(h, "ss.sclamp", (size_t)N, &sclamp));
-    ss_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
-    CKL();
+    {
+        PhaseTimer _pt(h, PH_SS_VEC, st);
+        ss_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
+        CKL();
+    }
     const int tiles_n = (N + 127) / 128;
     RET(ensure(h, "ss.loss_part", (size_t)tiles_n * N, &loss_part));
     RET(ensure(h, "ss.r_part", (size_t)tiles_n * N, &r_part));
@@ -353,7 +389,7 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
         p.a_row0 = r0; p.b_row0 = 0;
         p.epi.u = u; p.epi.w = w; p.epi.P = P; p.epi.ldp = np; p.epi.panel_row0 = r0;
         p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.write_p = want_grad ? 1 : 0;
-        RET((launch_gemm<128, 2, 6>(h, p, st)));
+        { PhaseTimer _pt(h, PH_SS1, st); RET((launch_gemm<128, 2, 6>(h, p, st))); }
         if (want_grad) {
             GemmParams<EpiStoreT<256>> q{};
             RET(make_tmap(h, &q.tmA[0], P, rows, np, np, BM));
@@ -363,9 +399,11 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
             q.a_row0 = 0; q.b_row0 = 0;
             q.epi.C = out.ss2 + static_cast<long long>(r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
             q.epi.alpha = 1.f; q.epi.row_off = 0;
+            PhaseTimer _pt(h, PH_SS2, st);
             RET((launch_gemm<256, 1, 4>(h, q, st)));
         }
     }
+    PhaseTimer _pm(h, PH_SS_MISC, st);
     ss_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(loss_part, r_part, tiles_n, N, u, sclamp, out.coef, rowloss);
     CKL();
     reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss, N, 1.f / N, loss_out);
@@ -384,6 +422,7 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
 }
 
 int finalize(strotss_ctx* h, const FinalizeArgs& a, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_FINALIZE, st);
     finalize_grad_kernel<<<a.N, 256, sizeof(float) * a.D, st>>>(a);
     CKL();
     return 0;
@@ -434,6 +473,31 @@ const char* strotss_last_error(strotss_handle h) { return h ? h->err.c_str() : "
 size_t strotss_workspace_bytes(strotss_handle h) { return h ? h->ws_bytes : 0; }
 
 long long strotss_launch_count(strotss_handle h) { return h ? h->launches : 0; }
+
+int strotss_profile_enable(strotss_handle h, int on) {
+    RET(check_handle(h));
+    h->profiling = on != 0;
+    return 0;
+}
+
+int strotss_profile_num_phases(void) { return PH_COUNT; }
+
+const char* strotss_profile_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
+
+int strotss_profile_read(strotss_handle h, double* ms_sum, long long* counts) {
+    RET(check_handle(h));
+    if (!ms_sum || !counts) { h->err = "profile_read: bad argument"; return STROTSS_ERR_ARG; }
+    for (int i = 0; i < PH_COUNT; ++i) { ms_sum[i] = 0.0; counts[i] = 0; }
+    for (auto& r : h->recs) {
+        CK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_sum[r.id] += ms; counts[r.id] += 1;
+        h->pool.push_back(r.a); h->pool.push_back(r.b);
+    }
+    h->recs.clear();
+    return 0;
+}
 
 int strotss_set_style_target(strotss_handle h, const float* style, int M, int D, long long ld, void* stream) {
     RET(check_handle(h));

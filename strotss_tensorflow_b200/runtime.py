@@ -78,6 +78,17 @@ class Handle:
     def workspace_bytes(self) -> int:
         return int(self.lib.strotss_workspace_bytes(self._h))
 
+    def profile_enable(self, on: bool = True):
+        self._ck(self.lib.strotss_profile_enable(self._h, 1 if on else 0), "strotss_profile_enable")
+
+    def profile_read(self):
+        """-> {phase: (total_ms, launches)} since the last read (synchronises on the recorded events)."""
+        n = self.lib.strotss_profile_num_phases()
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        self._ck(self.lib.strotss_profile_read(self._h, ms, cnt), "strotss_profile_read")
+        return {self.lib.strotss_profile_phase_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}
+
     # ---- fused path -----------------------------------------------------------------
     def set_style_target(self, style: torch.Tensor):
         style = _check_features("style target", reshape_2d(style)).contiguous()
