@@ -261,7 +261,7 @@ def main():
     panel_rows = min(2048, N)
     alg_flops_launch = 2 * (2.0 * panel_rows * N * D_FEAT)          # Xd and Yd tiles of one row panel
     ach = alg_flops_launch / (ss1_ms / max(ss1_n, 1) * 1e-3) / 1e12 if ss1_n else None
-    roof = {"bound": "tensor", "kernel": "gemm_kernel<128,2,6,EpiSS1> (self-similarity stage 1)",
+    roof = {"bound": "tensor", "kernel": "gemm_kernel<256,2,4,8,EpiSS1<256,8>> (self-similarity stage 1)",
             "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
             "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "executed_over_algorithmic": 1.5,

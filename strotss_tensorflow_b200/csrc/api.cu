@@ -159,12 +159,12 @@ int make_tmap(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int rows, int kc
     return 0;
 }
 
-template <int BN, int NACC, int STAGES, class Epi>
+template <int BN, int NACC, int STAGES, int EPI_WARPS = 4, class Epi>
 int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     using Cfg = TileCfg<BN, NACC>;
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    auto kern = gemm_kernel<BN, NACC, STAGES, Epi>;
+    auto kern = gemm_kernel<BN, NACC, STAGES, EPI_WARPS, Epi>;
     static bool configured = false;
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -172,8 +172,18 @@ int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     }
     const int tiles = p.tiles_m * p.tiles_n;
     if (tiles <= 0) return 0;
+    // L2 blocking: a group of column tiles holds ~32 MB of B operand (all segments)
+    GemmParams<Epi> q = p;
+    {
+        long long kbytes = 0;
+        for (int s = 0; s < p.nseg; ++s) kbytes += static_cast<long long>(p.seg_kblocks[s]) * BK * 2;
+        long long g = (32ll << 20) / (kbytes * BN);
+        if (g < 4) g = 4;
+        if (g > p.tiles_n) g = p.tiles_n;
+        q.group_n = static_cast<int>(g);
+    }
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    kern<<<grid, kGemmThreads, smem, st>>>(p);
+    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
     CKL();
     return 0;
 }
@@ -273,21 +283,21 @@ int remd_small(strotss_ctx* h, const float* arec, int M, const float* brec, int 
     RET(ensure(h, "pal.colbest", (size_t)N, &colbest));
     CK(cudaMemsetAsync(rowbest, 0, sizeof(unsigned long long) * M, st));
     CK(cudaMemsetAsync(colbest, 0, sizeof(unsigned long long) * N, st));
-    auto launch = [&](const float* q, int nq, const float* k, int nk, int swap, unsigned long long* best) -> int {
-        const int qblocks = (nq + 127) / 128;
-        int ks = (2 * h->num_sms + qblocks - 1) / qblocks;        // aim for >= 2 waves of blocks
-        const int maxks = (nk + 255) / 256;
+    auto launch = [&](const float* q, int nq, const float* k, int nk, unsigned long long* best) -> int {
+        const int qblocks = (nq + kPalThreads * kPalQT - 1) / (kPalThreads * kPalQT);
+        int ks = (4 * h->num_sms + qblocks - 1) / qblocks;        // aim for ~4 blocks per SM
+        const int maxks = (nk + kPalKeyTile - 1) / kPalKeyTile;
         if (ks > maxks) ks = maxks;
         if (ks < 1) ks = 1;
-        int kchunk = round_up((nk + ks - 1) / ks, 256);
+        const int kchunk = round_up((nk + ks - 1) / ks, kPalKeyTile);
         ks = (nk + kchunk - 1) / kchunk;
         dim3 grid(qblocks, ks);
-        pal_min_kernel<<<grid, 128, 0, st>>>(q, nq, k, nk, kchunk, mode, swap, best);
+        pal_min_kernel<<<grid, kPalThreads, 0, st>>>(q, nq, k, nk, kchunk, mode, best);
         CKL();
         return 0;
     };
-    RET(launch(arec, M, brec, N, 0, rowbest));
-    RET(launch(brec, N, arec, M, 1, colbest));
+    RET(launch(arec, M, brec, N, rowbest));
+    RET(launch(brec, N, arec, M, colbest));
     remd_finish_kernel<<<1, 1024, 0, st>>>(rowbest, M, colbest, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
                                            row_arg, col_arg);
     CKL();
@@ -314,7 +324,7 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     RET(make_tmap(h, &p.tmB[0], pred.cenT, D, pred.np, pred.np, 256));
     p.nseg = 1; p.seg_kblocks[0] = pred.np / BK; p.seg_acc[0] = 0;
     p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
-    const int npart = p.tiles_m * p.tiles_n * 4;
+    const int npart = p.tiles_m * p.tiles_n * 4;      // 4 epilogue warps
     RET(ensure(h, "mom.part", (size_t)npart, &part));
     p.epi.Vx = Vx; p.epi.ldv = Dp; p.epi.Sg = Sg; p.epi.lds = Dp; p.epi.part = part; p.epi.inv_n = 1.f / N; p.epi.D = D;
     p.epi.tiles_n = p.tiles_n;
@@ -356,9 +366,11 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
         ss_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
         CKL();
     }
-    const int tiles_n = (N + 127) / 128;
-    RET(ensure(h, "ss.loss_part", (size_t)tiles_n * N, &loss_part));
-    RET(ensure(h, "ss.r_part", (size_t)tiles_n * N, &r_part));
+    constexpr int kSsBN = 256, kSsEpiWarps = 8, kSsSplit = kSsEpiWarps / 4;
+    const int tiles_n = (N + kSsBN - 1) / kSsBN;
+    const int nslots = tiles_n * kSsSplit;
+    RET(ensure(h, "ss.loss_part", (size_t)nslots * N, &loss_part));
+    RET(ensure(h, "ss.r_part", (size_t)nslots * N, &r_part));
     RET(ensure(h, "ss.rowloss", (size_t)N, &rowloss));
     RET(ensure(h, "ss.coef", (size_t)N, &out.coef));
     const int np = x.np;
@@ -374,14 +386,14 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
     }
     for (int r0 = 0; r0 < N; r0 += panel) {
         const int rows = (N - r0 < panel) ? (N - r0) : panel;
-        GemmParams<EpiSS1> p{};
+        GemmParams<EpiSS1<kSsBN, kSsEpiWarps>> p{};
         // segment 0: delta_I . x^_J ; segment 1: y^_I . delta_J  (both into acc 0) ; segment 2: y^_I . y^_J (acc 1)
         RET(make_tmap(h, &p.tmA[0], x.dlt, N, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[0], x.xh, N, Dp, Dp, 128));
+        RET(make_tmap(h, &p.tmB[0], x.xh, N, Dp, Dp, kSsBN));
         RET(make_tmap(h, &p.tmA[1], y.xh, N, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[1], x.dlt, N, Dp, Dp, 128));
+        RET(make_tmap(h, &p.tmB[1], x.dlt, N, Dp, Dp, kSsBN));
         RET(make_tmap(h, &p.tmA[2], y.xh, N, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[2], y.xh, N, Dp, Dp, 128));
+        RET(make_tmap(h, &p.tmB[2], y.xh, N, Dp, Dp, kSsBN));
         p.nseg = 3;
         for (int s = 0; s < 3; ++s) p.seg_kblocks[s] = Dp / BK;
         p.seg_acc[0] = 0; p.seg_acc[1] = 0; p.seg_acc[2] = 1;
@@ -389,7 +401,7 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
         p.a_row0 = r0; p.b_row0 = 0;
         p.epi.u = u; p.epi.w = w; p.epi.P = P; p.epi.ldp = np; p.epi.panel_row0 = r0;
         p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.write_p = want_grad ? 1 : 0;
-        { PhaseTimer _pt(h, PH_SS1, st); RET((launch_gemm<128, 2, 6>(h, p, st))); }
+        { PhaseTimer _pt(h, PH_SS1, st); RET((launch_gemm<kSsBN, 2, 4, kSsEpiWarps>(h, p, st))); }
         if (want_grad) {
             GemmParams<EpiStoreT<256>> q{};
             RET(make_tmap(h, &q.tmA[0], P, rows, np, np, BM));
@@ -404,7 +416,7 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
         }
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
-    ss_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(loss_part, r_part, tiles_n, N, u, sclamp, out.coef, rowloss);
+    ss_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, u, sclamp, out.coef, rowloss);
     CKL();
     reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss, N, 1.f / N, loss_out);
     CKL();

@@ -18,8 +18,7 @@ namespace sb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kNonEpiThreads = 128;           // warps 0..3: TMA, MMA, TMEM alloc, spare
 constexpr int kMaxSeg = 3;
 constexpr int kSmemBudget = 232448 - 1024;   // 227 KB minus alignment slack
 
@@ -41,6 +40,7 @@ struct GemmParams {
     int seg_kblocks[kMaxSeg];
     int seg_acc[kMaxSeg];
     int tiles_m, tiles_n;
+    int group_n;                 // raster: column tiles are swept in groups of group_n (L2 blocking)
     int a_row0, b_row0;          // element row where tile (0,0) starts in A / B
     typename Epi::Params epi;
 };
@@ -48,18 +48,37 @@ struct GemmParams {
 struct TileInfo {
     int tm, tn;                  // tile indices
     int row0, col0;              // a_row0 + tm*BM, b_row0 + tn*BN  (global element coordinates)
-    int q, lane;                 // epilogue warp (TMEM lane quadrant) and lane
+    int q, lane;                 // TMEM lane quadrant (= warp % 4) and lane
+    int w, nw;                   // epilogue warp index and count (4 or 8)
+    int csplit, nsplit;          // with 8 epilogue warps the BN columns are split in two halves
+    int c0, c1;                  // range of 32-column chunks this warp handles
+    int tid;                     // thread index within the epilogue group
     uint32_t taddr;              // TMEM address of accumulator 0, this warp's lane quadrant
     int tile_seq;                // running count of tiles processed by this CTA
 };
 
-__device__ __forceinline__ void epi_bar_sync() {
-    asm volatile("bar.sync 1, %0;" :: "n"(kEpiThreads) : "memory");
+// Tile order: for each group of group_n column tiles, sweep all row tiles, column tile fastest.
+// CTAs that run concurrently then share a few A row blocks and one group of B column blocks, so
+// both stay L2-resident instead of B being re-streamed from HBM for every row block.
+template <class P>
+__device__ __forceinline__ void decode_tile(const P& p, int t, int& tm, int& tn) {
+    const int gsz = p.tiles_m * p.group_n;
+    const int tg = t / gsz;
+    const int r = t - tg * gsz;
+    const int gn = min(p.group_n, p.tiles_n - tg * p.group_n);
+    tm = r / gn;
+    tn = tg * p.group_n + (r - tm * gn);
 }
 
-template <int BN, int NACC, int STAGES, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int NT>
+__device__ __forceinline__ void epi_bar_sync() {
+    asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory");
+}
+
+template <int BN, int NACC, int STAGES, int EPI_WARPS, class Epi>
+__global__ void __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
 gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
     using Cfg = TileCfg<BN, NACC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -79,7 +98,7 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < Cfg::ACC_STAGES; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < Cfg::ACC_STAGES; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -94,7 +113,8 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+                int tm, tn;
+                decode_tile(p, t, tm, tn);
                 const int arow = p.a_row0 + tm * BM, brow = p.b_row0 + tn * BN;
                 for (int s = 0; s < p.nseg; ++s) {
                     for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
@@ -143,16 +163,21 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;
+        const int q = warp & 3;
         int as = 0; uint32_t aphase = 0;
         int seq = 0;
         typename Epi::State st;
         Epi::init(st, p.epi, q, lane);
+        constexpr int kSplit = EPI_WARPS / 4;
+        constexpr int kChunks = BN / 32 / kSplit;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++seq) {
             TileInfo ti;
-            ti.tm = t / p.tiles_n; ti.tn = t % p.tiles_n;
+            decode_tile(p, t, ti.tm, ti.tn);
             ti.row0 = p.a_row0 + ti.tm * BM; ti.col0 = p.b_row0 + ti.tn * BN;
             ti.q = q; ti.lane = lane; ti.tile_seq = seq;
+            ti.w = warp - 4; ti.nw = EPI_WARPS; ti.csplit = (warp - 4) >> 2; ti.nsplit = kSplit;
+            ti.c0 = ti.csplit * kChunks; ti.c1 = ti.c0 + kChunks;
+            ti.tid = threadIdx.x - kNonEpiThreads;
             ti.taddr = tmem_base + as * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             Epi::prologue(st, p.epi, ti, epi_smem);      // may overlap the MMAs of this tile
             mbar_wait(&tfull[as], aphase);
@@ -189,7 +214,7 @@ struct EpiStore {
         const bool rvalid = row < P.rows;
         float* crow = P.C + static_cast<long long>(row - P.row_off) * P.ldc;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = ti.c0; c < ti.c1; ++c) {
             uint32_t r[32];
             tmem_ld32(ti.taddr + c * 32, r);
             tmem_ld_wait();
@@ -233,7 +258,7 @@ struct EpiRemd {
         float best_v = -INFINITY;
         int best_j = 0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = ti.c0; c < ti.c1; ++c) {
             uint32_t r[32];
             tmem_ld32(ti.taddr + c * 32, r);
             tmem_ld_wait();
@@ -268,14 +293,15 @@ struct EpiRemd {
 // row form     term'_ij = term_ji               = diff*u_i + Yd*w_i      (Xd, Yd symmetric)
 // loss_i += |term'_ij|,  r_i += sign(term'_ij) * Xd_ij,  P_ij = sign(term_ij)*u_j + sign(term'_ij)*u_i
 // P (bf16) goes to the L2-resident row panel that stage 2 multiplies with x^.
+template <int BN_, int EPI_WARPS>
 struct EpiSS1 {
-    static constexpr int BN = 128;
+    static constexpr int BN = BN_;
     static constexpr int SMEM_BYTES = 2 * 2 * BN * sizeof(float);
     struct Params {
         const float* u; const float* w;       // per sample, length N
         __nv_bfloat16* P; long long ldp;      // panel, row stride (elements), panel starts at row panel_row0
         int panel_row0;
-        float* loss_part; float* r_part;      // [tiles_n_total][N]
+        float* loss_part; float* r_part;      // [tiles_n * nsplit][N]
         int N;
         int write_p;
     };
@@ -284,11 +310,12 @@ struct EpiSS1 {
     __device__ static void finish(State&, const Params&, int, int) {}
     __device__ static void prologue(State&, const Params& P, const TileInfo& ti, uint8_t* sm) {
         float* buf = reinterpret_cast<float*>(sm) + (ti.tile_seq & 1) * 2 * BN;
-        const int t = ti.q * 32 + ti.lane;
-        const int col = ti.col0 + t;
-        buf[t] = (col < P.N) ? P.u[col] : 0.f;
-        buf[BN + t] = (col < P.N) ? P.w[col] : 0.f;
-        epi_bar_sync();
+        for (int t = ti.tid; t < BN; t += 32 * EPI_WARPS) {
+            const int col = ti.col0 + t;
+            buf[t] = (col < P.N) ? P.u[col] : 0.f;
+            buf[BN + t] = (col < P.N) ? P.w[col] : 0.f;
+        }
+        epi_bar_sync<32 * EPI_WARPS>();
     }
     __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t* sm) {
         const float* su = reinterpret_cast<const float*>(sm) + (ti.tile_seq & 1) * 2 * BN;
@@ -300,7 +327,7 @@ struct EpiSS1 {
         float loss = 0.f, racc = 0.f;
         __nv_bfloat16* prow = P.P + static_cast<long long>(row - P.panel_row0) * P.ldp;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = ti.c0; c < ti.c1; ++c) {
             uint32_t a0[32], a1[32];
             tmem_ld32(ti.taddr + c * 32, a0);
             tmem_ld32(ti.taddr + BN + c * 32, a1);
@@ -337,8 +364,9 @@ struct EpiSS1 {
             }
         }
         if (rvalid) {
-            P.loss_part[static_cast<long long>(ti.tn) * P.N + row] = loss;
-            P.r_part[static_cast<long long>(ti.tn) * P.N + row] = racc;
+            const long long slot = static_cast<long long>(ti.tn) * ti.nsplit + ti.csplit;
+            P.loss_part[slot * P.N + row] = loss;
+            P.r_part[slot * P.N + row] = racc;
         }
     }
 };
@@ -365,7 +393,7 @@ struct EpiCovFwd {
         __nv_bfloat16* srow = P.Sg + static_cast<long long>(row) * P.lds;
         float part = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = ti.c0; c < ti.c1; ++c) {
             uint32_t r[32];
             tmem_ld32(ti.taddr + c * 32, r);
             tmem_ld_wait();
@@ -402,7 +430,7 @@ struct EpiCovFwd {
             }
         }
         part = warp_sum(part);
-        if (ti.lane == 0) P.part[(static_cast<long long>(ti.tm) * P.tiles_n + ti.tn) * 4 + ti.q] = part;
+        if (ti.lane == 0) P.part[(static_cast<long long>(ti.tm) * P.tiles_n + ti.tn) * ti.nw + ti.w] = part;
     }
 };
 

@@ -323,39 +323,65 @@ __global__ void pal_prep_kernel(const float* __restrict__ x, long long ld, int n
     o[0] = y; o[1] = u; o[2] = v; o[3] = y * iv; o[4] = u * iv; o[5] = v * iv; o[6] = sq; o[7] = iv;
 }
 
-// cost of one (a, b) pair for distance mode: 0 cosine, 1 l2, 2 both   (3 channels)
-__device__ __forceinline__ float pal_cost(const float* a, const float* b, int mode) {
-    float c = 0.f;
-    if (mode != 1) c = 1.f - (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
-    if (mode != 0) {
-        const float m = a[6] + b[6] - 2.f * (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
-        c += sqrtf(fmaxf(m, kL2DClamp) / 3.f);
-    }
-    return c;
-}
-
 // best[q] = max over keys of -cost(q, key)  (packed; ties -> lowest key index).
-// swap = 1 evaluates cost(key, query) so both directions see the same operand order as the reference.
-__global__ void __launch_bounds__(128) pal_min_kernel(const float* __restrict__ qrec, int nq, const float* __restrict__ krec, int nk,
-                                                      int kchunk, int mode, int swap, unsigned long long* __restrict__ best) {
-    __shared__ float sk[256 * 8];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    float a[8];
+// Each thread owns kPalQT queries (register blocking), keys stream through shared memory as float4
+// pairs, and the key range is split over blockIdx.y so the grid fills the chip.
+// sqrt.approx (MUFU, <= 1 ulp-class error): the candidate search needs ordering, not the last bit;
+// remd_finish recomputes nothing from it beyond the selected minimum (relative error ~1e-7).
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+constexpr int kPalQT = 4;
+constexpr int kPalThreads = 128;
+constexpr int kPalKeyTile = 256;
+
+__global__ void __launch_bounds__(kPalThreads) pal_min_kernel(const float* __restrict__ qrec, int nq, const float* __restrict__ krec, int nk,
+                                                              int kchunk, int mode, unsigned long long* __restrict__ best) {
+    __shared__ float4 sk[kPalKeyTile * 2];
+    float a[kPalQT][8];
+    float bv[kPalQT];
+    int bi[kPalQT];
+    const int qbase = blockIdx.x * (kPalThreads * kPalQT) + threadIdx.x;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = (q < nq) ? qrec[static_cast<long long>(q) * 8 + e] : 0.f;
+    for (int t = 0; t < kPalQT; ++t) {
+        const int q = qbase + t * kPalThreads;
+        const float4* src = reinterpret_cast<const float4*>(qrec + static_cast<long long>(q < nq ? q : 0) * 8);
+        const float4 v0 = src[0], v1 = src[1];
+        a[t][0] = v0.x; a[t][1] = v0.y; a[t][2] = v0.z; a[t][3] = v0.w;
+        a[t][4] = v1.x; a[t][5] = v1.y; a[t][6] = v1.z; a[t][7] = v1.w;
+        bv[t] = INFINITY; bi[t] = 0;
+    }
     const int k0 = blockIdx.y * kchunk, k1 = min(nk, k0 + kchunk);
-    float bv = INFINITY; int bi = 0;
-    for (int kb = k0; kb < k1; kb += 256) {
-        const int cnt = min(256, k1 - kb);
+    for (int kb = k0; kb < k1; kb += kPalKeyTile) {
+        const int cnt = min(kPalKeyTile, k1 - kb);
         __syncthreads();
-        for (int e = threadIdx.x; e < cnt * 8; e += blockDim.x) sk[e] = krec[static_cast<long long>(kb) * 8 + e];
+        const float4* ksrc = reinterpret_cast<const float4*>(krec + static_cast<long long>(kb) * 8);
+        for (int e = threadIdx.x; e < cnt * 2; e += kPalThreads) sk[e] = ksrc[e];
         __syncthreads();
+#pragma unroll 2
         for (int k = 0; k < cnt; ++k) {
-            const float c = swap ? pal_cost(sk + k * 8, a, mode) : pal_cost(a, sk + k * 8, mode);
-            if (c < bv) { bv = c; bi = kb + k; }
+            const float4 b0 = sk[2 * k], b1 = sk[2 * k + 1];       // (y,u,v,y^) (u^,v^,|.|^2,inv)
+#pragma unroll
+            for (int t = 0; t < kPalQT; ++t) {
+                float c = 0.f;
+                if (mode != 1) c = 1.f - (a[t][3] * b0.w + a[t][4] * b1.x + a[t][5] * b1.y);
+                if (mode != 0) {
+                    const float m = a[t][6] + b1.z - 2.f * (a[t][0] * b0.x + a[t][1] * b0.y + a[t][2] * b0.z);
+                    c += fast_sqrt(fmaxf(m, kL2DClamp) * (1.f / 3.f));
+                }
+                if (c < bv[t]) { bv[t] = c; bi[t] = kb + k; }
+            }
         }
     }
-    if (q < nq && k1 > k0) atomicMax(best + q, pack_best(-bv, static_cast<uint32_t>(bi)));
+    if (k1 > k0) {
+#pragma unroll
+        for (int t = 0; t < kPalQT; ++t) {
+            const int q = qbase + t * kPalThreads;
+            if (q < nq) atomicMax(best + q, pack_best(-bv[t], static_cast<uint32_t>(bi[t])));
+        }
+    }
 }
 
 // Sparse backward of the 3-channel relaxed EMD w.r.t. the prediction's RGB (through the YUV matrix).
