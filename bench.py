@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--eps", type=float, default=1.0, help="pred = content + eps*noise (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="rowshard", choices=["rowshard", "replicas"],
+                    help="N>1: shard one evaluation by prediction rows (strong scaling) or run one problem per GPU (weak)")
     args = ap.parse_args()
     N, M = WORKLOADS[args.workload]
 
@@ -203,9 +205,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # Replica mode: every rank evaluates its own (seeded per rank) problem of the full size.
-    style, content, pred = synth_torch(N, M, D_FEAT, args.eps, rank, dev)
+    # rowshard: every rank holds the same (replicated) inputs and computes its rows of ONE evaluation;
+    # replicas: every rank evaluates its own (seeded per rank) problem of the full size.
+    rowshard = world > 1 and args.mode == "rowshard"
+    style, content, pred = synth_torch(N, M, D_FEAT, args.eps, 0 if rowshard else rank, dev)
     h = S.Handle(dev)
+    if rowshard:
+        from strotss_tensorflow_b200 import distributed as Dm
+        Dm.attach(h)
     h.set_style_target(style)
     scalars = None
     for _ in range(max(args.warmup, 3)):
@@ -255,10 +262,12 @@ def main():
         return
 
     pk = peaks()
-    value = world * 1000.0 / ms_step
+    jobs = 1 if rowshard else world                     # evaluations completed per step across the job
+    value = jobs * 1000.0 / ms_step
     # dominant kernel: self-similarity stage 1 (one launch per 2048-row panel)
     ss1_ms, ss1_n = phases.get("ss_stage1_gemm", (0.0, 0))
-    panel_rows = min(2048, N)
+    own_rows = h.shard_rows(N)[1] - h.shard_rows(N)[0] if rowshard else N
+    panel_rows = min(2048, own_rows)
     alg_flops_launch = 2 * (2.0 * panel_rows * N * D_FEAT)          # Xd and Yd tiles of one row panel
     ach = alg_flops_launch / (ss1_ms / max(ss1_n, 1) * 1e-3) / 1e12 if ss1_n else None
     roof = {"bound": "tensor", "kernel": "gemm_kernel<256,2,4,8,EpiSS1<256,8>> (self-similarity stage 1)",
@@ -269,16 +278,19 @@ def main():
     line = {
         "metric": f"loss+grad evals/sec at N=M={N}, D={D_FEAT}", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if rowshard else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}"
                    if args.workload == "large" else f"default sample count N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one problem per GPU)",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"one evaluation row-sharded over {world} GPUs by prediction rows; per evaluation one NCCL allreduce-max of "
+                       f"2x{M} packed u64 minima + one allreduce-sum of {16 + D_FEAT} floats" if rowshard
+                       else f"{world} independent replicas (one problem per GPU, no collective)"),
                    "l2": "inputs (3 x %.0f MB fp32) exceed the 126 MB L2; no flush" % (N * D_FEAT * 4 / 1e6)
                    if N * D_FEAT * 4 * 3 > 126e6 else "inputs fit in L2 (launch-bound regime)",
                    "precision": "bf16 operands (delta-form self-similarity), fp32 accumulate/reductions"},
         "clocks": clocks,
-        "e2e": {"value": world * 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 2 * N * D_FEAT * 4, "d2h_bytes_per_step": N * D_FEAT * 4 + _lib.NUM_SCALARS * 4},
+        "e2e": {"value": jobs * 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 2 * N * D_FEAT * 4, "d2h_bytes_per_step": own_rows * D_FEAT * 4 + _lib.NUM_SCALARS * 4},
         "gpu_launches": int(launches),
         "roofline": roof,
         "whole_eval": {"f_alg": f_alg(N, M), "tflops_alg": f_alg(N, M) / (ms_step * 1e-3) / 1e12,

@@ -72,6 +72,18 @@ int strotss_profile_num_phases(void);
 const char* strotss_profile_phase_name(int i);
 int strotss_profile_read(strotss_handle h, double* ms_sum, long long* counts);
 
+/* Multi-GPU (one process per GPU, like --gpu_id): the evaluation shards by prediction-sample rows.
+ * Rank 0 creates an id with strotss_comm_unique_id (ncclGetUniqueId) and ships the 128 bytes to the
+ * other ranks by any means (bench.py uses torch.distributed); every rank then calls strotss_comm_init.
+ * Afterwards strotss_eval / strotss_eval_host compute rows [row_begin, row_end) of the prediction on
+ * this rank (strotss_shard_rows), exchange ONE allreduce-max of the packed (value, index) minima of the
+ * M style rows and ONE allreduce-sum of a (16 + D)-float block per evaluation over NCCL, write
+ * identical scalars on every rank and only this rank's rows of grad_pred.  Inputs are replicated.
+ * NCCL is loaded with dlopen("libnccl.so.2") at first use; the library itself does not link it. */
+int strotss_comm_unique_id(char* out128);
+int strotss_comm_init(strotss_handle h, int rank, int world, const char* id128);
+int strotss_shard_rows(strotss_handle h, int N, int* row_begin, int* row_end);
+
 /* StyleLoss.__init__(target, alpha) (run_strotss.py:28-31): fix the style target for a scale.
  * Caches what the reference recomputes every iteration (nn/losses.py:43,49; run_strotss.py:37):
  * normalised bf16 operand, column mean, covariance, YUV records.  style: M x D, row stride ld. */

@@ -29,6 +29,9 @@ SIGNATURES = {
     "strotss_profile_num_phases": (_i, []),
     "strotss_profile_phase_name": (C.c_char_p, [_i]),
     "strotss_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "strotss_comm_unique_id": (_i, [C.c_char_p]),
+    "strotss_comm_init": (_i, [_vp, _i, _i, C.c_char_p]),
+    "strotss_shard_rows": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "strotss_set_style_target": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "strotss_eval": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _f, _vp, _vp, _ll, _vp, _vp, _vp]),
     "strotss_eval_host": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),

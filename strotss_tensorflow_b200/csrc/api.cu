@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <dlfcn.h>
 
 #include "../../include/strotss_b200.h"
 #include "gemm_core.cuh"
@@ -78,6 +79,9 @@ struct strotss_ctx {
     float* Vx = nullptr;
     // host pinned staging for scalar read-back
     float* h_scalars = nullptr;
+    // multi-GPU row sharding (NCCL through dlopen; see strotss_comm_*)
+    int rank = 0, world = 1;
+    void* nccl_comm = nullptr;
     // optional per-phase CUDA-event timing
     bool profiling = false;
     std::vector<PhaseRec> recs;
@@ -241,81 +245,163 @@ int cov_store(strotss_ctx* h, const Feat& f, int D, int Dp, float* V, cudaStream
 }
 
 // ---- the three loss terms, each leaving its gradient contribution in workspace buffers --
-struct RemdOut { unsigned long long* rowbest; unsigned long long* colbest; float* g; long long ldg; };
+// Rows [r0, r1) of the prediction owned by this rank (everything for a single GPU).
+struct Shard { int r0, r1; int n() const { return r1 - r0; } };
 
-int remd_cosine(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int N, int D, int Dp, float* scalars,
-                int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, RemdOut& out,
-                int32_t* row_arg, int32_t* col_arg, cudaStream_t st) {
-    RET(ensure(h, "remd.rowbest", (size_t)M, &out.rowbest));
-    RET(ensure(h, "remd.colbest", (size_t)N, &out.colbest));
-    CK(cudaMemsetAsync(out.rowbest, 0, sizeof(unsigned long long) * M, st));
-    CK(cudaMemsetAsync(out.colbest, 0, sizeof(unsigned long long) * N, st));
-    GemmParams<EpiRemd<256>> p{};
-    RET(make_tmap(h, &p.tmA[0], target.xh, M, Dp, Dp, BM));
-    RET(make_tmap(h, &p.tmB[0], pred.xh, N, Dp, Dp, 256));
-    p.nseg = 1; p.seg_kblocks[0] = Dp / BK; p.seg_acc[0] = 0;
-    p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + 255) / 256;
-    p.epi.rowbest = out.rowbest; p.epi.colbest = out.colbest; p.epi.M = M; p.epi.N = N;
-    { PhaseTimer _pt(h, PH_REMD_GEMM, st); RET((launch_gemm<256, 1, 4>(h, p, st))); }
+// Slots of the float block that is summed over ranks once per evaluation.
+enum { PS_REMD_RY = 0, PS_PAL_RY = 1, PS_SS_LOSS = 2, PS_V = 16 };
+
+// ---- NCCL through dlopen (the library must not need libnccl to load) ---------------------
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+enum { kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclMax = 2 };
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return api; }
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    if (!api.ok) api.why = "libnccl is missing a required symbol";
+    return api;
+}
+
+#define NCK(expr)                                                                                        \
+    do {                                                                                                 \
+        int _r = (expr);                                                                                 \
+        if (_r != 0) { h->err = std::string(#expr) + ": " + nccl().GetErrorString(_r); return STROTSS_ERR_CUDA; } \
+    } while (0)
+
+Shard shard_of(const strotss_ctx* h, int N, bool sharded) {
+    if (!sharded || h->world <= 1) return Shard{0, N};
+    const int per = round_up((N + h->world - 1) / h->world, BM);
+    int r0 = h->rank * per, r1 = r0 + per;
+    if (r0 > N) r0 = N;
+    if (r1 > N) r1 = N;
+    return Shard{r0, r1};
+}
+
+// ---- the loss terms: "local" part (before the exchange) and "finish" part (after it) --------
+struct RemdState {
+    unsigned long long* rowbest = nullptr;   // [M]  per target row: best prediction over THIS rank's rows, global after exchange
+    unsigned long long* colbest = nullptr;   // [N]  per prediction row (only rows of this rank are valid)
+    float* g = nullptr; long long ldg = 0;   // [n_local x D] gradient w.r.t. normalised prediction rows
+};
+
+int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int N, Shard sh, int Dp, RemdState& rs,
+               float* ry_partial, cudaStream_t st) {
+    RET(ensure(h, "remd.colbest", (size_t)N, &rs.colbest));
+    CK(cudaMemsetAsync(rs.rowbest, 0, sizeof(unsigned long long) * M, st));
+    CK(cudaMemsetAsync(rs.colbest, 0, sizeof(unsigned long long) * N, st));
+    if (sh.n() > 0) {
+        GemmParams<EpiRemd<256>> p{};
+        RET(make_tmap(h, &p.tmA[0], target.xh, M, Dp, Dp, BM));
+        RET(make_tmap(h, &p.tmB[0], pred.xh, N, Dp, Dp, 256));
+        p.nseg = 1; p.seg_kblocks[0] = Dp / BK; p.seg_acc[0] = 0;
+        p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (sh.n() + 255) / 256;
+        p.a_row0 = 0; p.b_row0 = sh.r0;
+        p.epi.rowbest = rs.rowbest; p.epi.colbest = rs.colbest; p.epi.M = M; p.epi.N = sh.r1;
+        PhaseTimer _pt(h, PH_REMD_GEMM, st);
+        RET((launch_gemm<256, 1, 4>(h, p, st)));
+    }
     PhaseTimer _pm(h, PH_REMD_MISC, st);
-    remd_finish_kernel<<<1, 1024, 0, st>>>(out.rowbest, M, out.colbest, N, 1.f, scalars, slot_loss, slot_rx, slot_ry,
-                                           slot_branch, row_arg, col_arg);
+    best_partial_kernel<<<1, 1024, 0, st>>>(rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
     CKL();
-    out.g = nullptr; out.ldg = 0;
-    if (want_grad) {
-        RET(ensure(h, "remd.g", (size_t)N * D, &out.g));
-        out.ldg = D;
-        CK(cudaMemsetAsync(out.g, 0, sizeof(float) * (size_t)N * D, st));
-        const int rows = M > N ? M : N;
-        remd_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(out.rowbest, M, out.colbest, N, target.x, target.ld, target.inv, D,
-                                                             scalars, slot_branch, out.g, out.ldg);
+    return 0;
+}
+
+int remd_finish(strotss_ctx* h, const Feat& target, int M, int N, Shard sh, int D, RemdState& rs, const float* ry_sum,
+                float* scalars, int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, int32_t* row_arg,
+                int32_t* col_arg, cudaStream_t st) {
+    PhaseTimer _pm(h, PH_REMD_MISC, st);
+    remd_finish_kernel<<<1, 1024, 0, st>>>(rs.rowbest, M, ry_sum, N, 1.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
+                                           row_arg, rs.colbest, sh.r0, sh.r1, col_arg);
+    CKL();
+    rs.g = nullptr; rs.ldg = 0;
+    if (want_grad && sh.n() > 0) {
+        RET(ensure(h, "remd.g", (size_t)sh.n() * D, &rs.g));
+        rs.ldg = D;
+        CK(cudaMemsetAsync(rs.g, 0, sizeof(float) * (size_t)sh.n() * D, st));
+        const int rows = M > sh.n() ? M : sh.n();
+        remd_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(rs.rowbest, M, rs.colbest, N, sh.r0, sh.r1, target.x, target.ld,
+                                                             target.inv, D, scalars, slot_branch, rs.g, rs.ldg);
         CKL();
     }
     return 0;
 }
 
-int remd_small(strotss_ctx* h, const float* arec, int M, const float* brec, int N, int mode, int convert, float* scalars,
-               int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, float** gpal,
+struct PalState { unsigned long long* rowbest = nullptr; unsigned long long* colbest = nullptr; float* g = nullptr; };
+
+int pal_launch(strotss_ctx* h, const float* q, int nq, const float* k, int nk, int kidx_base, int mode,
+               unsigned long long* best, cudaStream_t st) {
+    if (nq <= 0 || nk <= 0) return 0;
+    const int qblocks = (nq + kPalThreads * kPalQT - 1) / (kPalThreads * kPalQT);
+    int ks = (4 * h->num_sms + qblocks - 1) / qblocks;        // aim for ~4 blocks per SM
+    const int maxks = (nk + kPalKeyTile - 1) / kPalKeyTile;
+    if (ks > maxks) ks = maxks;
+    if (ks < 1) ks = 1;
+    const int kchunk = round_up((nk + ks - 1) / ks, kPalKeyTile);
+    ks = (nk + kchunk - 1) / kchunk;
+    dim3 grid(qblocks, ks);
+    pal_min_kernel<<<grid, kPalThreads, 0, st>>>(q, nq, k, nk, kchunk, mode, kidx_base, best);
+    CKL();
+    return 0;
+}
+
+int pal_local(strotss_ctx* h, const float* arec, int M, const float* brec, int N, Shard sh, int mode, PalState& ps,
+              float* ry_partial, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_PALETTE, st);
+    RET(ensure(h, "pal.colbest", (size_t)N, &ps.colbest));
+    CK(cudaMemsetAsync(ps.rowbest, 0, sizeof(unsigned long long) * M, st));
+    CK(cudaMemsetAsync(ps.colbest, 0, sizeof(unsigned long long) * N, st));
+    // target rows (all) against this rank's prediction rows; this rank's prediction rows against all target rows
+    RET(pal_launch(h, arec, M, brec + (size_t)sh.r0 * 8, sh.n(), sh.r0, mode, ps.rowbest, st));
+    RET(pal_launch(h, brec + (size_t)sh.r0 * 8, sh.n(), arec, M, 0, mode, ps.colbest + sh.r0, st));
+    best_partial_kernel<<<1, 1024, 0, st>>>(ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
+    CKL();
+    return 0;
+}
+
+int pal_finish(strotss_ctx* h, const float* arec, int M, const float* brec, int N, Shard sh, int mode, int convert, PalState& ps,
+               const float* ry_sum, float* scalars, int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad,
                int32_t* row_arg, int32_t* col_arg, cudaStream_t st) {
     PhaseTimer _pt(h, PH_PALETTE, st);
-    unsigned long long *rowbest, *colbest;
-    RET(ensure(h, "pal.rowbest", (size_t)M, &rowbest));
-    RET(ensure(h, "pal.colbest", (size_t)N, &colbest));
-    CK(cudaMemsetAsync(rowbest, 0, sizeof(unsigned long long) * M, st));
-    CK(cudaMemsetAsync(colbest, 0, sizeof(unsigned long long) * N, st));
-    auto launch = [&](const float* q, int nq, const float* k, int nk, unsigned long long* best) -> int {
-        const int qblocks = (nq + kPalThreads * kPalQT - 1) / (kPalThreads * kPalQT);
-        int ks = (4 * h->num_sms + qblocks - 1) / qblocks;        // aim for ~4 blocks per SM
-        const int maxks = (nk + kPalKeyTile - 1) / kPalKeyTile;
-        if (ks > maxks) ks = maxks;
-        if (ks < 1) ks = 1;
-        const int kchunk = round_up((nk + ks - 1) / ks, kPalKeyTile);
-        ks = (nk + kchunk - 1) / kchunk;
-        dim3 grid(qblocks, ks);
-        pal_min_kernel<<<grid, kPalThreads, 0, st>>>(q, nq, k, nk, kchunk, mode, best);
-        CKL();
-        return 0;
-    };
-    RET(launch(arec, M, brec, N, rowbest));
-    RET(launch(brec, N, arec, M, colbest));
-    remd_finish_kernel<<<1, 1024, 0, st>>>(rowbest, M, colbest, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
-                                           row_arg, col_arg);
+    remd_finish_kernel<<<1, 1024, 0, st>>>(ps.rowbest, M, ry_sum, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
+                                           row_arg, ps.colbest, sh.r0, sh.r1, col_arg);
     CKL();
-    if (want_grad) {
-        RET(ensure(h, "pal.g", (size_t)N * 4, gpal));
-        CK(cudaMemsetAsync(*gpal, 0, sizeof(float) * (size_t)N * 4, st));
-        const int rows = M > N ? M : N;
-        pal_backward_kernel<<<(rows + 127) / 128, 128, 0, st>>>(rowbest, M, colbest, N, arec, brec, mode, convert, scalars,
-                                                                slot_branch, *gpal);
+    ps.g = nullptr;
+    if (want_grad && sh.n() > 0) {
+        RET(ensure(h, "pal.g", (size_t)sh.n() * 4, &ps.g));
+        CK(cudaMemsetAsync(ps.g, 0, sizeof(float) * (size_t)sh.n() * 4, st));
+        const int rows = M > sh.n() ? M : sh.n();
+        pal_backward_kernel<<<(rows + 127) / 128, 128, 0, st>>>(ps.rowbest, M, ps.colbest, N, sh.r0, sh.r1, arec, brec, mode,
+                                                                convert, scalars, slot_branch, ps.g);
         CKL();
     }
     return 0;
 }
 
-struct MomOut { float* Q; long long ldq; float q_scale; float* gmu; };
+struct MomOut { float* Q = nullptr; long long ldq = 0; float q_scale = 0.f; float* gmu = nullptr; };
 
-// target mean / covariance given explicitly (mu_x, Vx with row stride Dp)
-int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred, int N, int D, int Dp, float* scalars,
+// Target mean / covariance given explicitly (mu_x, Vx with row stride Dp).  The covariance forward is
+// replicated on every rank (3 % of the work); the backward GEMM covers this rank's rows only.
+int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred, int N, Shard sh, int D, int Dp, float* scalars,
             bool want_grad, MomOut& out, cudaStream_t st) {
     bf16* Sg; float* part;
     RET(ensure(h, "mom.Sg", (size_t)Dp * Dp, &Sg, /*zero_on_alloc=*/true));
@@ -336,27 +422,30 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
         CKL();
     }
     out.Q = nullptr; out.ldq = 0; out.q_scale = 0.f;
-    if (want_grad) {
+    if (want_grad && sh.n() > 0) {
         // Q = cen . (G + G^T) / N with G = sign(V_y - V_x)/D^2 symmetric  ->  q_scale * (cen . Sg^T)
-        RET(ensure(h, "mom.Q", (size_t)N * Dp, &out.Q));
+        RET(ensure(h, "mom.Q", (size_t)sh.n() * Dp, &out.Q));
         out.ldq = Dp; out.q_scale = 2.f / (static_cast<float>(N) * static_cast<float>(D) * static_cast<float>(D));
         GemmParams<EpiStoreT<256>> q{};
         RET(make_tmap(h, &q.tmA[0], pred.cen, N, Dp, Dp, BM));
         RET(make_tmap(h, &q.tmB[0], Sg, D, Dp, Dp, 256));
         q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
-        q.tiles_m = (N + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
-        q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = N; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = 0;
+        q.tiles_m = (sh.n() + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
+        q.a_row0 = sh.r0; q.b_row0 = 0;
+        q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = sh.r1; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = sh.r0;
         PhaseTimer _pt(h, PH_COV_BWD, st);
         RET((launch_gemm<256, 1, 4>(h, q, st)));
     }
     return 0;
 }
 
-struct SsOut { float* ss2; long long ld; float* v; float* coef; };
+struct SsOut { float* ss2 = nullptr; long long ld = 0; float* coef = nullptr; };
 
 // x = prediction (gradient side), y = content.  Needs x.{xh,xhT,dlt,sumhat}, y.{xh,sumhat}.
-int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp, float* loss_out, bool want_grad, SsOut& out,
-             cudaStream_t st) {
+// Leaves: sum of this rank's row losses in *loss_partial, this rank's part of v in v_partial[D]
+// (both to be summed over ranks), ss2 rows (local), coef (global indexing, this rank's rows valid).
+int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh, int D, int Dp, float* loss_partial,
+                   float* v_partial, bool want_grad, SsOut& out, cudaStream_t st) {
     float *u, *w, *sclamp, *loss_part, *r_part, *rowloss;
     RET(ensure(h, "ss.u", (size_t)N, &u));
     RET(ensure(h, "ss.w", (size_t)N, &w));
@@ -376,16 +465,16 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
     const int np = x.np;
     // row panel of P (bf16), sized to stay L2-resident between its producer and consumer GEMMs
     int panel = 2048;
-    if (panel > round_up(N, BM)) panel = round_up(N, BM);
+    if (panel > round_up(sh.n() > 0 ? sh.n() : 1, BM)) panel = round_up(sh.n() > 0 ? sh.n() : 1, BM);
     bf16* P = nullptr;
-    out.ss2 = nullptr; out.ld = 0; out.v = nullptr;
-    if (want_grad) {
+    out.ss2 = nullptr; out.ld = 0;
+    if (want_grad && sh.n() > 0) {
         RET(ensure(h, "ss.P", (size_t)panel * np, &P));
-        RET(ensure(h, "ss.ss2", (size_t)N * Dp, &out.ss2));
+        RET(ensure(h, "ss.ss2", (size_t)sh.n() * Dp, &out.ss2));
         out.ld = Dp;
     }
-    for (int r0 = 0; r0 < N; r0 += panel) {
-        const int rows = (N - r0 < panel) ? (N - r0) : panel;
+    for (int r0 = sh.r0; r0 < sh.r1; r0 += panel) {
+        const int rows = (sh.r1 - r0 < panel) ? (sh.r1 - r0) : panel;
         GemmParams<EpiSS1<kSsBN, kSsEpiWarps>> p{};
         // segment 0: delta_I . x^_J ; segment 1: y^_I . delta_J  (both into acc 0) ; segment 2: y^_I . y^_J (acc 1)
         RET(make_tmap(h, &p.tmA[0], x.dlt, N, Dp, Dp, BM));
@@ -400,7 +489,8 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
         p.tiles_m = (rows + BM - 1) / BM; p.tiles_n = tiles_n;
         p.a_row0 = r0; p.b_row0 = 0;
         p.epi.u = u; p.epi.w = w; p.epi.P = P; p.epi.ldp = np; p.epi.panel_row0 = r0;
-        p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.write_p = want_grad ? 1 : 0;
+        p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.row_end = sh.r1;
+        p.epi.write_p = (want_grad ? 1 : 0);
         { PhaseTimer _pt(h, PH_SS1, st); RET((launch_gemm<kSsBN, 2, 4, kSsEpiWarps>(h, p, st))); }
         if (want_grad) {
             GemmParams<EpiStoreT<256>> q{};
@@ -409,34 +499,51 @@ int self_sim(strotss_ctx* h, const Feat& x, const Feat& y, int N, int D, int Dp,
             q.nseg = 1; q.seg_kblocks[0] = np / BK; q.seg_acc[0] = 0;
             q.tiles_m = (rows + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
             q.a_row0 = 0; q.b_row0 = 0;
-            q.epi.C = out.ss2 + static_cast<long long>(r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
+            q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
             q.epi.alpha = 1.f; q.epi.row_off = 0;
             PhaseTimer _pt(h, PH_SS2, st);
             RET((launch_gemm<256, 1, 4>(h, q, st)));
         }
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
-    ss_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, u, sclamp, out.coef, rowloss);
-    CKL();
-    reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss, N, 1.f / N, loss_out);
+    if (sh.n() > 0) {
+        ss_rows_kernel<<<(sh.n() + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss);
+        CKL();
+    }
+    reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss + sh.r0, sh.n(), 1.f, loss_partial);
     CKL();
     if (want_grad) {
-        const int nblk = (N + kRowsPerBlock - 1) / kRowsPerBlock;
-        float* vpart;
-        RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
-        RET(ensure(h, "ss.v", (size_t)D, &out.v));
-        weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x, x.ld, N, D, x.inv, out.coef, vpart);
-        CKL();
-        colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(vpart, nblk, D, 1.f, out.v);
-        CKL();
+        if (sh.n() > 0) {
+            const int nblk = (sh.n() + kRowsPerBlock - 1) / kRowsPerBlock;
+            float* vpart;
+            RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
+            weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
+                                                         out.coef + sh.r0, vpart);
+            CKL();
+            colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(vpart, nblk, D, 1.f, v_partial);
+            CKL();
+        } else {
+            CK(cudaMemsetAsync(v_partial, 0, sizeof(float) * D, st));
+        }
     }
     return 0;
 }
 
-int finalize(strotss_ctx* h, const FinalizeArgs& a, cudaStream_t st) {
+int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) {
+    if (nrows <= 0) return 0;
     PhaseTimer _pt(h, PH_FINALIZE, st);
-    finalize_grad_kernel<<<a.N, 256, sizeof(float) * a.D, st>>>(a);
+    finalize_grad_kernel<<<nrows, 256, sizeof(float) * a.D, st>>>(a);
     CKL();
+    return 0;
+}
+
+// One exchange per evaluation when the handle is attached to a communicator:
+//   allreduce-max over the packed (value, ~index) bests of the target rows (relaxed EMD + palette, 2*M u64)
+//   allreduce-sum over the float block (partial column sums, self-similarity loss, v vector)
+int exchange(strotss_ctx* h, unsigned long long* best, size_t nbest, float* partials, size_t npartials, cudaStream_t st) {
+    if (h->world <= 1 || !h->nccl_comm) return 0;
+    NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
+    NCK(nccl().AllReduce(partials, partials, npartials, kNcclFloat32, kNcclSum, h->nccl_comm, st));
     return 0;
 }
 
@@ -449,7 +556,7 @@ int check_handle(strotss_handle h) { return h ? 0 : STROTSS_ERR_ARG; }
 // ======================================================================================
 extern "C" {
 
-const char* strotss_version(void) { return "strotss_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+const char* strotss_version(void) { return "strotss_b200 0.2 (sm_100a, tcgen05/TMA)"; }
 
 int strotss_create(int device, strotss_handle* out) {
     if (!out) return STROTSS_ERR_ARG;
@@ -478,7 +585,10 @@ int strotss_create(int device, strotss_handle* out) {
     return 0;
 }
 
-void strotss_destroy(strotss_handle h) { delete h; }
+void strotss_destroy(strotss_handle h) {
+    if (h && h->nccl_comm && nccl().ok) nccl().CommDestroy(h->nccl_comm);
+    delete h;
+}
 
 const char* strotss_last_error(strotss_handle h) { return h ? h->err.c_str() : "null handle"; }
 
@@ -511,6 +621,38 @@ int strotss_profile_read(strotss_handle h, double* ms_sum, long long* counts) {
     return 0;
 }
 
+// ---- multi-GPU ---------------------------------------------------------------------------
+int strotss_comm_unique_id(char* out128) {
+    if (!out128) return STROTSS_ERR_ARG;
+    if (!nccl().ok) return STROTSS_ERR_CUDA;
+    NcclApi::UniqueId id;
+    if (nccl().GetUniqueId(&id) != 0) return STROTSS_ERR_CUDA;
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+int strotss_comm_init(strotss_handle h, int rank, int world, const char* id128) {
+    RET(check_handle(h));
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) { h->err = "comm_init: bad argument"; return STROTSS_ERR_ARG; }
+    if (h->nccl_comm) { nccl().CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+    h->rank = rank; h->world = world;
+    if (world == 1) return 0;
+    if (!nccl().ok) { h->err = "NCCL unavailable: " + nccl().why; return STROTSS_ERR_CUDA; }
+    CK(cudaSetDevice(h->device));
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, 128);
+    NCK(nccl().CommInitRank(&h->nccl_comm, world, id, rank));
+    return 0;
+}
+
+int strotss_shard_rows(strotss_handle h, int N, int* row_begin, int* row_end) {
+    RET(check_handle(h));
+    if (N <= 0 || !row_begin || !row_end) { h->err = "shard_rows: bad argument"; return STROTSS_ERR_ARG; }
+    const Shard sh = shard_of(h, N, true);
+    *row_begin = sh.r0; *row_end = sh.r1;
+    return 0;
+}
+
 int strotss_set_style_target(strotss_handle h, const float* style, int M, int D, long long ld, void* stream) {
     RET(check_handle(h));
     if (!style || M <= 0 || D < 3 || ld < D) { h->err = "set_style_target: bad argument"; return STROTSS_ERR_ARG; }
@@ -530,14 +672,20 @@ int strotss_set_style_target(strotss_handle h, const float* style, int M, int D,
     return 0;
 }
 
+// grad (if non-NULL) points at row 0 of an N x D buffer; only rows [r0, r1) of this rank are written.
 static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,
                      int N, float alpha, float* scalars, float* grad, long long ld_grad, int32_t* row_arg, int32_t* col_arg,
-                     bool with_content, cudaStream_t st) {
+                     bool with_content, bool sharded, cudaStream_t st) {
     const int D = h->D, Dp = h->Dp, M = h->M;
     const bool want_grad = grad != nullptr;
     const float inv_alpha = 1.f / (alpha > 1.f ? alpha : 1.f);
     const float denom = with_content ? (2.f + alpha + inv_alpha) : 1.f;
+    const Shard sh = shard_of(h, N, sharded);
     CK(cudaMemsetAsync(scalars, 0, sizeof(float) * STROTSS_NUM_SCALARS, st));
+    unsigned long long* best; float* partials;
+    RET(ensure(h, "eval.best", (size_t)2 * M, &best));
+    RET(ensure(h, "eval.partials", (size_t)PS_V + D, &partials));
+    CK(cudaMemsetAsync(partials, 0, sizeof(float) * (PS_V + D), st));
     Feat fp, fc;
     if (with_content) {
         PrepWant wc{}; wc.sumhat = true; wc.xh = true;
@@ -547,24 +695,30 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     wp.cen = want_grad; wp.sumhat = with_content; wp.dlt = with_content; wp.xhT = with_content && want_grad;
     RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, with_content ? &fc : nullptr, 1, st));
 
-    RemdOut ro{}; MomOut mo{}; SsOut so{}; float* gpal = nullptr;
-    RET(remd_cosine(h, h->style, M, fp, N, D, Dp, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad, ro, row_arg,
-                    col_arg, st));
-    RET(remd_small(h, h->style.rec, M, fp.rec, N, STROTSS_DIST_BOTH, 1, scalars, S_LPAL, S_PAL_RX, S_PAL_RY, S_PAL_BRANCH,
-                   want_grad, &gpal, nullptr, nullptr, st));
-    RET(moments(h, h->style.mean, h->Vx, fp, N, D, Dp, scalars, want_grad, mo, st));
-    if (with_content) RET(self_sim(h, fp, fc, N, D, Dp, scalars + S_LOSS_C, want_grad, so, st));
-    combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom);
+    RemdState rs; PalState ps; MomOut mo; SsOut so;
+    rs.rowbest = best; ps.rowbest = best + M;
+    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, st));
+    RET(pal_local(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, st));
+    RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, st));
+    if (with_content)
+        RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
+    if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
+    RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
+                    want_grad, row_arg, col_arg, st));
+    RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
+                   S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st));
+    combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom,
+                                             with_content ? partials + PS_SS_LOSS : nullptr, 1.f / N);
     CKL();
     if (want_grad) {
         FinalizeArgs a{};
-        a.x = pred; a.ldx = ld_pred; a.inv = fp.inv; a.N = N; a.D = D;
-        if (with_content) { a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = so.v; a.coef = so.coef; a.sumhat = fp.sumhat; a.w_ss = alpha / denom; }
-        a.gremd = ro.g; a.ld_gremd = ro.ldg; a.w_remd = 1.f / denom;
+        a.x = pred; a.ldx = ld_pred; a.inv = fp.inv; a.N = N; a.D = D; a.r0 = sh.r0;
+        if (with_content) { a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = partials + PS_V; a.coef = so.coef; a.sumhat = fp.sumhat; a.w_ss = alpha / denom; }
+        a.gremd = rs.g; a.ld_gremd = rs.ldg; a.w_remd = 1.f / denom;
         a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = 1.f / denom;
-        a.gpal = gpal; a.w_pal = inv_alpha / denom;
+        a.gpal = ps.g; a.w_pal = inv_alpha / denom;
         a.grad = grad; a.ldg = ld_grad;
-        RET(finalize(h, a, st));
+        RET(finalize(h, a, sh.n(), st));
     }
     return 0;
 }
@@ -579,7 +733,7 @@ int strotss_eval(strotss_handle h, const float* pred, long long ld_pred, const f
     }
     CK(cudaSetDevice(h->device));
     return eval_impl(h, pred, ld_pred, content, ld_content, N, alpha, scalars, grad_pred, ld_grad, remd_row_argmin,
-                     remd_col_argmin, true, static_cast<cudaStream_t>(stream));
+                     remd_col_argmin, true, true, static_cast<cudaStream_t>(stream));
 }
 
 int strotss_style_loss(strotss_handle h, const float* pred, long long ld_pred, int N, float alpha, float* scalars,
@@ -590,7 +744,7 @@ int strotss_style_loss(strotss_handle h, const float* pred, long long ld_pred, i
         h->err = "strotss_style_loss: bad argument"; return STROTSS_ERR_ARG;
     }
     CK(cudaSetDevice(h->device));
-    return eval_impl(h, pred, ld_pred, nullptr, 0, N, alpha, scalars, grad_pred, ld_grad, nullptr, nullptr, false,
+    return eval_impl(h, pred, ld_pred, nullptr, 0, N, alpha, scalars, grad_pred, ld_grad, nullptr, nullptr, false, false,
                      static_cast<cudaStream_t>(stream));
 }
 
@@ -607,13 +761,25 @@ int strotss_eval_host(strotss_handle h, const float* pred_host, const float* con
     RET(ensure(h, "host.content", elems, &dc));
     RET(ensure(h, "host.scalars", (size_t)STROTSS_NUM_SCALARS, &ds));
     if (grad_host) RET(ensure(h, "host.grad", elems, &dg));
+    const Shard sh = shard_of(h, N, true);
     CK(cudaMemcpyAsync(dp, pred_host, elems * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dc, content_host, elems * sizeof(float), cudaMemcpyHostToDevice, st));
-    RET(eval_impl(h, dp, h->D, dc, h->D, N, alpha, ds, dg, h->D, nullptr, nullptr, true, st));
+    RET(eval_impl(h, dp, h->D, dc, h->D, N, alpha, ds, dg, h->D, nullptr, nullptr, true, true, st));
     CK(cudaMemcpyAsync(h->h_scalars, ds, sizeof(float) * STROTSS_NUM_SCALARS, cudaMemcpyDeviceToHost, st));
-    if (grad_host) CK(cudaMemcpyAsync(grad_host, dg, elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grad_host && sh.n() > 0) {
+        const size_t off = (size_t)sh.r0 * h->D;      // only this rank's rows exist
+        CK(cudaMemcpyAsync(grad_host + off, dg + off, (size_t)sh.n() * h->D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     memcpy(scalars_host, h->h_scalars, sizeof(float) * STROTSS_NUM_SCALARS);
+    return 0;
+}
+
+static int copy_out(strotss_handle h, const float* sc, const int (&hidx)[4], int n, float* loss, cudaStream_t st) {
+    int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
+    CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
+    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, n, loss);
+    CKL();
     return 0;
 }
 
@@ -627,28 +793,28 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    float* sc;
+    float* sc; unsigned long long* best; float* partials;
     RET(ensure(h, "fn.scalars", (size_t)S_COUNT, &sc));
+    RET(ensure(h, "fn.best", (size_t)M, &best));
+    RET(ensure(h, "fn.partials", (size_t)PS_V, &partials));
     CK(cudaMemsetAsync(sc, 0, sizeof(float) * S_COUNT, st));
     const bool want_grad = grad_y != nullptr;
+    const Shard sh{0, N};
     if (D == 3) {
         Feat fx, fy;
         PrepWant w{}; w.rec = true;
         RET(prep_features(h, "fn.x", fx, x, ldx, M, D, round_up(D, BK), w, nullptr, 0, st));
         RET(prep_features(h, "fn.y", fy, y, ldy, N, D, round_up(D, BK), w, nullptr, 0, st));
-        float* gpal = nullptr;
-        RET(remd_small(h, fx.rec, M, fy.rec, N, distance, 0, sc, S_LPAL, S_PAL_RX, S_PAL_RY, S_PAL_BRANCH, want_grad, &gpal,
-                       row_argmin, col_argmin, st));
+        PalState ps; ps.rowbest = best;
+        RET(pal_local(h, fx.rec, M, fy.rec, N, sh, distance, ps, partials + PS_PAL_RY, st));
+        RET(pal_finish(h, fx.rec, M, fy.rec, N, sh, distance, 0, ps, partials + PS_PAL_RY, sc, S_LPAL, S_PAL_RX, S_PAL_RY,
+                       S_PAL_BRANCH, want_grad, row_argmin, col_argmin, st));
         if (want_grad) {
-            CK(cudaMemcpy2DAsync(grad_y, sizeof(float) * ld_grad, gpal, sizeof(float) * 4, sizeof(float) * 3, N,
+            CK(cudaMemcpy2DAsync(grad_y, sizeof(float) * ld_grad, ps.g, sizeof(float) * 4, sizeof(float) * 3, N,
                                  cudaMemcpyDeviceToDevice, st));
         }
-        int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
         const int hidx[4] = {S_LPAL, S_PAL_RX, S_PAL_RY, S_PAL_BRANCH};
-        CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
-        copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, 4, loss);
-        CKL();
-        return 0;
+        return copy_out(h, sc, hidx, 4, loss, st);
     }
     if (distance != STROTSS_DIST_COSINE) {
         h->err = "relaxed_emd: 'l2'/'both' are implemented for D == 3 only (the palette call, run_strotss.py:39)";
@@ -659,22 +825,19 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
     PrepWant w{}; w.xh = true;
     RET(prep_features(h, "fn.x", fx, x, ldx, M, D, Dp, w, nullptr, 0, st));
     RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, w, nullptr, 0, st));
-    RemdOut ro{};
-    RET(remd_cosine(h, fx, M, fy, N, D, Dp, sc, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad, ro, row_argmin,
-                    col_argmin, st));
+    RemdState rs; rs.rowbest = best;
+    RET(remd_local(h, fx, M, fy, N, sh, Dp, rs, partials + PS_REMD_RY, st));
+    RET(remd_finish(h, fx, M, N, sh, D, rs, partials + PS_REMD_RY, sc, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad,
+                    row_argmin, col_argmin, st));
     if (want_grad) {
         FinalizeArgs a{};
-        a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D;
-        a.gremd = ro.g; a.ld_gremd = ro.ldg; a.w_remd = 1.f;
+        a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D; a.r0 = 0;
+        a.gremd = rs.g; a.ld_gremd = rs.ldg; a.w_remd = 1.f;
         a.grad = grad_y; a.ldg = ld_grad;
-        RET(finalize(h, a, st));
+        RET(finalize(h, a, N, st));
     }
-    int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
     const int hidx[4] = {S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH};
-    CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
-    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, 4, loss);
-    CKL();
-    return 0;
+    return copy_out(h, sc, hidx, 4, loss, st);
 }
 
 int strotss_moment_matching(strotss_handle h, const float* x, long long ldx, int M, const float* y, long long ldy, int N, int D,
@@ -698,21 +861,17 @@ int strotss_moment_matching(strotss_handle h, const float* x, long long ldx, int
     RET(cov_store(h, fx, D, Dp, Vx, st));
     PrepWant wy{}; wy.mean = true; wy.cenT = true; wy.cen = want_grad;
     RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, wy, nullptr, 0, st));
-    MomOut mo{};
-    RET(moments(h, fx.mean, Vx, fy, N, D, Dp, sc, want_grad, mo, st));
+    MomOut mo;
+    RET(moments(h, fx.mean, Vx, fy, N, Shard{0, N}, D, Dp, sc, want_grad, mo, st));
     if (want_grad) {
         FinalizeArgs a{};
-        a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D;
+        a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D; a.r0 = 0;
         a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = 1.f;
         a.grad = grad_y; a.ldg = ld_grad;
-        RET(finalize(h, a, st));
+        RET(finalize(h, a, N, st));
     }
-    int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
     const int hidx[4] = {S_LM, S_LCOV, S_LMEAN, S_LMEAN};
-    CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
-    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, 3, loss);
-    CKL();
-    return 0;
+    return copy_out(h, sc, hidx, 3, loss, st);
 }
 
 int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, const float* y, long long ldy, int N, int D,
@@ -725,19 +884,23 @@ int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, con
     CK(cudaSetDevice(h->device));
     const int Dp = round_up(D, BK);
     const bool want_grad = grad_x != nullptr;
+    float* partials;
+    RET(ensure(h, "fn.sspartials", (size_t)PS_V + D, &partials));
     Feat fx, fy;
     PrepWant wy{}; wy.sumhat = true; wy.xh = true;
     RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, wy, nullptr, 0, st));
     PrepWant wx{}; wx.sumhat = true; wx.xh = true; wx.dlt = true; wx.xhT = want_grad;
     RET(prep_features(h, "fn.x", fx, x, ldx, N, D, Dp, wx, &fy, 0, st));
-    SsOut so{};
-    RET(self_sim(h, fx, fy, N, D, Dp, loss, want_grad, so, st));
+    SsOut so;
+    RET(self_sim_local(h, fx, fy, N, Shard{0, N}, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
+    reduce_sum_kernel<<<1, 32, 0, st>>>(partials + PS_SS_LOSS, 1, 1.f / N, loss);
+    CKL();
     if (want_grad) {
         FinalizeArgs a{};
-        a.x = x; a.ldx = ldx; a.inv = fx.inv; a.N = N; a.D = D;
-        a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = so.v; a.coef = so.coef; a.sumhat = fx.sumhat; a.w_ss = 1.f;
+        a.x = x; a.ldx = ldx; a.inv = fx.inv; a.N = N; a.D = D; a.r0 = 0;
+        a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = partials + PS_V; a.coef = so.coef; a.sumhat = fx.sumhat; a.w_ss = 1.f;
         a.grad = grad_x; a.ldg = ld_grad;
-        RET(finalize(h, a, st));
+        RET(finalize(h, a, N, st));
     }
     return 0;
 }

@@ -303,6 +303,7 @@ struct EpiSS1 {
         int panel_row0;
         float* loss_part; float* r_part;      // [tiles_n * nsplit][N]
         int N;
+        int row_end;                          // rows >= row_end belong to another rank (or do not exist)
         int write_p;
     };
     struct State {};
@@ -321,7 +322,7 @@ struct EpiSS1 {
         const float* su = reinterpret_cast<const float*>(sm) + (ti.tile_seq & 1) * 2 * BN;
         const float* sw = su + BN;
         const int row = ti.row0 + ti.q * 32 + ti.lane;
-        const bool rvalid = row < P.N;
+        const bool rvalid = row < P.row_end;
         const float ui = rvalid ? P.u[row] : 0.f;
         const float wi = rvalid ? P.w[row] : 0.f;
         float loss = 0.f, racc = 0.f;

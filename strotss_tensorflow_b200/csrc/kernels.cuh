@@ -202,10 +202,10 @@ __global__ void __launch_bounds__(256) ss_vectors_kernel(const float* __restrict
 
 // r_i = (1/N) sum_tn r_part[tn][i];  coef_i = r_i u_i^2 [s_i >= clamp];  rowloss_i = sum_tn loss_part[tn][i]
 __global__ void ss_rows_kernel(const float* __restrict__ loss_part, const float* __restrict__ r_part, int ntn, int N,
-                               const float* __restrict__ u, const float* __restrict__ sclamp,
+                               int r0, int r1, const float* __restrict__ u, const float* __restrict__ sclamp,
                                float* __restrict__ coef, float* __restrict__ rowloss) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
     float l = 0.f, r = 0.f;
     for (int t = 0; t < ntn; ++t) {
         l += loss_part[static_cast<long long>(t) * N + i];
@@ -232,35 +232,50 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
 }
 
 // --------------------------------------------------------------------------------------
-// relaxed EMD finish:  R_X = mean_i cost(rowbest_i), R_Y = mean_j cost(colbest_j), L = max(R_X,R_Y)
-// cost = offset - value  (cosine: offset 1, value = max dot;  palette: offset 0, value = -min cost)
+// relaxed EMD reductions.  cost = offset - value  (cosine: offset 1, value = max dot;
+// palette: offset 0, value = -min cost).
+//   best_partial:  *out = sum_{j in [0,n)} cost(best[j])        (this rank's prediction rows)
+//   remd_finish:   R_X = mean_i cost(rowbest_i) over all M target rows (rowbest is already global),
+//                  R_Y = *ry_sum / N (already summed over ranks), L = max(R_X, R_Y).
 // tf.maximum sends the gradient to its FIRST argument (R_X) on ties -> branch = (R_X >= R_Y).
 // --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) best_partial_kernel(const unsigned long long* __restrict__ best, int n, float offset,
+                                                            float* __restrict__ out) {
+    __shared__ float sh[32];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += offset - best_val(best[i]);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float b = warp_sum(sh[threadIdx.x]);
+        if (threadIdx.x == 0) *out = b;
+    }
+}
+
 __global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long long* __restrict__ rowbest, int M,
-                                                           const unsigned long long* __restrict__ colbest, int N,
+                                                           const float* __restrict__ ry_sum, int N,
                                                            float offset, float* __restrict__ scalars, int slot_loss,
                                                            int slot_rx, int slot_ry, int slot_branch,
-                                                           int* __restrict__ row_arg, int* __restrict__ col_arg) {
-    __shared__ float sh[2][32];
-    float a = 0.f, b = 0.f;
+                                                           int* __restrict__ row_arg,
+                                                           const unsigned long long* __restrict__ colbest, int r0, int r1,
+                                                           int* __restrict__ col_arg) {
+    __shared__ float sh[32];
+    float a = 0.f;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const unsigned long long k = rowbest[i];
         a += offset - best_val(k);
         if (row_arg) row_arg[i] = static_cast<int>(best_idx(k));
     }
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        const unsigned long long k = colbest[j];
-        b += offset - best_val(k);
-        if (col_arg) col_arg[j] = static_cast<int>(best_idx(k));
-    }
-    a = warp_sum(a); b = warp_sum(b);
-    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    if (col_arg)
+        for (int j = r0 + threadIdx.x; j < r1; j += blockDim.x) col_arg[j] = static_cast<int>(best_idx(colbest[j]));
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float aa = sh[0][threadIdx.x], bb = sh[1][threadIdx.x];
-        aa = warp_sum(aa); bb = warp_sum(bb);
+        float aa = warp_sum(sh[threadIdx.x]);
         if (threadIdx.x == 0) {
-            const float rx = aa / static_cast<float>(M), ry = bb / static_cast<float>(N);
+            const float rx = aa / static_cast<float>(M), ry = *ry_sum / static_cast<float>(N);
             scalars[slot_rx] = rx; scalars[slot_ry] = ry;
             scalars[slot_loss] = fmaxf(rx, ry);
             scalars[slot_branch] = (rx >= ry) ? 1.f : 0.f;
@@ -268,12 +283,14 @@ __global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long l
     }
 }
 
-// Sparse backward of the cosine relaxed EMD into g (gradient w.r.t. the NORMALISED prediction rows):
-//   branch X: g[argmin_i][:] += -(1/M) x^_i   for every target row i   (scatter, atomics)
-//   branch Y: g[j][:]        += -(1/N) x^_{argmin_j}                    (gather)
-// One warp per row of max(M, N); the branch flag is read from device memory (no host sync).
+// Sparse backward of the cosine relaxed EMD into g (gradient w.r.t. the NORMALISED prediction rows
+// r0..r1 owned by this rank; g row 0 is prediction row r0):
+//   branch X: g[argmin_i][:] += -(1/M) x^_i   for every target row i whose match is owned here (scatter)
+//   branch Y: g[j][:]        += -(1/N) x^_{argmin_j}                                            (gather)
+// One warp per row of max(M, r1-r0); the branch flag is read from device memory (no host sync).
 __global__ void __launch_bounds__(256) remd_backward_kernel(const unsigned long long* __restrict__ rowbest, int M,
                                                             const unsigned long long* __restrict__ colbest, int N,
+                                                            int r0, int r1,
                                                             const float* __restrict__ xs, long long ldxs,
                                                             const float* __restrict__ inv_s, int D,
                                                             const float* __restrict__ scalars, int slot_branch,
@@ -284,13 +301,15 @@ __global__ void __launch_bounds__(256) remd_backward_kernel(const unsigned long 
     if (bx) {
         if (row >= M) return;
         const int j = static_cast<int>(best_idx(rowbest[row]));
+        if (j < r0 || j >= r1) return;
         const float sc = -inv_s[row] / static_cast<float>(M);
         const float* src = xs + static_cast<long long>(row) * ldxs;
-        float* dst = g + static_cast<long long>(j) * ldg;
+        float* dst = g + static_cast<long long>(j - r0) * ldg;
         for (int d = lane; d < D; d += 32) atomicAdd(dst + d, src[d] * sc);
     } else {
-        if (row >= N) return;
-        const int i = static_cast<int>(best_idx(colbest[row]));
+        const int j = r0 + row;
+        if (j >= r1) return;
+        const int i = static_cast<int>(best_idx(colbest[j]));
         const float sc = -inv_s[i] / static_cast<float>(N);
         const float* src = xs + static_cast<long long>(i) * ldxs;
         float* dst = g + static_cast<long long>(row) * ldg;
@@ -338,7 +357,8 @@ constexpr int kPalThreads = 128;
 constexpr int kPalKeyTile = 256;
 
 __global__ void __launch_bounds__(kPalThreads) pal_min_kernel(const float* __restrict__ qrec, int nq, const float* __restrict__ krec, int nk,
-                                                              int kchunk, int mode, unsigned long long* __restrict__ best) {
+                                                              int kchunk, int mode, int kidx_base,
+                                                              unsigned long long* __restrict__ best) {
     __shared__ float4 sk[kPalKeyTile * 2];
     float a[kPalQT][8];
     float bv[kPalQT];
@@ -379,22 +399,29 @@ __global__ void __launch_bounds__(kPalThreads) pal_min_kernel(const float* __res
 #pragma unroll
         for (int t = 0; t < kPalQT; ++t) {
             const int q = qbase + t * kPalThreads;
-            if (q < nq) atomicMax(best + q, pack_best(-bv[t], static_cast<uint32_t>(bi[t])));
+            if (q < nq) atomicMax(best + q, pack_best(-bv[t], static_cast<uint32_t>(kidx_base + bi[t])));
         }
     }
 }
 
 // Sparse backward of the 3-channel relaxed EMD w.r.t. the prediction's RGB (through the YUV matrix).
-// gpal[j][0..2] += weight-less gradient; one thread per selected pair.
+// gpal[j - r0][0..2] += gradient for prediction rows owned by this rank; one thread per selected pair.
 __global__ void pal_backward_kernel(const unsigned long long* __restrict__ rowbest, int M,
-                                    const unsigned long long* __restrict__ colbest, int N,
+                                    const unsigned long long* __restrict__ colbest, int N, int r0, int r1,
                                     const float* __restrict__ arec, const float* __restrict__ brec, int mode, int convert,
                                     const float* __restrict__ scalars, int slot_branch, float* __restrict__ gpal) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool bx = scalars[slot_branch] != 0.f;
     int i, j; float wgt;
-    if (bx) { if (t >= M) return; i = t; j = static_cast<int>(best_idx(rowbest[t])); wgt = 1.f / static_cast<float>(M); }
-    else    { if (t >= N) return; j = t; i = static_cast<int>(best_idx(colbest[t])); wgt = 1.f / static_cast<float>(N); }
+    if (bx) {
+        if (t >= M) return;
+        i = t; j = static_cast<int>(best_idx(rowbest[t])); wgt = 1.f / static_cast<float>(M);
+        if (j < r0 || j >= r1) return;
+    } else {
+        j = r0 + t;
+        if (j >= r1) return;
+        i = static_cast<int>(best_idx(colbest[j])); wgt = 1.f / static_cast<float>(N);
+    }
     const float* a = arec + static_cast<long long>(i) * 8;
     const float* b = brec + static_cast<long long>(j) * 8;
     float g[3] = {0.f, 0.f, 0.f};
@@ -419,7 +446,7 @@ __global__ void pal_backward_kernel(const unsigned long long* __restrict__ rowbe
         for (int c = 0; c < 3; ++c) o[c] = g[0] * c_rgb2yuv[3 * c] + g[1] * c_rgb2yuv[3 * c + 1] + g[2] * c_rgb2yuv[3 * c + 2];
     } else { o[0] = g[0]; o[1] = g[1]; o[2] = g[2]; }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) atomicAdd(gpal + static_cast<long long>(j) * 4 + c, o[c] * wgt);
+    for (int c = 0; c < 3; ++c) atomicAdd(gpal + static_cast<long long>(j - r0) * 4 + c, o[c] * wgt);
 }
 
 // --------------------------------------------------------------------------------------
@@ -452,8 +479,10 @@ __global__ void __launch_bounds__(1024) moment_finish_kernel(const float* __rest
 }
 
 // loss_s = l_m + l_remd + inv_alpha*l_pal ; total = (alpha*loss_c + loss_s)/denom   (run_strotss.py:40,140)
-__global__ void combine_scalars_kernel(float* __restrict__ s, float alpha, float inv_alpha, float denom) {
+__global__ void combine_scalars_kernel(float* __restrict__ s, float alpha, float inv_alpha, float denom,
+                                       const float* __restrict__ ss_loss_sum, float inv_n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (ss_loss_sum) s[S_LOSS_C] = *ss_loss_sum * inv_n;
         const float ls = s[S_LM] + s[S_LREMD] + inv_alpha * s[S_LPAL];
         s[S_LOSS_S] = ls;
         s[S_TOTAL] = (alpha * s[S_LOSS_C] + ls) / denom;
@@ -470,6 +499,7 @@ __global__ void combine_scalars_kernel(float* __restrict__ s, float alpha, float
 // --------------------------------------------------------------------------------------
 struct FinalizeArgs {
     const float* x; long long ldx; const float* inv; int N, D;
+    int r0;                                   // first prediction row owned by this rank; local buffers start there
     const float* ss2; long long ld_ss2; const float* v; const float* coef; const float* sumhat; float w_ss;
     const float* gremd; long long ld_gremd; float w_remd;
     const float* Q; long long ldq; float q_scale; const float* gmu; float w_mom;
@@ -481,7 +511,8 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a
     extern __shared__ float sg[];       // D floats: g^
     __shared__ float sh[8];
     __shared__ float s_dot;
-    const int i = blockIdx.x;
+    const int li = blockIdx.x;                // local row (ss2, gremd, Q, gpal)
+    const int i = a.r0 + li;                  // global row (x, inv, coef, grad)
     const float* xr = a.x + static_cast<long long>(i) * a.ldx;
     const float iv = a.inv[i];
     const float invN = 1.f / static_cast<float>(a.N);
@@ -489,8 +520,8 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a
     float dot = 0.f, ssq = 0.f;
     for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
         float g = 0.f;
-        if (a.ss2) g += a.w_ss * (-a.ss2[static_cast<long long>(i) * a.ld_ss2 + d] * invN + a.v[d] + ci * a.sumhat[d]);
-        if (a.gremd) g += a.w_remd * a.gremd[static_cast<long long>(i) * a.ld_gremd + d];
+        if (a.ss2) g += a.w_ss * (-a.ss2[static_cast<long long>(li) * a.ld_ss2 + d] * invN + a.v[d] + ci * a.sumhat[d]);
+        if (a.gremd) g += a.w_remd * a.gremd[static_cast<long long>(li) * a.ld_gremd + d];
         sg[d] = g;
         const float xv = xr[d];
         dot = fmaf(g, xv, dot);
@@ -511,8 +542,8 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a
     float* gr = a.grad + static_cast<long long>(i) * a.ldg;
     for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
         float o = sg[d] * iv - xr[d] * pd;
-        if (a.Q) o += a.w_mom * (a.q_scale * a.Q[static_cast<long long>(i) * a.ldq + d] + a.gmu[d] * invN);
-        if (a.gpal && d < 3) o += a.w_pal * a.gpal[static_cast<long long>(i) * 4 + d];
+        if (a.Q) o += a.w_mom * (a.q_scale * a.Q[static_cast<long long>(li) * a.ldq + d] + a.gmu[d] * invN);
+        if (a.gpal && d < 3) o += a.w_pal * a.gpal[static_cast<long long>(li) * 4 + d];
         gr[d] = o;
     }
 }

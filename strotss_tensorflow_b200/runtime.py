@@ -56,6 +56,7 @@ class Handle:
             self._h = None
             raise _lib.StrotssError(f"strotss_create(device={idx}) failed (code {code}): {msg}")
         self.style_shape = None
+        self.rank, self.world = 0, 1
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -77,6 +78,17 @@ class Handle:
     @property
     def workspace_bytes(self) -> int:
         return int(self.lib.strotss_workspace_bytes(self._h))
+
+    # ---- multi-GPU ------------------------------------------------------------------
+    def comm_init(self, rank: int, world: int, unique_id):
+        """Attach this handle to an NCCL communicator (see distributed.attach)."""
+        self._ck(self.lib.strotss_comm_init(self._h, int(rank), int(world), unique_id), "strotss_comm_init")
+        self.rank, self.world = int(rank), int(world)
+
+    def shard_rows(self, N: int):
+        r0, r1 = C.c_int(), C.c_int()
+        self._ck(self.lib.strotss_shard_rows(self._h, int(N), C.byref(r0), C.byref(r1)), "strotss_shard_rows")
+        return r0.value, r1.value
 
     def profile_enable(self, on: bool = True):
         self._ck(self.lib.strotss_profile_enable(self._h, 1 if on else 0), "strotss_profile_enable")

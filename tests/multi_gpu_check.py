@@ -1,0 +1,57 @@
+"""Multi-GPU parity check (developer/driver tool; launch with torchrun, one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py
+Every rank evaluates the same problem twice -- row-sharded over all ranks, and alone on its own GPU --
+and the sharded scalars / gradient rows must match the single-GPU ones."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import strotss_tensorflow_b200 as S  # noqa: E402
+from strotss_tensorflow_b200 import distributed as Dm  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for (N, M, eps) in [(1000, 777, 0.1), (4096, 4096, 1.0), (130, 300, 0.1)]:
+        style, content, pred = bench.synth_torch(N, M, 2179, eps, 0, dev)
+        solo = S.Handle(dev)
+        solo.set_style_target(style)
+        s1, g1, ra1, ca1 = solo.eval(pred, content, 16.0, True, True)
+        sh = S.Handle(dev)
+        Dm.attach(sh)
+        sh.set_style_target(style)
+        s2, g2, ra2, ca2 = sh.eval(pred, content, 16.0, True, True)
+        torch.cuda.synchronize()
+        r0, r1 = sh.shard_rows(N)
+        assert (r0, r1) == Dm.shard_rows(N, world, rank)
+        ds = float((s1[:12] - s2[:12]).abs().max() / s1[:12].abs().max())
+        dg = float((g1[r0:r1] - g2[r0:r1]).norm() / g1.norm()) if r1 > r0 else 0.0
+        same_rows = bool(torch.equal(ra1, ra2))
+        same_cols = bool(torch.equal(ca1[r0:r1], ca2[r0:r1]))
+        full = Dm.all_gather_rows(g2, N)
+        dfull = float((full - g1).norm() / g1.norm())
+        good = ds < 1e-5 and dg < 1e-4 and same_rows and same_cols and dfull < 1e-4
+        ok = ok and good
+        print(f"[rank {rank}/{world}] N={N} M={M}: rows [{r0},{r1}) scalars rel diff {ds:.2e}, grad rows rel diff {dg:.2e}, "
+              f"gathered grad rel diff {dfull:.2e}, argmin equal {same_rows}/{same_cols} -> {'OK' if good else 'MISMATCH'}", flush=True)
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if t.item() != 1.0:
+        raise SystemExit(1)
+    if rank == 0:
+        print("multi-GPU parity: OK")
+
+
+if __name__ == "__main__":
+    main()
