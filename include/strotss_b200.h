@@ -140,6 +140,10 @@ int strotss_convert_rgb_to_yuv(strotss_handle h, const float* x, long long ldx, 
 int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha,
                        float* C, int tile_n, void* stream);
 
+/* Test hook for the MN-major (transposed-A) operand path: At is k x m; C (+)= alpha * At^T . B^T. */
+int strotss_debug_gemm_ta(strotss_handle h, const float* At, int m, const float* B, int n, int k, float alpha,
+                          float* C, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

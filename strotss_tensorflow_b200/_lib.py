@@ -41,6 +41,7 @@ SIGNATURES = {
     "strotss_self_similarity": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp]),
     "strotss_convert_rgb_to_yuv": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "strotss_debug_gemm": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
+    "strotss_debug_gemm_ta": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
 }
 
 _lib = None

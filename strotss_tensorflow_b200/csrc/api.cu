@@ -163,12 +163,28 @@ int make_tmap(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int rows, int kc
     return 0;
 }
 
-template <int BN, int NACC, int STAGES, int EPI_WARPS = 4, class Epi>
+// Tensor map for an MN-major A operand: the matrix is stored k_rows x m_extent (m contiguous).
+int make_tmap_mn(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int m_extent, int k_rows, long long ld_elems) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(m_extent), static_cast<cuuint64_t>(k_rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * sizeof(bf16)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BK)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        h->err = "cuTensorMapEncodeTiled (MN-major) failed with code " + std::to_string(static_cast<int>(r));
+        return STROTSS_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <int BN, int NACC, int STAGES, int EPI_WARPS = 4, bool A_MN = false, class Epi>
 int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     using Cfg = TileCfg<BN, NACC>;
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    auto kern = gemm_kernel<BN, NACC, STAGES, EPI_WARPS, Epi>;
+    auto kern = gemm_kernel<BN, NACC, STAGES, EPI_WARPS, Epi, A_MN>;
     static bool configured = false;
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -207,8 +223,8 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
     if (w.sumhat) { RET(ensure(h, (t + ".sumhat").c_str(), D, &f.sumhat)); RET(ensure(h, (t + ".phat").c_str(), (size_t)nblk * D, &part_hat)); }
     row_stats_kernel<<<nblk, 256, 0, st>>>(x, ld, n, D, f.inv, part_raw, part_hat);
     CKL();
-    if (w.mean) { colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(part_raw, nblk, D, 1.f / n, f.mean); CKL(); }
-    if (w.sumhat) { colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(part_hat, nblk, D, 1.f, f.sumhat); CKL(); }
+    if (w.mean) { colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(part_raw, nblk, D, 1.f / n, f.mean); CKL(); }
+    if (w.sumhat) { colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(part_hat, nblk, D, 1.f, f.sumhat); CKL(); }
     EmitArgs a{};
     a.x = x; a.ldx = ld; a.n = n; a.D = D; a.Dp = Dp; a.np = f.np; a.inv = f.inv; a.mean = f.mean;
     if (w.xh) { RET(ensure(h, (t + ".xh").c_str(), (size_t)n * Dp, &f.xh)); a.xh = f.xh; }
@@ -466,6 +482,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     // row panel of P (bf16), sized to stay L2-resident between its producer and consumer GEMMs
     int panel = 2048;
     if (panel > round_up(sh.n() > 0 ? sh.n() : 1, BM)) panel = round_up(sh.n() > 0 ? sh.n() : 1, BM);
+    // Symmetric mode (this rank owns every row): Xd and Yd are symmetric, so a panel only computes the
+    // column tiles at or right of its own rows; tiles strictly right of the panel also account for their
+    // mirror images (loss, r column sums, and the transposed product P^T x^ in "stage 2b").
+    const bool sym = (sh.r0 == 0 && sh.r1 == N);
+    float* rcol_part = nullptr;
+    if (sym) RET(ensure(h, "ss.rcol_part", (size_t)((N + BM - 1) / BM) * 4 * N, &rcol_part));
     bf16* P = nullptr;
     out.ss2 = nullptr; out.ld = 0;
     if (want_grad && sh.n() > 0) {
@@ -486,28 +508,45 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         p.nseg = 3;
         for (int s = 0; s < 3; ++s) p.seg_kblocks[s] = Dp / BK;
         p.seg_acc[0] = 0; p.seg_acc[1] = 0; p.seg_acc[2] = 1;
-        p.tiles_m = (rows + BM - 1) / BM; p.tiles_n = tiles_n;
-        p.a_row0 = r0; p.b_row0 = 0;
+        const int c0 = sym ? r0 : 0;                       // first column computed by this panel
+        p.tiles_m = (rows + BM - 1) / BM; p.tiles_n = (N - c0 + kSsBN - 1) / kSsBN;
+        p.a_row0 = r0; p.b_row0 = c0;
         p.epi.u = u; p.epi.w = w; p.epi.P = P; p.epi.ldp = np; p.epi.panel_row0 = r0;
         p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.row_end = sh.r1;
         p.epi.write_p = (want_grad ? 1 : 0);
+        p.epi.sym = sym ? 1 : 0; p.epi.panel_end = r0 + panel; p.epi.rcol_part = rcol_part;
         { PhaseTimer _pt(h, PH_SS1, st); RET((launch_gemm<kSsBN, 2, 4, kSsEpiWarps>(h, p, st))); }
         if (want_grad) {
+            // stage 2a: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]
             GemmParams<EpiStoreT<256>> q{};
-            RET(make_tmap(h, &q.tmA[0], P, rows, np, np, BM));
-            RET(make_tmap(h, &q.tmB[0], x.xhT, D, np, np, 256));
-            q.nseg = 1; q.seg_kblocks[0] = np / BK; q.seg_acc[0] = 0;
+            RET(make_tmap(h, &q.tmA[0], P + c0, rows, np - c0, np, BM));
+            RET(make_tmap(h, &q.tmB[0], x.xhT + c0, D, np - c0, np, 256));
+            q.nseg = 1; q.seg_kblocks[0] = (np - c0) / BK; q.seg_acc[0] = 0;
             q.tiles_m = (rows + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
             q.a_row0 = 0; q.b_row0 = 0;
             q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
-            q.epi.alpha = 1.f; q.epi.row_off = 0;
+            q.epi.alpha = 1.f; q.epi.row_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
             PhaseTimer _pt(h, PH_SS2, st);
             RET((launch_gemm<256, 1, 4>(h, q, st)));
+            if (sym && r0 + panel < N) {
+                // stage 2b: ss2[rows right of the panel] += P[panel, those columns]^T . x^[panel rows]
+                const int m0 = r0 + panel, mext = N - m0;
+                GemmParams<EpiStoreT<256>> t{};
+                RET(make_tmap_mn(h, &t.tmA[0], P + m0, mext, rows, np));
+                RET(make_tmap(h, &t.tmB[0], x.xhT + r0, D, rows, np, 256));
+                t.nseg = 1; t.seg_kblocks[0] = (rows + BK - 1) / BK; t.seg_acc[0] = 0;
+                t.tiles_m = (mext + BM - 1) / BM; t.tiles_n = (D + 255) / 256;
+                t.a_row0 = 0; t.b_row0 = 0;
+                t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = mext; t.epi.cols = D;
+                t.epi.alpha = 1.f; t.epi.row_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
+                RET((launch_gemm<256, 1, 4, 4, true>(h, t, st)));
+            }
         }
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
-        ss_rows_kernel<<<(sh.n() + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss);
+        ss_rows_kernel<<<(sh.n() + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
+                                                             sym ? 1 : 0, panel, (panel / kSsBN) * kSsSplit, rcol_part, (panel / BM) * 4);
         CKL();
     }
     reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss + sh.r0, sh.n(), 1.f, loss_partial);
@@ -520,7 +559,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
                                                          out.coef + sh.r0, vpart);
             CKL();
-            colsum_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(vpart, nblk, D, 1.f, v_partial);
+            colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(vpart, nblk, D, 1.f, v_partial);
             CKL();
         } else {
             CK(cudaMemsetAsync(v_partial, 0, sizeof(float) * D, st));
@@ -912,6 +951,30 @@ int strotss_convert_rgb_to_yuv(strotss_handle h, const float* x, long long ldx, 
     yuv_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, n, out);
     CKL();
     return 0;
+}
+
+// C[m][n] (+)= alpha * sum_k bf16(At[k][m]) * bf16(B[n][k]): A is given TRANSPOSED (k x m) and read through
+// the MN-major descriptor path.
+int strotss_debug_gemm_ta(strotss_handle h, const float* At, int m, const float* B, int n, int k, float alpha, float* C,
+                          int accumulate, void* stream) {
+    RET(check_handle(h));
+    if (!At || !B || !C || m <= 0 || n <= 0 || k <= 0) { h->err = "debug_gemm_ta: bad argument"; return STROTSS_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int kp = round_up(k, BK), mp = round_up(m, 64);
+    bf16 *a16, *b16;
+    RET(ensure(h, "dbg.a", (size_t)k * mp, &a16));
+    RET(ensure(h, "dbg.b", (size_t)n * kp, &b16));
+    cast_pad_kernel<<<(unsigned)(((long long)k * mp + 255) / 256), 256, 0, st>>>(At, k, m, a16, mp); CKL();
+    cast_pad_kernel<<<(unsigned)(((long long)n * kp + 255) / 256), 256, 0, st>>>(B, n, k, b16, kp); CKL();
+    GemmParams<EpiStoreT<256>> p{};
+    RET(make_tmap_mn(h, &p.tmA[0], a16, m, k, mp));
+    RET(make_tmap(h, &p.tmB[0], b16, n, k, kp, 256));
+    p.nseg = 1; p.seg_kblocks[0] = kp / BK; p.seg_acc[0] = 0;
+    p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + 255) / 256;
+    p.epi.C = C; p.epi.ldc = n; p.epi.rows = m; p.epi.cols = n; p.epi.alpha = alpha; p.epi.row_off = 0;
+    p.epi.accumulate = accumulate ? 1 : 0;
+    return launch_gemm<256, 1, 4, 4, true>(h, p, st);
 }
 
 int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha, float* C, int tile_n,

@@ -139,12 +139,25 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                              // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// MN-major operand tile (the M/N index is contiguous in memory, K strided), 128-byte swizzle:
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, i.e. 64 elements of MN per
+// 128-byte row, one row per k, 8-row groups SBO = 1024 B apart, 64-element MN chunks LBO apart.
+// Two TMA boxes {64 (mn), 64 (k)} stacked 8192 B apart produce exactly this for a 128 x 64 tile.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;                 // LBO: next 64-wide MN chunk
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                      // SBO: next group of 8 k-rows
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M x N tile; B K-major, A K- or MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false) {
     return (1u << 4)                 // D format  = F32
          | (1u << 7)                 // A format  = BF16
          | (1u << 10)                // B format  = BF16
-         | (0u << 15) | (0u << 16)   // A, B K-major
+         | ((a_mn_major ? 1u : 0u) << 15) | (0u << 16)
          | (static_cast<uint32_t>(N >> 3) << 17)
          | (static_cast<uint32_t>(M >> 4) << 24);
 }

@@ -75,7 +75,9 @@ __device__ __forceinline__ void epi_bar_sync() {
     asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory");
 }
 
-template <int BN, int NACC, int STAGES, int EPI_WARPS, class Epi>
+// A_MN: the A operand is read from a matrix stored K x M (M contiguous), i.e. A = (stored)^T, through
+// MN-major shared-memory descriptors; its tensor map has dims {M, K} and box {64, 64}.
+template <int BN, int NACC, int STAGES, int EPI_WARPS, class Epi, bool A_MN = false>
 __global__ void __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
 gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
@@ -122,7 +124,12 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
                         uint8_t* sB = sA + Cfg::A_BYTES;
                         mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                        tma_load_2d(sA, &p.tmA[s], &full[stage], kb * BK, arow);
+                        if constexpr (A_MN) {
+                            tma_load_2d(sA, &p.tmA[s], &full[stage], arow, kb * BK);
+                            tma_load_2d(sA + Cfg::A_BYTES / 2, &p.tmA[s], &full[stage], arow + 64, kb * BK);
+                        } else {
+                            tma_load_2d(sA, &p.tmA[s], &full[stage], kb * BK, arow);
+                        }
                         tma_load_2d(sB, &p.tmB[s], &full[stage], kb * BK, brow);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -131,7 +138,7 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -145,12 +152,14 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(a_addr, Cfg::A_BYTES / 2)
+                                                    : make_kmajor_sw128_desc(a_addr);
                         const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+                        // K-major: 16 bf16 = 32 bytes along K inside the swizzle atom; MN-major: 16 k-rows = 2048 bytes
+                        constexpr uint32_t a_step = A_MN ? (16 * 128) >> 4 : 2;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom
-                            umma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc,
+                            umma_bf16(d_addr, adesc + a_step * k, bdesc + 2 * k, idesc,
                                       ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
                         }
                         touched |= (1u << acc);
@@ -203,7 +212,7 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
 // ---- plain store:  C[row][col] = alpha * acc   (fp32, row stride ldc) -----------------
 struct EpiStore {
     static constexpr int SMEM_BYTES = 0;
-    struct Params { float* C; long long ldc; int rows, cols; float alpha; int row_off; };
+    struct Params { float* C; long long ldc; int rows, cols; float alpha; int row_off; int accumulate; };
     struct State {};
     __device__ static void init(State&, const Params&, int, int) {}
     __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
@@ -225,12 +234,15 @@ struct EpiStore {
                     for (int e = 0; e < 32; e += 4) {
                         float4 v = make_float4(__uint_as_float(r[e]) * P.alpha, __uint_as_float(r[e + 1]) * P.alpha,
                                                __uint_as_float(r[e + 2]) * P.alpha, __uint_as_float(r[e + 3]) * P.alpha);
-                        *reinterpret_cast<float4*>(crow + col + e) = v;
+                        float4* dst = reinterpret_cast<float4*>(crow + col + e);
+                        if (P.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *dst = v;
                     }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 32; ++e)
-                        if (col + e < P.cols) crow[col + e] = __uint_as_float(r[e]) * P.alpha;
+                        if (col + e < P.cols)
+                            crow[col + e] = __uint_as_float(r[e]) * P.alpha + (P.accumulate ? crow[col + e] : 0.f);
                 }
             }
         }
@@ -305,6 +317,10 @@ struct EpiSS1 {
         int N;
         int row_end;                          // rows >= row_end belong to another rank (or do not exist)
         int write_p;
+        // symmetric mode (single GPU): only column tiles >= the panel's first row are computed; tiles
+        // strictly right of the panel (col0 >= panel_end) also account for their mirror images:
+        int sym, panel_end;
+        float* rcol_part;                     // [row_blocks * 4][N]: per-warp column sums of sign_col * Xd
     };
     struct State {};
     __device__ static void init(State&, const Params&, int, int) {}
@@ -326,6 +342,7 @@ struct EpiSS1 {
         const float ui = rvalid ? P.u[row] : 0.f;
         const float wi = rvalid ? P.w[row] : 0.f;
         float loss = 0.f, racc = 0.f;
+        const bool both = P.sym && (ti.col0 >= P.panel_end);
         __nv_bfloat16* prow = P.P + static_cast<long long>(row - P.panel_row0) * P.ldp;
 #pragma unroll 1
         for (int c = ti.c0; c < ti.c1; ++c) {
@@ -335,6 +352,7 @@ struct EpiSS1 {
             tmem_ld_wait();
             const int colbase = ti.col0 + c * 32;
             uint32_t packed[16];
+            float cv[32];                     // sign_col * Xd, reduced over the warp's rows when `both`
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
                 float pv[2];
@@ -351,6 +369,7 @@ struct EpiSS1 {
                     const float sr = live ? ((tr > 0.f) ? 1.f : ((tr < 0.f) ? -1.f : 0.f)) : 0.f;
                     loss += live ? fabsf(tr) : 0.f;
                     racc = fmaf(sr, yd + diff, racc);
+                    if (both) { loss += live ? fabsf(tc) : 0.f; cv[e + h] = sc * (yd + diff); }
                     pv[h] = fmaf(sc, uj, sr * ui);
                 }
                 packed[e >> 1] = pack_bf16x2(pv[0], pv[1]);
@@ -363,9 +382,25 @@ struct EpiSS1 {
                 for (int v = 0; v < 4; ++v)
                     dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
             }
+            if (both) {
+                // transpose-reduce: after 5 exchange steps lane l holds the sum over the warp's 32 rows of column l
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+                    const bool up = (ti.lane & sft) != 0;
+#pragma unroll
+                    for (int e = 0; e < sft; ++e) {
+                        const float send = up ? cv[e] : cv[e + sft];
+                        const float keep = up ? cv[e + sft] : cv[e];
+                        cv[e] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                    }
+                }
+                const int col = colbase + ti.lane;
+                if (col < P.N)
+                    P.rcol_part[(static_cast<long long>(ti.row0 / BM) * 4 + ti.q) * P.N + col] = cv[0];
+            }
         }
         if (rvalid) {
-            const long long slot = static_cast<long long>(ti.tn) * ti.nsplit + ti.csplit;
+            const long long slot = static_cast<long long>(ti.col0 / BN) * ti.nsplit + ti.csplit;
             P.loss_part[slot * P.N + row] = loss;
             P.r_part[slot * P.N + row] = racc;
         }

@@ -78,14 +78,24 @@ __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __res
     }
 }
 
-// out[d] = scale * sum_b part[b][d]   (fixed order)
-__global__ void colsum_finish_kernel(const float* __restrict__ part, int nblocks, int D, float scale,
-                                     float* __restrict__ out) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
+// out[d] = scale * sum_b part[b][d]   (fixed order: 8 interleaved block groups, then a fixed tree)
+// block = 32 columns x 8 block-groups
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ part, int nblocks, int D, float scale,
+                                                            float* __restrict__ out) {
+    __shared__ float sh[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + c;
     float a = 0.f;
-    for (int b = 0; b < nblocks; ++b) a += part[static_cast<long long>(b) * D + d];
-    out[d] = a * scale;
+    if (d < D)
+        for (int b = g; b < nblocks; b += 8) a += part[static_cast<long long>(b) * D + d];
+    sh[g][c] = a;
+    __syncthreads();
+    if (g == 0 && d < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][c];
+        out[d] = t * scale;
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -200,16 +210,25 @@ __global__ void __launch_bounds__(256) ss_vectors_kernel(const float* __restrict
     }
 }
 
-// r_i = (1/N) sum_tn r_part[tn][i];  coef_i = r_i u_i^2 [s_i >= clamp];  rowloss_i = sum_tn loss_part[tn][i]
-__global__ void ss_rows_kernel(const float* __restrict__ loss_part, const float* __restrict__ r_part, int ntn, int N,
+// r_i = (1/N) sum of the row-form partials (+ in symmetric mode the column-form partials written by the
+// panels left of row i's panel);  coef_i = r_i u_i^2 [s_i >= clamp];  rowloss_i = sum of loss partials.
+// In symmetric mode a panel only wrote the slots of column tiles >= its first row.
+__global__ void ss_rows_kernel(const float* __restrict__ loss_part, const float* __restrict__ r_part, int nslots, int N,
                                int r0, int r1, const float* __restrict__ u, const float* __restrict__ sclamp,
-                               float* __restrict__ coef, float* __restrict__ rowloss) {
+                               float* __restrict__ coef, float* __restrict__ rowloss,
+                               int sym, int panel_rows, int slots_per_panel, const float* __restrict__ rcol_part,
+                               int colparts_per_panel) {
     const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r1) return;
+    const int pi = sym ? i / panel_rows : 0;
     float l = 0.f, r = 0.f;
-    for (int t = 0; t < ntn; ++t) {
+    for (int t = pi * slots_per_panel * sym; t < nslots; ++t) {
         l += loss_part[static_cast<long long>(t) * N + i];
         r += r_part[static_cast<long long>(t) * N + i];
+    }
+    if (sym) {
+        const int nb = pi * colparts_per_panel;
+        for (int b = 0; b < nb; ++b) r += rcol_part[static_cast<long long>(b) * N + i];
     }
     rowloss[i] = l;
     const float ui = u[i];

@@ -210,6 +210,19 @@ class Handle:
                  "strotss_debug_gemm")
         return Cm
 
+    def debug_gemm_ta(self, At, B, alpha=1.0, C=None):
+        """C (+)= alpha * At^T @ B^T with At given (k, m): exercises the MN-major A descriptor path."""
+        At = _check_features("At", At).contiguous()
+        B = _check_features("B", B).contiguous()
+        k, m = At.shape
+        n = B.shape[0]
+        acc = C is not None
+        if C is None:
+            C = torch.empty(m, n, device=At.device, dtype=torch.float32)
+        self._ck(self.lib.strotss_debug_gemm_ta(self._h, _ptr(At), m, _ptr(B), n, k, float(alpha), _ptr(C), 1 if acc else 0,
+                                                _stream(At.device)), "strotss_debug_gemm_ta")
+        return C
+
 
 _shared: Dict[int, Handle] = {}
 

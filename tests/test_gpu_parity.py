@@ -58,6 +58,20 @@ def test_tcgen05_gemm_core(handle, cuda_device, m, n, k, tile):
     assert (C.double() - ref).abs().max().item() <= 1e-5 * k ** 0.5 * ref.abs().max().item() + 1e-6
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 500, 2048), (1000, 2179, 200), (64, 16, 64), (129, 257, 130)])
+def test_tcgen05_gemm_transposed_a(handle, cuda_device, m, n, k):
+    """MN-major A operand (used by stage 2b of the symmetric self-similarity) incl. the accumulate epilogue."""
+    g = torch.Generator().manual_seed(m + 3 * n + k)
+    At = torch.randn(k, m, generator=g).to(cuda_device)
+    B = torch.randn(n, k, generator=g).to(cuda_device)
+    ref = At.bfloat16().double().T @ B.bfloat16().double().T
+    C = handle.debug_gemm_ta(At, B, 1.0)
+    tol = 1e-5 * k ** 0.5 * ref.abs().max().item() + 1e-6
+    assert (C.double() - ref).abs().max().item() <= tol
+    C2 = handle.debug_gemm_ta(At, B, 0.5, C=C.clone())
+    assert (C2.double() - 1.5 * ref).abs().max().item() <= 2 * tol
+
+
 # ------------------------------------------------------------------------------ relaxed EMD
 @pytest.mark.parametrize("N,M,seed", [(700, 517, 0), (333, 1024, 1), (128, 256, 2), (1, 300, 3), (130, 1, 4)])
 def test_relaxed_emd_cosine(handle, cuda_device, N, M, seed):
@@ -160,6 +174,23 @@ def test_self_similarity(handle, cuda_device, N, eps, seed):
     assert float((grad * _t(pr, cuda_device)).sum(dim=1).abs().max()) <= 1e-3 * float(grad.norm())
     same = handle.self_similarity(_t(co, cuda_device), _t(co, cuda_device), False)[0].item()
     assert abs(same) <= 1e-6 * max(l64, 1e-4) * 100
+
+
+@pytest.mark.parametrize("N,D,eps,seed", [(4500, 515, 0.1, 31), (2300, 2179, 0.1, 32), (4096, 259, 1.0, 33)])
+def test_self_similarity_multi_panel(handle, cuda_device, N, D, eps, seed):
+    """N > 2048: several row panels; exercises the symmetric path (mirror accounting, transposed stage 2b)."""
+    st, co, pr = O.synth_problem(N, 8, D, eps=eps, seed=seed)
+    out, grad = handle.self_similarity(_t(pr, cuda_device), _t(co, cuda_device), True)
+    l64, g64, _ = O.self_similarity(pr, co, np.float64, True)
+    assert abs(out.item() - l64) / l64 <= LOSS_RTOL
+    _gcheck(grad, g64, cos_min=0.999)
+    # every row block must carry the right gradient, not just the total
+    g = grad.double().cpu().numpy()
+    for lo in range(0, N, 1024):
+        ref = g64[lo:lo + 1024]
+        got = g[lo:lo + 1024]
+        assert abs(np.linalg.norm(got) - np.linalg.norm(ref)) / np.linalg.norm(ref) <= GRADNORM_RTOL
+        assert float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref))) >= 0.999
 
 
 # ------------------------------------------------------------------------------ fused evaluation
