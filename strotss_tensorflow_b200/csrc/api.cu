@@ -12,6 +12,9 @@
 #include "../../include/strotss_b200.h"
 #include "gemm_core.cuh"
 #include "kernels.cuh"
+#include "gemm2_core.cuh"
+#include "ss1_kernel.cuh"
+#include <cstdlib>
 
 using namespace sb;
 typedef __nv_bfloat16 bf16;
@@ -208,6 +211,48 @@ int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     return 0;
 }
 
+// CTA-pair (cta_group::2) kernels are the default for the 256-wide tiles; STROTSS_NO_PAIR=1 falls back to
+// one CTA per 128 x 256 tile (kept for A/B measurements).
+bool pair_enabled() {
+    static const bool on = (getenv("STROTSS_NO_PAIR") == nullptr);
+    return on;
+}
+// rows of the B box in a tensor map: each CTA of a pair stages half of the 256-row B tile
+int bbox256() { return pair_enabled() ? 128 : 256; }
+
+// p.tiles_m counts 128-row blocks (as for the single-CTA kernel); converted to 256-row pair tiles here.
+template <int NACC, int EPI_WARPS = 4, class Epi>
+int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
+    if (!pair_enabled()) return launch_gemm<256, NACC, 4, EPI_WARPS>(h, p, st);
+    using Cfg = PairCfg<NACC>;
+    constexpr int STAGES = 6;
+    constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
+    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    GemmParams<Epi> q = p;
+    q.tiles_m = (p.tiles_m + 1) / 2;
+    const int tiles = q.tiles_m * q.tiles_n;
+    if (tiles <= 0) return 0;
+    {
+        long long kbytes = 0;
+        for (int s = 0; s < p.nseg; ++s) kbytes += static_cast<long long>(p.seg_kblocks[s]) * BK * 2;
+        long long g = (32ll << 20) / (kbytes * 256);
+        if (g < 4) g = 4;
+        if (g > q.tiles_n) g = q.tiles_n;
+        q.group_n = static_cast<int>(g);
+    }
+    const int max_pairs = h->num_sms / 2;
+    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    CKL();
+    return 0;
+}
+
 // ---- operand preparation --------------------------------------------------------------
 struct PrepWant { bool mean, sumhat, xh, cen, dlt, xhT, cenT, rec; };
 
@@ -253,11 +298,11 @@ int cov_store(strotss_ctx* h, const Feat& f, int D, int Dp, float* V, cudaStream
     PhaseTimer _pt(h, PH_COV_FWD, st);
     GemmParams<EpiStoreT<256>> p{};
     RET(make_tmap(h, &p.tmA[0], f.cenT, D, f.np, f.np, BM));
-    RET(make_tmap(h, &p.tmB[0], f.cenT, D, f.np, f.np, 256));
+    RET(make_tmap(h, &p.tmB[0], f.cenT, D, f.np, f.np, bbox256()));
     p.nseg = 1; p.seg_kblocks[0] = f.np / BK; p.seg_acc[0] = 0;
     p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
     p.epi.C = V; p.epi.ldc = Dp; p.epi.rows = D; p.epi.cols = D; p.epi.alpha = 1.f / f.n; p.epi.row_off = 0;
-    return launch_gemm<256, 1, 4>(h, p, st);
+    return launch_gemm256<1>(h, p, st);
 }
 
 // ---- the three loss terms, each leaving its gradient contribution in workspace buffers --
@@ -328,13 +373,13 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
     if (sh.n() > 0) {
         GemmParams<EpiRemd<256>> p{};
         RET(make_tmap(h, &p.tmA[0], target.xh, M, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[0], pred.xh, N, Dp, Dp, 256));
+        RET(make_tmap(h, &p.tmB[0], pred.xh, N, Dp, Dp, bbox256()));
         p.nseg = 1; p.seg_kblocks[0] = Dp / BK; p.seg_acc[0] = 0;
         p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (sh.n() + 255) / 256;
         p.a_row0 = 0; p.b_row0 = sh.r0;
         p.epi.rowbest = rs.rowbest; p.epi.colbest = rs.colbest; p.epi.M = M; p.epi.N = sh.r1;
         PhaseTimer _pt(h, PH_REMD_GEMM, st);
-        RET((launch_gemm<256, 1, 4>(h, p, st)));
+        RET((launch_gemm256<1>(h, p, st)));
     }
     PhaseTimer _pm(h, PH_REMD_MISC, st);
     best_partial_kernel<<<1, 1024, 0, st>>>(rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
@@ -423,14 +468,16 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     RET(ensure(h, "mom.Sg", (size_t)Dp * Dp, &Sg, /*zero_on_alloc=*/true));
     GemmParams<EpiCovFwd<256>> p{};
     RET(make_tmap(h, &p.tmA[0], pred.cenT, D, pred.np, pred.np, BM));
-    RET(make_tmap(h, &p.tmB[0], pred.cenT, D, pred.np, pred.np, 256));
+    RET(make_tmap(h, &p.tmB[0], pred.cenT, D, pred.np, pred.np, bbox256()));
     p.nseg = 1; p.seg_kblocks[0] = pred.np / BK; p.seg_acc[0] = 0;
     p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
-    const int npart = p.tiles_m * p.tiles_n * 4;      // 4 epilogue warps
+    // one partial per (128-row block, column tile, epilogue warp); a pair tile always has two row blocks
+    const int npart = ((p.tiles_m + 1) / 2 * 2) * p.tiles_n * 4;
     RET(ensure(h, "mom.part", (size_t)npart, &part));
     p.epi.Vx = Vx; p.epi.ldv = Dp; p.epi.Sg = Sg; p.epi.lds = Dp; p.epi.part = part; p.epi.inv_n = 1.f / N; p.epi.D = D;
     p.epi.tiles_n = p.tiles_n;
-    { PhaseTimer _pt(h, PH_COV_FWD, st); RET((launch_gemm<256, 1, 4>(h, p, st))); }
+    CK(cudaMemsetAsync(part, 0, sizeof(float) * npart, st));
+    { PhaseTimer _pt(h, PH_COV_FWD, st); RET((launch_gemm256<1>(h, p, st))); }
     RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
     {
         PhaseTimer _pt(h, PH_MOM_MISC, st);
@@ -444,13 +491,13 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
         out.ldq = Dp; out.q_scale = 2.f / (static_cast<float>(N) * static_cast<float>(D) * static_cast<float>(D));
         GemmParams<EpiStoreT<256>> q{};
         RET(make_tmap(h, &q.tmA[0], pred.cen, N, Dp, Dp, BM));
-        RET(make_tmap(h, &q.tmB[0], Sg, D, Dp, Dp, 256));
+        RET(make_tmap(h, &q.tmB[0], Sg, D, Dp, Dp, bbox256()));
         q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
         q.tiles_m = (sh.n() + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
         q.a_row0 = sh.r0; q.b_row0 = 0;
         q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = sh.r1; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = sh.r0;
         PhaseTimer _pt(h, PH_COV_BWD, st);
-        RET((launch_gemm<256, 1, 4>(h, q, st)));
+        RET((launch_gemm256<1>(h, q, st)));
     }
     return 0;
 }
@@ -500,11 +547,13 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         GemmParams<EpiSS1<kSsBN, kSsEpiWarps>> p{};
         // segment 0: delta_I . x^_J ; segment 1: y^_I . delta_J  (both into acc 0) ; segment 2: y^_I . y^_J (acc 1)
         RET(make_tmap(h, &p.tmA[0], x.dlt, N, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[0], x.xh, N, Dp, Dp, kSsBN));
+        static const bool generic_ss1 = (getenv("STROTSS_SS1_GENERIC") != nullptr);
+        const int ssbox = (pair_enabled() && !generic_ss1) ? 128 : kSsBN;
+        RET(make_tmap(h, &p.tmB[0], x.xh, N, Dp, Dp, ssbox));
         RET(make_tmap(h, &p.tmA[1], y.xh, N, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[1], x.dlt, N, Dp, Dp, kSsBN));
+        RET(make_tmap(h, &p.tmB[1], x.dlt, N, Dp, Dp, ssbox));
         RET(make_tmap(h, &p.tmA[2], y.xh, N, Dp, Dp, BM));
-        RET(make_tmap(h, &p.tmB[2], y.xh, N, Dp, Dp, kSsBN));
+        RET(make_tmap(h, &p.tmB[2], y.xh, N, Dp, Dp, ssbox));
         p.nseg = 3;
         for (int s = 0; s < 3; ++s) p.seg_kblocks[s] = Dp / BK;
         p.seg_acc[0] = 0; p.seg_acc[1] = 0; p.seg_acc[2] = 1;
@@ -515,19 +564,60 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.row_end = sh.r1;
         p.epi.write_p = (want_grad ? 1 : 0);
         p.epi.sym = sym ? 1 : 0; p.epi.panel_end = r0 + panel; p.epi.rcol_part = rcol_part;
-        { PhaseTimer _pt(h, PH_SS1, st); RET((launch_gemm<kSsBN, 2, 4, kSsEpiWarps>(h, p, st))); }
+        if (generic_ss1) {
+            PhaseTimer _pt(h, PH_SS1, st);
+            RET((launch_gemm<kSsBN, 2, 4, kSsEpiWarps>(h, p, st)));
+        } else {
+            // specialised kernel: accumulators released separately so the epilogue overlaps the next tile
+            Ss1Params sp{};
+            sp.tmA[0] = p.tmA[2]; sp.tmB[0] = p.tmB[2];       // y^ . y^T      -> acc1 (first)
+            sp.tmA[1] = p.tmA[0]; sp.tmB[1] = p.tmB[0];       // delta . x^T   -> acc0
+            sp.tmA[2] = p.tmA[1]; sp.tmB[2] = p.tmB[1];       // y^ . delta^T  -> acc0
+            sp.kblocks = Dp / BK;
+            sp.tiles_m = p.tiles_m; sp.tiles_n = p.tiles_n; sp.a_row0 = p.a_row0; sp.b_row0 = p.b_row0;
+            sp.epi = p.epi;
+            {
+                long long g = (32ll << 20) / (3ll * sp.kblocks * BK * 2 * kSs1BN);
+                if (g < 4) g = 4;
+                if (g > sp.tiles_n) g = sp.tiles_n;
+                sp.group_n = static_cast<int>(g);
+            }
+            static bool configured = false;
+            if (!configured) {
+                CK(cudaFuncSetAttribute(ss1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1SmemBytes));
+                CK(cudaFuncSetAttribute(ss1_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1PairSmemBytes));
+                configured = true;
+            }
+            if (pair_enabled()) {
+                sp.tiles_m = (p.tiles_m + 1) / 2;              // 256-row pair tiles
+                const int tiles = sp.tiles_m * sp.tiles_n;
+                const int max_pairs = h->num_sms / 2;
+                if (tiles > 0) {
+                    PhaseTimer _pt(h, PH_SS1, st);
+                    ss1_pair_kernel<<<2 * (tiles < max_pairs ? tiles : max_pairs), kSs1Threads, kSs1PairSmemBytes, st>>>(sp);
+                    CKL();
+                }
+            } else {
+                const int tiles = sp.tiles_m * sp.tiles_n;
+                if (tiles > 0) {
+                    PhaseTimer _pt(h, PH_SS1, st);
+                    ss1_kernel<<<tiles < h->num_sms ? tiles : h->num_sms, kSs1Threads, kSs1SmemBytes, st>>>(sp);
+                    CKL();
+                }
+            }
+        }
         if (want_grad) {
             // stage 2a: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]
             GemmParams<EpiStoreT<256>> q{};
             RET(make_tmap(h, &q.tmA[0], P + c0, rows, np - c0, np, BM));
-            RET(make_tmap(h, &q.tmB[0], x.xhT + c0, D, np - c0, np, 256));
+            RET(make_tmap(h, &q.tmB[0], x.xhT + c0, D, np - c0, np, bbox256()));
             q.nseg = 1; q.seg_kblocks[0] = (np - c0) / BK; q.seg_acc[0] = 0;
             q.tiles_m = (rows + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
             q.a_row0 = 0; q.b_row0 = 0;
             q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
             q.epi.alpha = 1.f; q.epi.row_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
             PhaseTimer _pt(h, PH_SS2, st);
-            RET((launch_gemm<256, 1, 4>(h, q, st)));
+            RET((launch_gemm256<1>(h, q, st)));
             if (sym && r0 + panel < N) {
                 // stage 2b: ss2[rows right of the panel] += P[panel, those columns]^T . x^[panel rows]
                 const int m0 = r0 + panel, mext = N - m0;
@@ -994,11 +1084,11 @@ int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, 
     if (tile_n == 256) {
         GemmParams<EpiStoreT<256>> p{};
         RET(make_tmap(h, &p.tmA[0], a16, m, kp, kp, BM));
-        RET(make_tmap(h, &p.tmB[0], b16, n, kp, kp, 256));
+        RET(make_tmap(h, &p.tmB[0], b16, n, kp, kp, bbox256()));
         p.nseg = 1; p.seg_kblocks[0] = kp / BK; p.seg_acc[0] = 0;
         p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + 255) / 256;
         p.epi.C = C; p.epi.ldc = n; p.epi.rows = m; p.epi.cols = n; p.epi.alpha = alpha; p.epi.row_off = 0;
-        return launch_gemm<256, 1, 4>(h, p, st);
+        return launch_gemm256<1>(h, p, st);
     }
     GemmParams<EpiStoreT<128>> p{};
     RET(make_tmap(h, &p.tmA[0], a16, m, kp, kp, BM));

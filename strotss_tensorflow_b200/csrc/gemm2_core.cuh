@@ -1,0 +1,165 @@
+// CTA-pair (cta_group::2) variant of the GEMM core: a cluster of two CTAs (one SM pair) owns one
+// 256 x 256 output tile.  Each CTA stages its own 128 rows of A and its own 128 rows of B per K block
+// (32 KB instead of 48 KB), the leader CTA issues 256 x 256 x 16 MMAs that read both CTAs' shared
+// memory, and each CTA's TMEM receives its 128 accumulator rows.
+//
+// Why: with one CTA per tile a K block moves 48 KB into shared memory (TMA) and 48 KB out of it (MMA
+// operand reads) per 512 tensor cycles = 192 B/clk against the SM's 128 B/clk shared-memory bandwidth,
+// which caps the tensor pipe at ~68 % (measured, profiles/).  The pair halves the B traffic per SM:
+// 32 KB in + 32 KB out per 512 cycles = 128 B/clk.
+//
+// Protocol (per pipeline stage / accumulator stage):
+//   full[s]   lives in the LEADER: its producer arms it with the bytes of BOTH CTAs; both CTAs' TMA
+//             loads credit it (cp.async.bulk.tensor ... cta_group::2 with the leader's barrier address)
+//   empty[s]  one per CTA: tcgen05.commit.cta_group::2 multicast arrives in both after the MMAs that
+//             read the stage completed
+//   tfull[a]  one per CTA, same multicast commit after the last K block of a tile
+//   tempty[a] lives in the LEADER: the epilogue warps of both CTAs arrive on it (remote arrive via mapa)
+#pragma once
+#include "gemm_core.cuh"
+
+namespace sb {
+
+constexpr int BM2 = 256;             // rows of A per CTA pair
+
+template <int NACC>
+struct PairCfg {
+    static constexpr int BN = 256;
+    static constexpr int ACC_COLS = BN * NACC;
+    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int A_BYTES = 128 * BK * 2;
+    static constexpr int B_BYTES = 128 * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // per CTA
+};
+
+// tiles_m of GemmParams counts 256-row tiles here.
+template <int NACC, int STAGES, int EPI_WARPS, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
+gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
+    using Cfg = PairCfg<NACC>;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::SMEM_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + Cfg::ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) { tma_prefetch_desc(&p.tmA[s]); tma_prefetch_desc(&p.tmB[s]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < Cfg::ACC_STAGES; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    tc_fence_before();
+    cluster_sync_all();                 // barriers of BOTH CTAs are initialised before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                int tm, tn;
+                decode_tile(p, t, tm, tn);
+                const int arow = p.a_row0 + tm * BM2 + static_cast<int>(rank) * 128;
+                const int brow = p.b_row0 + tn * BN + static_cast<int>(rank) * 128;
+                for (int s = 0; s < p.nseg; ++s) {
+                    for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sB = sA + Cfg::A_BYTES;
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                        tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
+                        tma_load_2d_2cta(sB, &p.tmB[s], lead_full, kb * BK, brow);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM2, BN);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                uint32_t touched = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int acc = p.seg_acc[s];
+                    const uint32_t d_addr = tmem_base + as * Cfg::ACC_COLS + acc * BN;
+                    for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                           ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
+                        touched |= (1u << acc);
+                        umma_commit_2cta(&empty[stage], 3);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit_2cta(&tfull[as], 3);
+                if (++as == Cfg::ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        int as = 0; uint32_t aphase = 0;
+        int seq = 0;
+        typename Epi::State st;
+        Epi::init(st, p.epi, q, lane);
+        constexpr int kSplit = EPI_WARPS / 4;
+        constexpr int kChunks = BN / 32 / kSplit;
+        for (int t = pair; t < num_tiles; t += npairs, ++seq) {
+            TileInfo ti;
+            int tm2;
+            decode_tile(p, t, tm2, ti.tn);
+            ti.tm = tm2 * 2 + static_cast<int>(rank);            // row block in units of 128 rows
+            ti.row0 = p.a_row0 + tm2 * BM2 + static_cast<int>(rank) * 128;
+            ti.col0 = p.b_row0 + ti.tn * BN;
+            ti.q = q; ti.lane = lane; ti.tile_seq = seq;
+            ti.w = warp - 4; ti.nw = EPI_WARPS; ti.csplit = (warp - 4) >> 2; ti.nsplit = kSplit;
+            ti.c0 = ti.csplit * kChunks; ti.c1 = ti.c0 + kChunks;
+            ti.tid = threadIdx.x - kNonEpiThreads;
+            ti.taddr = tmem_base + as * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            Epi::prologue(st, p.epi, ti, epi_smem);
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            Epi::run(st, p.epi, ti, epi_smem);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+            if (++as == Cfg::ACC_STAGES) { as = 0; aphase ^= 1; }
+        }
+        Epi::finish(st, p.epi, q, lane);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                 // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 2) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
+}  // namespace sb
