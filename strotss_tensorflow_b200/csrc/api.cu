@@ -82,6 +82,10 @@ struct strotss_ctx {
     float* Vx = nullptr;
     // host pinned staging for scalar read-back
     float* h_scalars = nullptr;
+    // side stream: the CUDA-core palette search runs concurrently with the HBM-bound operand preparation
+    // and the tensor-core GEMMs of the main stream (fork/join with events, no host sync)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // multi-GPU row sharding (NCCL through dlopen; see strotss_comm_*)
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
@@ -95,6 +99,9 @@ struct strotss_ctx {
         if (h_scalars) cudaFreeHost(h_scalars);
         for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto& e : pool) cudaEventDestroy(e);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
     }
 };
 
@@ -290,6 +297,14 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
         pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, rec_convert, f.rec);
         CKL();
     }
+    return 0;
+}
+
+int prep_rec(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long ld, int n, int convert, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_PREP, st);
+    RET(ensure(h, (std::string(tag) + ".rec").c_str(), (size_t)n * 8, &f.rec));
+    pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, convert, f.rec);
+    CKL();
     return 0;
 }
 
@@ -711,6 +726,9 @@ int strotss_create(int device, strotss_handle* out) {
     if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled not available"; return STROTSS_ERR_CUDA; }
     h->encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
     CK(cudaMallocHost(&h->h_scalars, sizeof(float) * STROTSS_NUM_SCALARS));
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return 0;
 }
 
@@ -816,21 +834,31 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     RET(ensure(h, "eval.partials", (size_t)PS_V + D, &partials));
     CK(cudaMemsetAsync(partials, 0, sizeof(float) * (PS_V + D), st));
     Feat fp, fc;
+    RemdState rs; PalState ps; MomOut mo; SsOut so;
+    rs.rowbest = best; ps.rowbest = best + M;
+    // fork: the palette search (CUDA cores, K = 3) only needs the YUV records of the prediction; it runs on the
+    // side stream underneath the operand preparation (HBM-bound) and the first GEMMs (tensor cores)
+    RET(prep_rec(h, "pred", fp, pred, ld_pred, N, 1, st));
+    float* pal_rec = fp.rec;
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    RET(pal_local(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, h->side));
+    CK(cudaEventRecord(h->ev_join, h->side));
+
     if (with_content) {
         PrepWant wc{}; wc.sumhat = true; wc.xh = true;
         RET(prep_features(h, "content", fc, content, ld_content, N, D, Dp, wc, nullptr, 0, st));
     }
-    PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true; wp.rec = true;
+    PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true;
     wp.cen = want_grad; wp.sumhat = with_content; wp.dlt = with_content; wp.xhT = with_content && want_grad;
     RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, with_content ? &fc : nullptr, 1, st));
+    fp.rec = pal_rec;
 
-    RemdState rs; PalState ps; MomOut mo; SsOut so;
-    rs.rowbest = best; ps.rowbest = best + M;
     RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, st));
-    RET(pal_local(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, st));
     RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, st));
     if (with_content)
         RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join
     if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
     RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                     want_grad, row_arg, col_arg, st));

@@ -254,6 +254,39 @@ def test_region_sizes_of_masked_mode(S, cuda_device):
     assert abs(total - ref_total) / ref_total <= LOSS_RTOL
 
 
+# ------------------------------------------------------------------------------ alternative kernel paths
+_ALT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import strotss_oracle as O
+import strotss_tensorflow_b200 as S
+dev = torch.device('cuda', 0)
+st, co, pr = O.synth_problem(2300, 700, 2179, eps=0.1, seed=41)
+mod = S.StrotssLoss(torch.tensor(st, device=dev), 16.0)
+sc, grad, _, _ = mod.handle.eval(torch.tensor(pr, device=dev), torch.tensor(co, device=dev), 16.0, True)
+ref, gref, info = O.total_loss(st, co, pr, 16.0, np.float64, True)
+g = grad.double().cpu().numpy()
+print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.norm(gref)) / np.linalg.norm(gref),
+      float((g * gref).sum() / (np.linalg.norm(g) * np.linalg.norm(gref))))
+"""
+
+
+@pytest.mark.parametrize("env", [{"STROTSS_NO_PAIR": "1"}, {"STROTSS_SS1_GENERIC": "1"},
+                                 {"STROTSS_NO_PAIR": "1", "STROTSS_SS1_GENERIC": "1"}])
+def test_alternative_kernel_paths(cuda_device, env):
+    """The single-CTA GEMM kernels (STROTSS_NO_PAIR) and the generic stage-1 epilogue (STROTSS_SS1_GENERIC) stay
+    selectable for A/B measurements; they must give the same answers.  The switches are read once per process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", _ALT_SCRIPT % root], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rel = [float(v) for v in out.stdout.strip().splitlines()[-1].split()[1:]]
+    assert rel[0] <= LOSS_RTOL and rel[1] <= GRADNORM_RTOL and rel[2] >= 0.999
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties(S, cuda_device):
     """N = M = 16384, D = 2179 (BASELINE.json configs[3]) through size-independent properties: the oracle
