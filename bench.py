@@ -169,8 +169,10 @@ def main():
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--eps", type=float, default=1.0, help="pred = content + eps*noise (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="rowshard", choices=["rowshard", "replicas"],
-                    help="N>1: shard one evaluation by prediction rows (strong scaling) or run one problem per GPU (weak)")
+    ap.add_argument("--mode", default="replicas", choices=["rowshard", "replicas"],
+                    help="N>1: 'replicas' = one problem per GPU, no collective (throughput mode, weak scaling; the headline); "
+                         "'rowshard' = ONE evaluation sharded by prediction rows over all GPUs (latency mode, strong scaling). "
+                         "In replicas mode the row-sharded latency is measured as well and reported under 'rowshard'.")
     args = ap.parse_args()
     N, M = WORKLOADS[args.workload]
 
@@ -256,6 +258,30 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     barrier()
 
+    # ---- N>1, replicas mode: also time ONE evaluation row-sharded over all GPUs (same inputs everywhere) ----
+    shard_info = None
+    if world > 1 and not rowshard:
+        from strotss_tensorflow_b200 import distributed as Dm
+        style0, content0, pred0 = synth_torch(N, M, D_FEAT, args.eps, 0, dev)
+        hs = S.Handle(dev)
+        Dm.attach(hs)
+        hs.set_style_target(style0)
+        for _ in range(3):
+            hs.eval(pred0, content0, ALPHA, True, False)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            sc_s, _, _, _ = hs.eval(pred0, content0, ALPHA, True, False)
+        s1.record()
+        barrier()
+        ms_shard = max_over_ranks(s0.elapsed_time(s1) / args.steps)
+        r0s, r1s = hs.shard_rows(N)
+        shard_info = {"value": 1000.0 / ms_shard, "unit": "evals/s", "ms_per_step": ms_shard, "scaling": "strong",
+                      "rows_per_rank": r1s - r0s, "loss": float(sc_s[_lib.S_TOTAL].item()),
+                      "collectives_per_eval": f"1 allreduce-max of 2x{M} packed u64 minima + 1 allreduce-sum of {16 + D_FEAT} floats (NCCL)"}
+        del hs
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,6 +332,8 @@ def main():
         "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in phases.items()},
         "loss": total,
     }
+    if shard_info is not None:
+        line["rowshard"] = shard_info
     if world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
         n_s = min(N, 2048)

@@ -300,6 +300,47 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
     return 0;
 }
 
+// Fused preparation of the prediction (x) and content (y) for the full evaluation: one pass over the rows of
+// both (norms, x^, y^, delta, column sums), then one tiled pass over x for the transposed / centred operands.
+int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long long ldx, const float* y, long long ldy, int n, int D,
+                      int Dp, bool want_grad, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_PREP, st);
+    if (Dp > 2560) { h->err = "prep: feature width above 2560 is not supported by the fused row pass"; return STROTSS_ERR_UNSUPPORTED; }
+    fx.x = x; fx.ld = ldx; fx.n = n; fx.np = round_up(n, 64);
+    fy.x = y; fy.ld = ldy; fy.n = n; fy.np = fx.np;
+    RET(ensure(h, "pred.inv", (size_t)n, &fx.inv));
+    RET(ensure(h, "content.inv", (size_t)n, &fy.inv));
+    RET(ensure(h, "pred.xh", (size_t)n * Dp, &fx.xh));
+    RET(ensure(h, "content.xh", (size_t)n * Dp, &fy.xh));
+    RET(ensure(h, "pred.dlt", (size_t)n * Dp, &fx.dlt));
+    RET(ensure(h, "pred.mean", (size_t)D, &fx.mean));
+    RET(ensure(h, "pred.sumhat", (size_t)D, &fx.sumhat));
+    RET(ensure(h, "content.sumhat", (size_t)D, &fy.sumhat));
+    const int nblk = (n + kPrRowsPerBlock - 1) / kPrRowsPerBlock;
+    float* part;
+    RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
+    const int smem = 2 * kPrGroup * Dp * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(prep_pair_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPrGroup * 2560 * (int)sizeof(float)));
+        configured = true;
+    }
+    prep_pair_rows_kernel<<<nblk, 256, smem, st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh, fy.xh, fx.dlt, part);
+    CKL();
+    colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+    CKL();
+    EmitArgs a{};
+    a.x = x; a.ldx = ldx; a.n = n; a.D = D; a.Dp = Dp; a.np = fx.np; a.inv = fx.inv; a.mean = fx.mean;
+    if (want_grad) {
+        RET(ensure(h, "pred.cen", (size_t)n * Dp, &fx.cen)); a.cen = fx.cen;
+        RET(ensure(h, "pred.xhT", (size_t)D * fx.np, &fx.xhT)); a.xhT = fx.xhT;
+    }
+    RET(ensure(h, "pred.cenT", (size_t)D * fx.np, &fx.cenT)); a.cenT = fx.cenT;
+    emit_operands_kernel<<<dim3(Dp / 64, fx.np / 64), 256, 0, st>>>(a);
+    CKL();
+    return 0;
+}
+
 int prep_rec(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long ld, int n, int convert, cudaStream_t st) {
     PhaseTimer _pt(h, PH_PREP, st);
     RET(ensure(h, (std::string(tag) + ".rec").c_str(), (size_t)n * 8, &f.rec));
@@ -413,10 +454,11 @@ int remd_finish(strotss_ctx* h, const Feat& target, int M, int N, Shard sh, int 
     if (want_grad && sh.n() > 0) {
         RET(ensure(h, "remd.g", (size_t)sh.n() * D, &rs.g));
         rs.ldg = D;
-        CK(cudaMemsetAsync(rs.g, 0, sizeof(float) * (size_t)sh.n() * D, st));
-        const int rows = M > sh.n() ? M : sh.n();
-        remd_backward_kernel<<<(rows + 7) / 8, 256, 0, st>>>(rs.rowbest, M, rs.colbest, N, sh.r0, sh.r1, target.x, target.ld,
-                                                             target.inv, D, scalars, slot_branch, rs.g, rs.ldg);
+        // scatter branch only (both kernels return immediately in the gather branch, which finalize handles)
+        cond_zero_kernel<<<2 * h->num_sms, 256, 0, st>>>(rs.g, (long long)sh.n() * D, scalars, slot_branch);
+        CKL();
+        remd_backward_kernel<<<(M + 7) / 8, 256, 0, st>>>(rs.rowbest, M, sh.r0, sh.r1, target.x, target.ld, target.inv, D, scalars,
+                                                          slot_branch, rs.g, rs.ldg);
         CKL();
     }
     return 0;
@@ -840,25 +882,29 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     // side stream underneath the operand preparation (HBM-bound) and the first GEMMs (tensor cores)
     RET(prep_rec(h, "pred", fp, pred, ld_pred, N, 1, st));
     float* pal_rec = fp.rec;
-    CK(cudaEventRecord(h->ev_fork, st));
-    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    RET(pal_local(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, h->side));
-    CK(cudaEventRecord(h->ev_join, h->side));
+    static const bool no_side = (getenv("STROTSS_NO_SIDE") != nullptr);     // A/B switch: palette on the main stream
+    if (no_side) {
+        RET(pal_local(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, st));
+    } else {
+        CK(cudaEventRecord(h->ev_fork, st));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        RET(pal_local(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, h->side));
+        CK(cudaEventRecord(h->ev_join, h->side));
+    }
 
     if (with_content) {
-        PrepWant wc{}; wc.sumhat = true; wc.xh = true;
-        RET(prep_features(h, "content", fc, content, ld_content, N, D, Dp, wc, nullptr, 0, st));
+        RET(prep_pred_content(h, fp, fc, pred, ld_pred, content, ld_content, N, D, Dp, want_grad, st));
+    } else {
+        PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true; wp.cen = want_grad;
+        RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, nullptr, 1, st));
     }
-    PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true;
-    wp.cen = want_grad; wp.sumhat = with_content; wp.dlt = with_content; wp.xhT = with_content && want_grad;
-    RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, with_content ? &fc : nullptr, 1, st));
     fp.rec = pal_rec;
 
     RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, st));
     RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, st));
     if (with_content)
         RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join
+    if (!no_side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join
     if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
     RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                     want_grad, row_arg, col_arg, st));
@@ -872,6 +918,8 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         a.x = pred; a.ldx = ld_pred; a.inv = fp.inv; a.N = N; a.D = D; a.r0 = sh.r0;
         if (with_content) { a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = partials + PS_V; a.coef = so.coef; a.sumhat = fp.sumhat; a.w_ss = alpha / denom; }
         a.gremd = rs.g; a.ld_gremd = rs.ldg; a.w_remd = 1.f / denom;
+        a.remd_colbest = rs.colbest; a.remd_xs = h->style.x; a.remd_ldxs = h->style.ld; a.remd_inv_s = h->style.inv;
+        a.scalars = scalars; a.slot_branch = S_REMD_BRANCH;
         a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = 1.f / denom;
         a.gpal = ps.g; a.w_pal = inv_alpha / denom;
         a.grad = grad; a.ldg = ld_grad;
@@ -990,6 +1038,8 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
         FinalizeArgs a{};
         a.x = y; a.ldx = ldy; a.inv = fy.inv; a.N = N; a.D = D; a.r0 = 0;
         a.gremd = rs.g; a.ld_gremd = rs.ldg; a.w_remd = 1.f;
+        a.remd_colbest = rs.colbest; a.remd_xs = fx.x; a.remd_ldxs = fx.ld; a.remd_inv_s = fx.inv;
+        a.scalars = sc; a.slot_branch = S_REMD_BRANCH;
         a.grad = grad_y; a.ldg = ld_grad;
         RET(finalize(h, a, N, st));
     }

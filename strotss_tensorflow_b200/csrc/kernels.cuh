@@ -180,6 +180,121 @@ __global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
 }
 
 // --------------------------------------------------------------------------------------
+// Fused row pass over the prediction x and the content y (one read of each):
+//   inv_x[r], inv_y[r]                          row norms
+//   xh[r][:], yh[r][:]   = x^, y^               bf16, row-major, zero K padding
+//   dlt[r][:]            = x^ - y^              bf16 (fp32 difference, then rounded)
+//   part[b][0][d] = sum_r x[r][d]   part[b][1][d] = sum_r x^[r][d]   part[b][2][d] = sum_r y^[r][d]
+// over the kPrRowsPerBlock rows of block b, in a fixed order (deterministic).
+// Rows are staged in shared memory four at a time (4 x 2 x Dp floats), so three blocks fit on an SM
+// and loads of one block overlap the arithmetic/stores of the others.
+// --------------------------------------------------------------------------------------
+constexpr int kPrGroup = 4;               // rows per staging group
+constexpr int kPrRowsPerBlock = 32;
+
+__global__ void __launch_bounds__(256) prep_pair_rows_kernel(const float* __restrict__ x, long long ldx,
+                                                             const float* __restrict__ y, long long ldy, int n, int D, int Dp,
+                                                             float* __restrict__ inv_x, float* __restrict__ inv_y,
+                                                             __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ yh,
+                                                             __nv_bfloat16* __restrict__ dlt, float* __restrict__ part) {
+    extern __shared__ float sm[];          // [2][kPrGroup][Dp]
+    __shared__ float s_inv[2][kPrGroup];
+    float* sx = sm;
+    float* sy = sm + kPrGroup * Dp;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row_base = blockIdx.x * kPrRowsPerBlock;
+    constexpr int kMaxCols = 10;           // columns per thread: Dp <= 2560
+    float ax[kMaxCols], ahx[kMaxCols], ahy[kMaxCols];
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c) { ax[c] = 0.f; ahx[c] = 0.f; ahy[c] = 0.f; }
+
+    for (int g = 0; g < kPrRowsPerBlock; g += kPrGroup) {
+        __syncthreads();                    // previous group fully consumed
+        for (int rr = 0; rr < kPrGroup; ++rr) {
+            const int r = row_base + g + rr;
+            const bool live = r < n;
+            const float* xr = x + static_cast<long long>(r) * ldx;
+            const float* yr = y + static_cast<long long>(r) * ldy;
+            for (int d = threadIdx.x; d < Dp; d += 256) {
+                const bool ok = live && d < D;
+                sx[rr * Dp + d] = ok ? xr[d] : 0.f;
+                sy[rr * Dp + d] = ok ? yr[d] : 0.f;
+            }
+        }
+        __syncthreads();
+        // warps 0..3: norm of prediction row `warp`; warps 4..7: norm of content row `warp - 4`
+        {
+            const float* src = (warp < kPrGroup) ? sx + warp * Dp : sy + (warp - kPrGroup) * Dp;
+            float ss = 0.f;
+            for (int d = lane; d < Dp; d += 32) { const float v = src[d]; ss = fmaf(v, v, ss); }
+            ss = warp_sum(ss);
+            if (lane == 0) s_inv[warp / kPrGroup][warp % kPrGroup] = rsqrtf(fmaxf(ss, kL2NEps));
+        }
+        __syncthreads();
+        // emit: two warps per row, 64-column chunks alternate between them (bf16x2 per lane = 128 B per warp store)
+        {
+            const int rr = warp >> 1;
+            const int r = row_base + g + rr;
+            if (r < n) {
+                const float ix = s_inv[0][rr], iy = s_inv[1][rr];
+                if (lane == 0 && (warp & 1) == 0) { inv_x[r] = ix; inv_y[r] = iy; }
+                const long long off = static_cast<long long>(r) * Dp;
+                for (int d = (warp & 1) * 64 + 2 * lane; d < Dp; d += 128) {
+                    const float x0 = sx[rr * Dp + d] * ix, x1 = sx[rr * Dp + d + 1] * ix;
+                    const float y0 = sy[rr * Dp + d] * iy, y1 = sy[rr * Dp + d + 1] * iy;
+                    *reinterpret_cast<uint32_t*>(xh + off + d) = pack_bf16x2(x0, x1);
+                    *reinterpret_cast<uint32_t*>(yh + off + d) = pack_bf16x2(y0, y1);
+                    *reinterpret_cast<uint32_t*>(dlt + off + d) = pack_bf16x2(x0 - y0, x1 - y1);
+                }
+            }
+        }
+        // column sums over the group's rows, thread t owns columns t, t+256, ...
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+            const int d = threadIdx.x + c * 256;
+            if (d < D) {
+#pragma unroll
+                for (int rr = 0; rr < kPrGroup; ++rr) {
+                    const float xv = sx[rr * Dp + d], yv = sy[rr * Dp + d];
+                    ax[c] += xv;
+                    ahx[c] = fmaf(xv, s_inv[0][rr], ahx[c]);
+                    ahy[c] = fmaf(yv, s_inv[1][rr], ahy[c]);
+                }
+            }
+        }
+    }
+    float* pb = part + static_cast<long long>(blockIdx.x) * 3 * D;
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c) {
+        const int d = threadIdx.x + c * 256;
+        if (d < D) { pb[d] = ax[c]; pb[D + d] = ahx[c]; pb[2 * D + d] = ahy[c]; }
+    }
+}
+
+// out[q][d] = scale_q * sum_b part[b][q][d] for the three sums of prep_pair_rows_kernel (fixed order)
+__global__ void __launch_bounds__(256) colsum3_finish_kernel(const float* __restrict__ part, int nblocks, int D,
+                                                             float scale0, float* __restrict__ out0,
+                                                             float* __restrict__ out1, float* __restrict__ out2) {
+    __shared__ float sh[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + c;
+    const int q = blockIdx.y;
+    float a = 0.f;
+    if (d < D)
+        for (int b = g; b < nblocks; b += 8) a += part[(static_cast<long long>(b) * 3 + q) * D + d];
+    sh[g][c] = a;
+    __syncthreads();
+    if (g == 0 && d < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][c];
+        if (q == 0) out0[d] = t * scale0;
+        else if (q == 1) out1[d] = t;
+        else out2[d] = t;
+    }
+}
+
+// --------------------------------------------------------------------------------------
 // self-similarity per-sample vectors (one warp per sample j):
 //   s_j = N - x^_j . sum_i x^_i,  t_j = N - y^_j . sum_i y^_i      (column sums of Xd, Yd)
 //   u_j = 1/max(s_j,1e-12),  w_j = 1/max(s_j,..) - 1/max(t_j,..)
@@ -302,38 +417,36 @@ __global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long l
     }
 }
 
-// Sparse backward of the cosine relaxed EMD into g (gradient w.r.t. the NORMALISED prediction rows
-// r0..r1 owned by this rank; g row 0 is prediction row r0):
-//   branch X: g[argmin_i][:] += -(1/M) x^_i   for every target row i whose match is owned here (scatter)
-//   branch Y: g[j][:]        += -(1/N) x^_{argmin_j}                                            (gather)
-// One warp per row of max(M, r1-r0); the branch flag is read from device memory (no host sync).
+// Sparse backward of the cosine relaxed EMD (gradient w.r.t. the NORMALISED prediction rows r0..r1 owned by
+// this rank).  The branch flag lives in device memory (no host sync):
+//   branch Y (R_Y > R_X): g^_j = -(1/N) x^_{argmin_j}: a pure gather, done inside finalize_grad_kernel.
+//   branch X (R_X >= R_Y): g[argmin_i][:] += -(1/M) x^_i for every target row i whose match is owned here:
+//            a scatter with atomics into a zeroed buffer; both kernels below return at once in branch Y.
+__global__ void cond_zero_kernel(float* __restrict__ g, long long n, const float* __restrict__ scalars, int slot_branch) {
+    if (scalars[slot_branch] == 0.f) return;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n / 4; i += stride)
+        g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) g[(n & ~3ll) + threadIdx.x] = 0.f;
+}
+
 __global__ void __launch_bounds__(256) remd_backward_kernel(const unsigned long long* __restrict__ rowbest, int M,
-                                                            const unsigned long long* __restrict__ colbest, int N,
                                                             int r0, int r1,
                                                             const float* __restrict__ xs, long long ldxs,
                                                             const float* __restrict__ inv_s, int D,
                                                             const float* __restrict__ scalars, int slot_branch,
                                                             float* __restrict__ g, long long ldg) {
+    if (scalars[slot_branch] == 0.f) return;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const bool bx = scalars[slot_branch] != 0.f;
-    if (bx) {
-        if (row >= M) return;
-        const int j = static_cast<int>(best_idx(rowbest[row]));
-        if (j < r0 || j >= r1) return;
-        const float sc = -inv_s[row] / static_cast<float>(M);
-        const float* src = xs + static_cast<long long>(row) * ldxs;
-        float* dst = g + static_cast<long long>(j - r0) * ldg;
-        for (int d = lane; d < D; d += 32) atomicAdd(dst + d, src[d] * sc);
-    } else {
-        const int j = r0 + row;
-        if (j >= r1) return;
-        const int i = static_cast<int>(best_idx(colbest[j]));
-        const float sc = -inv_s[i] / static_cast<float>(N);
-        const float* src = xs + static_cast<long long>(i) * ldxs;
-        float* dst = g + static_cast<long long>(row) * ldg;
-        for (int d = lane; d < D; d += 32) dst[d] += src[d] * sc;
-    }
+    if (row >= M) return;
+    const int j = static_cast<int>(best_idx(rowbest[row]));
+    if (j < r0 || j >= r1) return;
+    const float sc = -inv_s[row] / static_cast<float>(M);
+    const float* src = xs + static_cast<long long>(row) * ldxs;
+    float* dst = g + static_cast<long long>(j - r0) * ldg;
+    for (int d = lane; d < D; d += 32) atomicAdd(dst + d, src[d] * sc);
 }
 
 // --------------------------------------------------------------------------------------
@@ -521,6 +634,9 @@ struct FinalizeArgs {
     int r0;                                   // first prediction row owned by this rank; local buffers start there
     const float* ss2; long long ld_ss2; const float* v; const float* coef; const float* sumhat; float w_ss;
     const float* gremd; long long ld_gremd; float w_remd;
+    // relaxed-EMD gather branch (R_Y > R_X): g^_j = -(1/N) x^_{argmin_j}, read straight from the target rows
+    const unsigned long long* remd_colbest; const float* remd_xs; long long remd_ldxs; const float* remd_inv_s;
+    const float* scalars; int slot_branch;
     const float* Q; long long ldq; float q_scale; const float* gmu; float w_mom;
     const float* gpal; float w_pal;
     float* grad; long long ldg;
@@ -536,11 +652,18 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a
     const float iv = a.inv[i];
     const float invN = 1.f / static_cast<float>(a.N);
     const float ci = a.ss2 ? a.coef[i] : 0.f;
+    const bool remd_gather = a.gremd && a.scalars[a.slot_branch] == 0.f;
+    const float* gsrc = nullptr; float gsc = 0.f;
+    if (remd_gather) {
+        const int it = static_cast<int>(best_idx(a.remd_colbest[i]));
+        gsrc = a.remd_xs + static_cast<long long>(it) * a.remd_ldxs;
+        gsc = -a.remd_inv_s[it] * invN;
+    }
     float dot = 0.f, ssq = 0.f;
     for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
         float g = 0.f;
         if (a.ss2) g += a.w_ss * (-a.ss2[static_cast<long long>(li) * a.ld_ss2 + d] * invN + a.v[d] + ci * a.sumhat[d]);
-        if (a.gremd) g += a.w_remd * a.gremd[static_cast<long long>(li) * a.ld_gremd + d];
+        if (a.gremd) g += a.w_remd * (remd_gather ? gsrc[d] * gsc : a.gremd[static_cast<long long>(li) * a.ld_gremd + d]);
         sg[d] = g;
         const float xv = xr[d];
         dot = fmaf(g, xv, dot);
