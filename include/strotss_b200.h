@@ -135,6 +135,20 @@ int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, con
 /* convert_rgb_to_yuv(x) (nn/strotss_utils.py:166-167): out[n][3] = x[n][0:3] . K_yuv. */
 int strotss_convert_rgb_to_yuv(strotss_handle h, const float* x, long long ldx, int n, float* out, void* stream);
 
+/* Sampling._sample(xs, indices, bilinear_sampling) (nn/strotss_utils.py:25-81): gather the hypercolumns of n
+ * sample positions from nmaps NHWC feature maps (maps[k]: device pointer to h[k] x w[k] x c[k] fp32) into
+ * out (n x sum_k c[k], row stride ld_out).  indices: device (n, 2) fp32 (row, column) in the resolution of
+ * map 0; the per-map rescaling of :33-37 is derived from the shapes.  bilinear != 0 selects the 4-tap path.
+ * `maps`, `hs`, `ws`, `cs` are HOST arrays.  The result is bit-identical to an fp32 evaluation of the
+ * reference op sequence. */
+int strotss_sample(strotss_handle h, int nmaps, const float* const* maps, const int* hs, const int* ws, const int* cs,
+                   const float* indices, int n, int bilinear, float* out, long long ld_out, void* stream);
+/* Its backward (what tape.gradient does for the tf.gather calls at :67-70,75): scatter-ADD grad_out through the
+ * same taps into grad_maps[k] (device buffers shaped like the maps, zeroed by the caller; NULL entries are skipped). */
+int strotss_sample_backward(strotss_handle h, int nmaps, float* const* grad_maps, const int* hs, const int* ws,
+                            const int* cs, const float* indices, int n, int bilinear, const float* grad_out,
+                            long long ld, void* stream);
+
 /* Test hook: C[m][n] = alpha * sum_k bf16(A[m][k]) * bf16(B[n][k]) through the tcgen05 GEMM core
  * (fp32 in, fp32 out; tile_n is 128 or 256).  Not part of the reference interface. */
 int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha,

@@ -337,3 +337,70 @@ def synth_problem(N: int, M: int, D: int = 2179, eps: float = 1.0, seed: int = 0
     noise = rng.standard_normal((N, D), dtype=np.float32)
     pred = np.maximum(0.0, content + np.float32(eps) * np.mean(np.abs(content)) * noise).astype(np.float32)
     return style, content, pred
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY section 8(f) "next #1": hypercolumn sampler (nn/strotss_utils.py:25-136)
+# --------------------------------------------------------------------------------------
+def sampler_scales(shapes):
+    """Cumulative index divisors per feature map, nn/strotss_utils.py:31-37.
+
+    shapes: list of (h, w, c).  When a map is lower than its predecessor the indices are divided by
+    prev.shape[index] / cur.shape[index], where `index` is fixed at the FIRST such map: the height axis if
+    that map's height is a power of two, else the width axis (:35).  Returns the per-map divisor applied
+    at that map (1.0 = none); divisions accumulate in float32 in the reference (`indices /= y`)."""
+    import math
+    divs = []
+    index = None
+    for i, (h, w, c) in enumerate(shapes):
+        d = 1.0
+        if i > 0 and h < shapes[i - 1][0]:
+            if index is None:
+                index = 0 if not (math.log2(h) % 1) else 1      # position in (h, w) == axis 1 or 2 of NHWC
+            d = shapes[i - 1][index] / shapes[i][index]
+        divs.append(d)
+    return divs
+
+
+def sample_hypercolumns(xs, indices, bilinear_sampling: bool):
+    """Sampling._sample (nn/strotss_utils.py:25-81).  xs: list of (1, h, w, c) or (h, w, c) float32 arrays;
+    indices: (n, 2) float32 (row coordinate, column coordinate).  Returns (n, sum c) float32."""
+    maps = [np.asarray(x, dtype=np.float32).reshape(x.shape[-3], x.shape[-2], x.shape[-1]) for x in xs]
+    divs = sampler_scales([m.shape for m in maps])
+    idx = np.asarray(indices, dtype=np.float32).copy()
+    feats = []
+    for cur, d in zip(maps, divs):
+        if d != 1.0:
+            idx = (idx / np.float32(d)).astype(np.float32)
+        h, w, c = cur.shape
+        gx, gy = idx[:, 0], idx[:, 1]
+        flat = cur.reshape(h * w, c)
+        if bilinear_sampling:
+            gxf = np.floor(gx); dx = gx - gxf
+            gyf = np.floor(gy); dy = gy - gyf
+            wa = ((1 - dx) * (1 - dy))[:, None]; wb = ((1 - dx) * dy)[:, None]
+            wc = (dx * (1 - dy))[:, None]; wd = (dx * dy)[:, None]
+            gxi = np.clip(gxf, 0, h - 1).astype(np.int32); gyi = np.clip(gyf, 0, w - 1).astype(np.int32)
+            gxb = np.clip(gxi + 1, 0, h - 1); gyb = np.clip(gyi + 1, 0, w - 1)
+            g = (flat[gxi * w + gyi] * wa + flat[gxi * w + gyb] * wb + flat[gxb * w + gyi] * wc + flat[gxb * w + gyb] * wd)
+        else:
+            gxi = np.clip(gx, 0, h - 1).astype(np.int32); gyi = np.clip(gy, 0, w - 1).astype(np.int32)
+            g = flat[gxi * w + gyi]
+        feats.append(g.astype(np.float32))
+    return np.concatenate(feats, axis=1)
+
+
+def sampler_grid(h, w, bilinear_sampling: bool, off_x=0, off_y=0):
+    """The deterministic part of Sampling._make_indices (nn/strotss_utils.py:87-103): the strided grid of
+    candidate (row, col) pairs before masking / shuffling.  off_x, off_y stand for the two tf_rng draws."""
+    import math
+    if bilinear_sampling:
+        area = math.sqrt((h * w) // (128 ** 2))
+        step_x, step_y = max(1, math.floor(area)), max(1, math.ceil(area))
+        X = np.arange(h)[off_x::step_x]
+        Y = np.arange(w)[off_y::step_y]
+    else:
+        X, Y = np.arange(h), np.arange(w)
+    XX, YY = np.meshgrid(X, Y)
+    return np.stack([XX.reshape(-1), YY.reshape(-1)], axis=1), (max(1, math.floor(math.sqrt((h * w) // (128 ** 2)))) if bilinear_sampling else 1,
+                                                                  max(1, math.ceil(math.sqrt((h * w) // (128 ** 2)))) if bilinear_sampling else 1)

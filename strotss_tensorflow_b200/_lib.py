@@ -40,6 +40,8 @@ SIGNATURES = {
     "strotss_moment_matching": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp]),
     "strotss_self_similarity": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp]),
     "strotss_convert_rgb_to_yuv": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
+    "strotss_sample": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp, _ll, _vp]),
+    "strotss_sample_backward": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp, _ll, _vp]),
     "strotss_debug_gemm": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
     "strotss_debug_gemm_ta": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
 }

@@ -1112,6 +1112,60 @@ int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, con
     return 0;
 }
 
+// ---- hypercolumn sampler -------------------------------------------------
+static int sampler_setup(strotss_handle h, const char* who, int nmaps, const int* hs, const int* ws, const int* cs, SamplerMaps& m,
+                         int* total_c) {
+    if (nmaps <= 0 || nmaps > kMaxSamplerMaps || !hs || !ws || !cs) { h->err = std::string(who) + ": bad argument"; return STROTSS_ERR_ARG; }
+    m.nmaps = nmaps;
+    int off = 0, index = -1;
+    for (int k = 0; k < nmaps; ++k) {
+        if (hs[k] <= 0 || ws[k] <= 0 || cs[k] <= 0) { h->err = std::string(who) + ": bad map shape"; return STROTSS_ERR_ARG; }
+        m.h[k] = hs[k]; m.w[k] = ws[k]; m.c[k] = cs[k]; m.off[k] = off; off += cs[k];
+        double d = 1.0;
+        if (k > 0 && hs[k] < hs[k - 1]) {
+            // nn/strotss_utils.py:33-37: the axis is fixed at the first down-scaled map: height if it is a power of two
+            if (index < 0) index = ((hs[k] & (hs[k] - 1)) == 0) ? 0 : 1;
+            d = index == 0 ? static_cast<double>(hs[k - 1]) / hs[k] : static_cast<double>(ws[k - 1]) / ws[k];
+        }
+        m.div[k] = static_cast<float>(d);
+    }
+    *total_c = off;
+    return 0;
+}
+
+int strotss_sample(strotss_handle h, int nmaps, const float* const* maps, const int* hs, const int* ws, const int* cs,
+                   const float* indices, int n, int bilinear, float* out, long long ld_out, void* stream) {
+    RET(check_handle(h));
+    if (!maps || !indices || !out || n <= 0) { h->err = "sample: bad argument"; return STROTSS_ERR_ARG; }
+    SamplerMaps m{};
+    int total = 0;
+    RET(sampler_setup(h, "sample", nmaps, hs, ws, cs, m, &total));
+    if (ld_out < total) { h->err = "sample: ld_out smaller than the hypercolumn width"; return STROTSS_ERR_ARG; }
+    for (int k = 0; k < nmaps; ++k) {
+        if (!maps[k]) { h->err = "sample: null feature map"; return STROTSS_ERR_ARG; }
+        m.ptr[k] = maps[k];
+    }
+    CK(cudaSetDevice(h->device));
+    sampler_fwd_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, indices, n, bilinear ? 1 : 0, out, ld_out);
+    CKL();
+    return 0;
+}
+
+int strotss_sample_backward(strotss_handle h, int nmaps, float* const* grad_maps, const int* hs, const int* ws, const int* cs,
+                            const float* indices, int n, int bilinear, const float* grad_out, long long ld, void* stream) {
+    RET(check_handle(h));
+    if (!grad_maps || !indices || !grad_out || n <= 0) { h->err = "sample_backward: bad argument"; return STROTSS_ERR_ARG; }
+    SamplerMaps m{};
+    int total = 0;
+    RET(sampler_setup(h, "sample_backward", nmaps, hs, ws, cs, m, &total));
+    if (ld < total) { h->err = "sample_backward: ld smaller than the hypercolumn width"; return STROTSS_ERR_ARG; }
+    for (int k = 0; k < nmaps; ++k) m.gptr[k] = grad_maps[k];
+    CK(cudaSetDevice(h->device));
+    sampler_bwd_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, indices, n, bilinear ? 1 : 0, grad_out, ld);
+    CKL();
+    return 0;
+}
+
 int strotss_convert_rgb_to_yuv(strotss_handle h, const float* x, long long ldx, int n, float* out, void* stream) {
     RET(check_handle(h));
     if (!x || !out || n <= 0 || ldx < 3) { h->err = "convert_rgb_to_yuv: bad argument"; return STROTSS_ERR_ARG; }

@@ -582,6 +582,96 @@ __global__ void pal_backward_kernel(const unsigned long long* __restrict__ rowbe
 }
 
 // --------------------------------------------------------------------------------------
+// Hypercolumn sampler (SURVEY 8f "next #1"; Sampling._sample, nn/strotss_utils.py:25-81):
+// out[i][:] = concat_k gather_k(indices_i), feature maps NHWC, nearest or 4-tap bilinear.  One block per
+// sample; the index rescaling (`indices /= y`, :36-37) is replayed per map in fp32 in the reference's order,
+// and products/sums are left unfused so the result is bit-identical to an fp32 NumPy/TF evaluation.
+// --------------------------------------------------------------------------------------
+constexpr int kMaxSamplerMaps = 16;
+struct SamplerMaps {
+    const float* ptr[kMaxSamplerMaps];
+    float* gptr[kMaxSamplerMaps];          // gradient buffers (backward; may be null per map)
+    int h[kMaxSamplerMaps], w[kMaxSamplerMaps], c[kMaxSamplerMaps], off[kMaxSamplerMaps];
+    float div[kMaxSamplerMaps];            // divisor applied to the running indices at this map (1 = none)
+    int nmaps;
+};
+
+struct SamplerTaps { int a, b, c, d; float wa, wb, wc, wd; };
+
+__device__ __forceinline__ SamplerTaps sampler_taps(float gx, float gy, int h, int w, int bilinear) {
+    SamplerTaps t;
+    if (bilinear) {
+        const float gxf = floorf(gx), gyf = floorf(gy);
+        const float dx = __fsub_rn(gx, gxf), dy = __fsub_rn(gy, gyf);
+        t.wa = __fmul_rn(__fsub_rn(1.f, dx), __fsub_rn(1.f, dy));
+        t.wb = __fmul_rn(__fsub_rn(1.f, dx), dy);
+        t.wc = __fmul_rn(dx, __fsub_rn(1.f, dy));
+        t.wd = __fmul_rn(dx, dy);
+        const int xi = static_cast<int>(fminf(fmaxf(gxf, 0.f), static_cast<float>(h - 1)));
+        const int yi = static_cast<int>(fminf(fmaxf(gyf, 0.f), static_cast<float>(w - 1)));
+        const int xb = min(max(xi + 1, 0), h - 1), yb = min(max(yi + 1, 0), w - 1);
+        t.a = xi * w + yi; t.b = xi * w + yb; t.c = xb * w + yi; t.d = xb * w + yb;
+    } else {
+        const int xi = static_cast<int>(fminf(fmaxf(gx, 0.f), static_cast<float>(h - 1)));
+        const int yi = static_cast<int>(fminf(fmaxf(gy, 0.f), static_cast<float>(w - 1)));
+        t.a = t.b = t.c = t.d = xi * w + yi;
+        t.wa = 1.f; t.wb = t.wc = t.wd = 0.f;
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256) sampler_fwd_kernel(const SamplerMaps m, const float* __restrict__ idx, int n, int bilinear,
+                                                          float* __restrict__ out, long long ld) {
+    const int i = blockIdx.x;
+    float gx = idx[2 * i], gy = idx[2 * i + 1];
+    float* o = out + static_cast<long long>(i) * ld;
+    for (int k = 0; k < m.nmaps; ++k) {
+        if (m.div[k] != 1.f) { gx = __fdiv_rn(gx, m.div[k]); gy = __fdiv_rn(gy, m.div[k]); }
+        const int c = m.c[k];
+        const SamplerTaps t = sampler_taps(gx, gy, m.h[k], m.w[k], bilinear);
+        const float* pa = m.ptr[k] + static_cast<long long>(t.a) * c;
+        if (bilinear) {
+            const float* pb = m.ptr[k] + static_cast<long long>(t.b) * c;
+            const float* pc = m.ptr[k] + static_cast<long long>(t.c) * c;
+            const float* pd = m.ptr[k] + static_cast<long long>(t.d) * c;
+            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+                float v = __fmul_rn(pa[ch], t.wa);
+                v = __fadd_rn(v, __fmul_rn(pb[ch], t.wb));
+                v = __fadd_rn(v, __fmul_rn(pc[ch], t.wc));
+                v = __fadd_rn(v, __fmul_rn(pd[ch], t.wd));
+                o[m.off[k] + ch] = v;
+            }
+        } else {
+            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) o[m.off[k] + ch] = pa[ch];
+        }
+    }
+}
+
+// Backward: scatter-add of grad_out through the same taps into the feature-map gradients (atomics).
+__global__ void __launch_bounds__(256) sampler_bwd_kernel(const SamplerMaps m, const float* __restrict__ idx, int n, int bilinear,
+                                                          const float* __restrict__ gout, long long ld) {
+    const int i = blockIdx.x;
+    float gx = idx[2 * i], gy = idx[2 * i + 1];
+    const float* g = gout + static_cast<long long>(i) * ld;
+    for (int k = 0; k < m.nmaps; ++k) {
+        if (m.div[k] != 1.f) { gx = __fdiv_rn(gx, m.div[k]); gy = __fdiv_rn(gy, m.div[k]); }
+        float* gm = m.gptr[k];
+        if (!gm) continue;
+        const int c = m.c[k];
+        const SamplerTaps t = sampler_taps(gx, gy, m.h[k], m.w[k], bilinear);
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            const float v = g[m.off[k] + ch];
+            atomicAdd(gm + static_cast<long long>(t.a) * c + ch, v * t.wa);
+            if (bilinear) {
+                atomicAdd(gm + static_cast<long long>(t.b) * c + ch, v * t.wb);
+                atomicAdd(gm + static_cast<long long>(t.c) * c + ch, v * t.wc);
+                atomicAdd(gm + static_cast<long long>(t.d) * c + ch, v * t.wd);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
 // moment matching, mean part + covariance partial sum (single block):
 //   l_mean = mean_d |mu_y - mu_x|,  gmu[d] = sign(mu_y - mu_x) / D
 //   l_cov  = sum(part) / D^2 ;  l_m = l_cov + l_mean

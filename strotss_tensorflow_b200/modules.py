@@ -76,8 +76,9 @@ class StrotssLoss(torch.nn.Module):
     def __init__(self, target: torch.Tensor, alpha: float):
         super().__init__()
         self.alpha = float(alpha)
-        self.handle = Handle(reshape_2d(target).device)
-        self.handle.set_style_target(target)
+        self.style_features = reshape_2d(target).detach()
+        self.handle = Handle(self.style_features.device)
+        self.handle.set_style_target(self.style_features)
         self.last_scalars = None
 
     def forward(self, content: torch.Tensor, prediction: torch.Tensor) -> torch.Tensor:

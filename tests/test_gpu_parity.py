@@ -257,6 +257,74 @@ def test_region_sizes_of_masked_mode(S, cuda_device):
     assert abs(total - ref_total) / ref_total <= LOSS_RTOL
 
 
+# ------------------------------------------------------------------------------ hypercolumn sampler (8f next #1)
+_SAMPLER_SHAPES = [(85, 128, 3), (85, 128, 64), (85, 128, 64), (42, 64, 128), (42, 64, 128), (21, 32, 256), (21, 32, 256),
+                   (21, 32, 256), (10, 16, 512), (10, 16, 512)]                 # content at scale 128
+
+
+@pytest.mark.parametrize("bilinear", [True, False])
+def test_sampler_forward_is_bit_exact(S, cuda_device, bilinear):
+    rng = np.random.default_rng(5)
+    xs = [rng.standard_normal((1,) + s).astype(np.float32) for s in _SAMPLER_SHAPES]
+    idx = np.stack([rng.uniform(-1, 86, 700), rng.uniform(-1, 129, 700)], axis=1).astype(np.float32)   # incl. out-of-range
+    ref = O.sample_hypercolumns(xs, idx, bilinear)
+    samp = S.Sampling(1024)
+    got = samp._sample([_t(x, cuda_device) for x in xs], _t(idx, cuda_device), bilinear).cpu().numpy()
+    assert got.shape == (700, 2179)
+    assert np.array_equal(got, ref)
+
+
+def test_sampler_backward_matches_autograd(S, cuda_device):
+    rng = np.random.default_rng(6)
+    shapes = [(20, 24, 3), (20, 24, 16), (10, 12, 32), (5, 6, 40)]
+    xs_np = [rng.standard_normal((1,) + s).astype(np.float32) for s in shapes]
+    idx = np.stack([rng.uniform(0, 20, 300), rng.uniform(0, 24, 300)], axis=1).astype(np.float32)
+    gout = rng.standard_normal((300, sum(s[2] for s in shapes))).astype(np.float32)
+    xs = [_t(x, cuda_device).requires_grad_(True) for x in xs_np]
+    out = S.Sampling(300)._sample(xs, _t(idx, cuda_device), True)
+    out.backward(_t(gout, cuda_device))
+    # reference: the same gather written with torch indexing on the CPU in fp64
+    xr = [torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in xs_np]
+    divs = O.sampler_scales(shapes)
+    cur = torch.tensor(idx, dtype=torch.float32)
+    feats = []
+    for x, d, (h, w, c) in zip(xr, divs, shapes):
+        if d != 1.0:
+            cur = cur / np.float32(d)
+        gx, gy = cur[:, 0], cur[:, 1]
+        gxf, gyf = gx.floor(), gy.floor()
+        dx, dy = (gx - gxf).double()[:, None], (gy - gyf).double()[:, None]
+        xi = gxf.clamp(0, h - 1).long(); yi = gyf.clamp(0, w - 1).long()
+        xb = (xi + 1).clamp(0, h - 1); yb = (yi + 1).clamp(0, w - 1)
+        flat = x.reshape(h * w, c)
+        feats.append(flat[xi * w + yi] * (1 - dx) * (1 - dy) + flat[xi * w + yb] * (1 - dx) * dy
+                     + flat[xb * w + yi] * dx * (1 - dy) + flat[xb * w + yb] * dx * dy)
+    torch.cat(feats, dim=1).backward(torch.tensor(gout, dtype=torch.float64))
+    for a, b in zip(xs, xr):
+        assert float((a.grad.double().cpu() - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max())
+
+
+def test_sampler_feeds_the_loss_path(S, cuda_device):
+    """train_step shape of the path (run_strotss.py:134-141): sample content/pred maps at the same points,
+    evaluate the fused loss, and carry the gradient back to the prediction's feature maps."""
+    g = torch.Generator(device=cuda_device).manual_seed(0)
+    content_maps = [torch.rand((1,) + s, generator=g, device=cuda_device) for s in _SAMPLER_SHAPES]
+    pred_maps = [(m + 0.05 * torch.rand(m.shape, generator=g, device=cuda_device)).requires_grad_(True) for m in content_maps]
+    style_maps = [torch.rand((1,) + s, generator=g, device=cuda_device) for s in _SAMPLER_SHAPES]
+    samp = S.Sampling(1024, torch.Generator().manual_seed(0))
+    loss_fn = S.StrotssLoss(samp(style_maps), 16.0)
+    c_feat, p_feat = samp.bilinear(content_maps, pred_maps)
+    assert c_feat.shape == (1024, 2179) and p_feat.shape == (1024, 2179)
+    loss = loss_fn(c_feat, p_feat)
+    loss.backward()
+    assert torch.isfinite(loss) and all(m.grad is not None and bool(torch.isfinite(m.grad).all()) for m in pred_maps)
+    assert float(pred_maps[0].grad.abs().sum()) > 0 and float(pred_maps[-1].grad.abs().sum()) > 0
+    # parity of this evaluation against the oracle on the very same sampled features
+    st = loss_fn.style_features.cpu().numpy()
+    want = O.total_loss(st, c_feat.detach().cpu().numpy(), p_feat.detach().cpu().numpy(), 16.0)
+    assert abs(loss.item() - want) / want <= LOSS_RTOL
+
+
 # ------------------------------------------------------------------------------ alternative kernel paths
 _ALT_SCRIPT = r"""
 import sys, numpy as np, torch
