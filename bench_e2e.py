@@ -1,0 +1,195 @@
+#!/usr/bin/env python
+"""End-to-end seconds per stylised image (BASELINE.json metric part ii, configs[1]): the reference driver loop
+(run_strotss.py:43-161) restated in torch AROUND the B200 loss path, on synthetic images of the shapes the
+shipped samples produce (content 321x481 -> 341x512 at the last scale, style 1600x1200 -> 512x384).
+
+What is measured and what is not:
+  * loss path (sampler, loss + gradient): this repo's CUDA kernels -- the thing being built;
+  * VGG16 forward/backward: torch/cuDNN with RANDOM weights (the reference's weights are fetched from a URL and are
+    not available offline) -- a stand-in for "the reference's TF/cuDNN path", timing only;
+  * pyramid fold, RMSprop on the six Laplacian-pyramid variables: torch eager ops.
+The stylised image is therefore meaningless; only the time is reported.  One JSON line on stdout.
+
+    python bench_e2e.py [--max_iter 200] [--level 4] [--sample 1024]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import strotss_tensorflow_b200 as S  # noqa: E402
+
+# (out_channels, taps_this_layer?) of VGG16 up to block5_conv3; 'M' = 2x2 max-pool (nn/model.py:7-15 lists the taps)
+_VGG16 = [(64, True), (64, True), "M", (128, True), (128, True), "M", (256, True), (256, True), (256, True), "M",
+          (512, False), (512, False), (512, True), "M", (512, False), (512, False), (512, True)]
+
+
+class VGG16Features(torch.nn.Module):
+    """Conv stack of Keras VGG16(include_top=False) returning the nine post-ReLU maps the reference taps."""
+
+    def __init__(self):
+        super().__init__()
+        convs, cin = [], 3
+        for item in _VGG16:
+            if item == "M":
+                continue
+            conv = torch.nn.Conv2d(cin, item[0], 3, padding=1)
+            torch.nn.init.kaiming_normal_(conv.weight, nonlinearity="relu")
+            torch.nn.init.zeros_(conv.bias)
+            convs.append(conv)
+            cin = item[0]
+        self.convs = torch.nn.ModuleList(convs)
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def forward(self, x):                       # x: (1, 3, H, W) in [0, 1]
+        x = (x - self.mean) / self.std
+        outs, k = [], 0
+        for item in _VGG16:
+            if item == "M":
+                x = F.max_pool2d(x, 2, 2)
+                continue
+            x = F.relu(self.convs[k](x))
+            k += 1
+            if item[1]:
+                outs.append(x)
+        return outs
+
+
+def nhwc(x):                                    # (1, C, H, W) -> contiguous (1, H, W, C) for the sampler
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def resize_long(img, long_side):                # nn/utils.py:32-37
+    h, w = img.shape[-2:]
+    f = max(h / long_side, w / long_side)
+    return F.interpolate(img, size=(int(h / f), int(w / f)), mode="bilinear", align_corners=False)
+
+
+def make_laplacian(x, return_down=False):       # nn/strotss_utils.py:139-146
+    h, w = x.shape[-2:]
+    hd, wd = max(h // 2, 1), max(w // 2, 1)
+    down = F.interpolate(x, size=(hd, wd), mode="bilinear", align_corners=False)
+    pyr = x - F.interpolate(down, size=(h, w), mode="bilinear", align_corners=False)
+    return (pyr, down) if return_down else pyr
+
+
+def make_pyramid(x, levels=5):                  # nn/strotss_utils.py:149-156
+    out, cur = [], x
+    for _ in range(levels):
+        pyr, cur = make_laplacian(cur, True)
+        out.append(pyr)
+    out.append(cur)
+    return out
+
+
+def fold_pyramid(xs):                           # nn/strotss_utils.py:159-163
+    ret = xs[-1]
+    for x in reversed(xs[:-1]):
+        ret = x + F.interpolate(ret, size=x.shape[-2:], mode="bilinear", align_corners=False)
+    return ret
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--max_iter", type=int, default=200)
+    ap.add_argument("--level", type=int, default=4)
+    ap.add_argument("--sample", type=int, default=1024)
+    ap.add_argument("--lr", type=float, default=2e-3)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    content = torch.rand(1, 3, 321, 481, generator=gen, device=dev)
+    style = torch.rand(1, 3, 1600, 1200, generator=gen, device=dev)
+    vgg = VGG16Features().to(dev).to(memory_format=torch.channels_last)
+    sampling = S.Sampling(args.sample, torch.Generator().manual_seed(0))
+
+    def feats(img):
+        return [nhwc(img)] + [nhwc(f) for f in vgg(img.contiguous(memory_format=torch.channels_last))]
+
+    def run(max_iter):
+        return _run(args, content, style, sampling, feats, max_iter)
+
+    run(3)                                       # warm-up: cuDNN autotune, workspace growth, module load
+    torch.cuda.synchronize()
+    t_all = time.perf_counter()
+    per_scale = run(args.max_iter)
+    torch.cuda.synchronize()
+    total = time.perf_counter() - t_all
+    print(json.dumps({
+        "metric": "end-to-end seconds per stylised image, 512 px long side, default settings", "value": total, "unit": "s/image",
+        "higher_is_better": False, "n_gpus": 1, "data": "synthetic images (content 321x481, style 1600x1200), random VGG16 weights",
+        "config": {"level": args.level, "max_iter": args.max_iter, "sample_size": args.sample, "optimizer": "RMSprop(0.99, 1e-8)",
+                   "vgg": "torch/cuDNN conv stack, fp32 tensors, channels_last (stand-in for the reference's TF/cuDNN path)",
+                   "loss_path": "strotss_tensorflow_b200 (fused sampler + loss/grad kernels)",
+                   "warmup": "one untimed pass of 3 iterations per scale"},
+        "per_scale": per_scale}))
+
+
+def _run(args, content, style, sampling, feats, max_iter):
+    alpha = 16.0
+    per_scale = []
+    stylized = None
+    for i in range(args.level):
+        scl = 2 << (5 + i)
+        sc, ss = resize_long(content, scl), resize_long(style, scl)
+        lap = make_laplacian(sc)
+        lr = args.lr
+        if i == 0:
+            stylized = lap + ss.mean(dim=(2, 3), keepdim=True)
+        elif i < args.level - 1:
+            stylized = F.interpolate(stylized, size=sc.shape[-2:], mode="bilinear", align_corners=False) + lap
+        else:
+            stylized = F.interpolate(stylized, size=sc.shape[-2:], mode="bilinear", align_corners=False)
+            lr = args.lr / 2
+        variables = [torch.nn.Parameter(v.clone()) for v in make_pyramid(stylized)]
+        opt = torch.optim.RMSprop(variables, lr=lr, alpha=0.99, eps=1e-8)
+        with torch.no_grad():
+            content_feat = feats(sc)
+            style_feat = feats(ss)
+            loss_fn = S.StrotssLoss(sampling(style_feat), alpha)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t_vgg = t_loss = 0.0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        last = None
+        for it in range(max_iter):
+            opt.zero_grad(set_to_none=True)
+            ev[0].record()
+            img = fold_pyramid(variables)
+            pred = feats(img)
+            ev[1].record()
+            c_feat, p_feat = sampling.bilinear(content_feat, pred)
+            loss = loss_fn(c_feat, p_feat)
+            ev[2].record()
+            loss.backward()
+            opt.step()
+            ev[3].record()
+            last = float(loss.item())           # the reference formats three scalars per iteration (run_strotss.py:150-152)
+            t_vgg += ev[0].elapsed_time(ev[1])
+            t_loss += ev[1].elapsed_time(ev[2])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        with torch.no_grad():
+            stylized = fold_pyramid(variables).detach()
+        per_scale.append({"scale": scl, "content_hw": list(sc.shape[-2:]), "style_hw": list(ss.shape[-2:]), "alpha": alpha,
+                          "seconds": dt, "ms_per_iter": dt / max_iter * 1e3,
+                          "fold_vgg_fwd_ms_per_iter": t_vgg / max_iter,
+                          "sample_loss_fwd_ms_per_iter": t_loss / max_iter, "last_loss": last})
+        alpha /= 2.0
+    return per_scale
+
+
+if __name__ == "__main__":
+    main()

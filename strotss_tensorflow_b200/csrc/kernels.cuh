@@ -186,10 +186,10 @@ __global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
 //   dlt[r][:]            = x^ - y^              bf16 (fp32 difference, then rounded)
 //   part[b][0][d] = sum_r x[r][d]   part[b][1][d] = sum_r x^[r][d]   part[b][2][d] = sum_r y^[r][d]
 // over the kPrRowsPerBlock rows of block b, in a fixed order (deterministic).
-// Rows are staged in shared memory four at a time (4 x 2 x Dp floats), so three blocks fit on an SM
-// and loads of one block overlap the arithmetic/stores of the others.
+// Rows are staged in shared memory two at a time (2 x 2 x Dp floats = 36 KB), so six blocks fit on an SM
+// and the loads of some blocks overlap the arithmetic/stores of the others.
 // --------------------------------------------------------------------------------------
-constexpr int kPrGroup = 4;               // rows per staging group
+constexpr int kPrGroup = 2;               // rows per staging group
 constexpr int kPrRowsPerBlock = 32;
 
 __global__ void __launch_bounds__(256) prep_pair_rows_kernel(const float* __restrict__ x, long long ldx,
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(256) prep_pair_rows_kernel(const float* __rest
             }
         }
         __syncthreads();
-        // warps 0..3: norm of prediction row `warp`; warps 4..7: norm of content row `warp - 4`
-        {
+        // warps 0..G-1: norm of prediction row `warp`; warps G..2G-1: norm of content row `warp - G`
+        if (warp < 2 * kPrGroup) {
             const float* src = (warp < kPrGroup) ? sx + warp * Dp : sy + (warp - kPrGroup) * Dp;
             float ss = 0.f;
             for (int d = lane; d < Dp; d += 32) { const float v = src[d]; ss = fmaf(v, v, ss); }
@@ -231,15 +231,16 @@ __global__ void __launch_bounds__(256) prep_pair_rows_kernel(const float* __rest
             if (lane == 0) s_inv[warp / kPrGroup][warp % kPrGroup] = rsqrtf(fmaxf(ss, kL2NEps));
         }
         __syncthreads();
-        // emit: two warps per row, 64-column chunks alternate between them (bf16x2 per lane = 128 B per warp store)
+        // emit: 8/G warps per row, 64-column chunks dealt round-robin (bf16x2 per lane = 128 B per warp store)
         {
-            const int rr = warp >> 1;
+            constexpr int kWarpsPerRow = 8 / kPrGroup;
+            const int rr = warp / kWarpsPerRow, sub = warp % kWarpsPerRow;
             const int r = row_base + g + rr;
             if (r < n) {
                 const float ix = s_inv[0][rr], iy = s_inv[1][rr];
-                if (lane == 0 && (warp & 1) == 0) { inv_x[r] = ix; inv_y[r] = iy; }
+                if (lane == 0 && sub == 0) { inv_x[r] = ix; inv_y[r] = iy; }
                 const long long off = static_cast<long long>(r) * Dp;
-                for (int d = (warp & 1) * 64 + 2 * lane; d < Dp; d += 128) {
+                for (int d = sub * 64 + 2 * lane; d < Dp; d += 64 * kWarpsPerRow) {
                     const float x0 = sx[rr * Dp + d] * ix, x1 = sx[rr * Dp + d + 1] * ix;
                     const float y0 = sy[rr * Dp + d] * iy, y1 = sy[rr * Dp + d + 1] * iy;
                     *reinterpret_cast<uint32_t*>(xh + off + d) = pack_bf16x2(x0, x1);
