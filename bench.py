@@ -300,10 +300,14 @@ def main():
     npan = -(-own_rows // 2048)
     visited = 1.0 if rowshard else sum(N - p * 2048 for p in range(npan)) * 2048.0 / (float(N) * N) if N > 2048 else 1.0
     ach = alg_flops_step / (ss1_ms / args.steps * 1e-3) / 1e12 if ss1_n else None
-    roof = {"bound": "tensor", "kernel": "gemm_kernel<256,2,4,8,EpiSS1<256,8>> (self-similarity stage 1, all launches of a step)",
+    roof = {"bound": "tensor", "kernel": "ss1_pair_kernel (self-similarity stage 1, cta_group::2; all launches of a step)",
             "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
-            "traffic": None, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 8 launches of one step of this workload
+            # (profiles/r01_v7_ss1_pair_ncu_raw.csv); algorithmic: operands 220 + 990 MB, P panel 302 MB
+            "traffic": 1.7148e9 if (world == 1 and args.workload == "large") else None,
+            "traffic_unit": "bytes per step (all launches of the kernel)", "algorithmic_bytes": 1.512e9,
+            "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": ss1_n / args.steps if ss1_n else None,
             "executed_over_algorithmic": 1.5 * visited,
             "note": "algorithmic = 2 Gram GEMMs (Xd, Yd); executed = 3 bf16 K-passes over the visited tiles "

@@ -50,6 +50,25 @@ def test_create_fails_loudly_without_gpu(lib):
     lib.strotss_destroy(h)
 
 
+def test_plain_c_program_links_against_the_boundary(lib, tmp_path):
+    """gcc-compiled C consumer of include/strotss_b200.h + libstrotss_b200.so (tests/c_abi/abi_smoke.c)."""
+    import shutil
+    import subprocess
+    from strotss_tensorflow_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"),
+           "-L", libdir, "-lstrotss_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "ok" in run.stdout
+
+
 def test_no_cpu_fallback_in_host_mirror():
     import strotss_tensorflow_b200 as S
     x = torch.rand(8, 5)
