@@ -228,14 +228,17 @@ bool pair_enabled() {
 int bbox256() { return pair_enabled() ? 128 : 256; }
 
 // p.tiles_m counts 128-row blocks (as for the single-CTA kernel); converted to 256-row pair tiles here.
-template <int NACC, int EPI_WARPS = 4, class Epi>
+template <int NACC, int EPI_WARPS = 4, bool B_MN = false, class Epi>
 int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
-    if (!pair_enabled()) return launch_gemm<256, NACC, 4, EPI_WARPS>(h, p, st);
+    if (!pair_enabled()) {
+        if constexpr (B_MN) { h->err = "internal: MN-major B needs the CTA-pair kernels"; return STROTSS_ERR_STATE; }
+        else return launch_gemm<256, NACC, 4, EPI_WARPS>(h, p, st);
+    }
     using Cfg = PairCfg<NACC>;
     constexpr int STAGES = 6;
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi>;
+    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi, B_MN>;
     static bool configured = false;
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -546,15 +549,27 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
         // Q = cen . (G + G^T) / N with G = sign(V_y - V_x)/D^2 symmetric  ->  q_scale * (cen . Sg^T)
         RET(ensure(h, "mom.Q", (size_t)sh.n() * Dp, &out.Q));
         out.ldq = Dp; out.q_scale = 2.f / (static_cast<float>(N) * static_cast<float>(D) * static_cast<float>(D));
-        GemmParams<EpiStoreT<256>> q{};
-        RET(make_tmap(h, &q.tmA[0], pred.cen, N, Dp, Dp, BM));
-        RET(make_tmap(h, &q.tmB[0], Sg, D, Dp, Dp, bbox256()));
-        q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
-        q.tiles_m = (sh.n() + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
-        q.a_row0 = sh.r0; q.b_row0 = 0;
-        q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = sh.r1; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = sh.r0;
         PhaseTimer _pt(h, PH_COV_BWD, st);
-        RET((launch_gemm256<1>(h, q, st)));
+        if (pair_enabled()) {
+            // operand roles swapped (A = Sg rows d, B = cen rows i) so the epilogue writes Q[i][d] coalesced
+            GemmParams<EpiStoreTr<256>> q{};
+            RET(make_tmap(h, &q.tmA[0], Sg, D, Dp, Dp, BM));
+            RET(make_tmap(h, &q.tmB[0], pred.cen, N, Dp, Dp, 128));
+            q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
+            q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (sh.n() + 255) / 256;
+            q.a_row0 = 0; q.b_row0 = sh.r0;
+            q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = sh.r1; q.epi.alpha = 1.f; q.epi.col_off = sh.r0;
+            RET((launch_gemm256<1>(h, q, st)));
+        } else {
+            GemmParams<EpiStoreT<256>> q{};
+            RET(make_tmap(h, &q.tmA[0], pred.cen, N, Dp, Dp, BM));
+            RET(make_tmap(h, &q.tmB[0], Sg, D, Dp, Dp, 256));
+            q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
+            q.tiles_m = (sh.n() + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
+            q.a_row0 = sh.r0; q.b_row0 = 0;
+            q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = sh.r1; q.epi.cols = D; q.epi.alpha = 1.f; q.epi.row_off = sh.r0;
+            RET((launch_gemm<256, 1, 4>(h, q, st)));
+        }
     }
     return 0;
 }
@@ -664,29 +679,56 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             }
         }
         if (want_grad) {
-            // stage 2a: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]
-            GemmParams<EpiStoreT<256>> q{};
-            RET(make_tmap(h, &q.tmA[0], P + c0, rows, np - c0, np, BM));
-            RET(make_tmap(h, &q.tmB[0], x.xhT + c0, D, np - c0, np, bbox256()));
-            q.nseg = 1; q.seg_kblocks[0] = (np - c0) / BK; q.seg_acc[0] = 0;
-            q.tiles_m = (rows + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
-            q.a_row0 = 0; q.b_row0 = 0;
-            q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
-            q.epi.alpha = 1.f; q.epi.row_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
             PhaseTimer _pt(h, PH_SS2, st);
-            RET((launch_gemm256<1>(h, q, st)));
-            if (sym && r0 + panel < N) {
-                // stage 2b: ss2[rows right of the panel] += P[panel, those columns]^T . x^[panel rows]
-                const int m0 = r0 + panel, mext = N - m0;
-                GemmParams<EpiStoreT<256>> t{};
-                RET(make_tmap_mn(h, &t.tmA[0], P + m0, mext, rows, np));
-                RET(make_tmap(h, &t.tmB[0], x.xhT + r0, D, rows, np, 256));
-                t.nseg = 1; t.seg_kblocks[0] = (rows + BK - 1) / BK; t.seg_acc[0] = 0;
-                t.tiles_m = (mext + BM - 1) / BM; t.tiles_n = (D + 255) / 256;
-                t.a_row0 = 0; t.b_row0 = 0;
-                t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = mext; t.epi.cols = D;
-                t.epi.alpha = 1.f; t.epi.row_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
-                RET((launch_gemm<256, 1, 4, 4, true>(h, t, st)));
+            if (pair_enabled()) {
+                // Operand roles swapped (A = x^T rows d, B = P rows): thread = feature d, so every epilogue store
+                // instruction writes 32 consecutive floats of one ss2 row (coalesced), also for the accumulating 2b.
+                // stage 2a: ss2[panel rows][d] (+)= sum_{j >= c0} P[i][j] x^[j][d]
+                GemmParams<EpiStoreTr<256>> q{};
+                RET(make_tmap(h, &q.tmA[0], x.xhT + c0, D, np - c0, np, BM));
+                RET(make_tmap(h, &q.tmB[0], P + c0, rows, np - c0, np, 128));
+                q.nseg = 1; q.seg_kblocks[0] = (np - c0) / BK; q.seg_acc[0] = 0;
+                q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (rows + 255) / 256;
+                q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = rows;
+                q.epi.alpha = 1.f; q.epi.col_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
+                RET((launch_gemm256<1, 8>(h, q, st)));
+                if (sym && r0 + panel < N) {
+                    // stage 2b: ss2[j][d] += sum_{i in panel} P[i][j] x^[i][d] for the rows j right of the panel;
+                    // B = P^T is read from the row-major panel through MN-major descriptors
+                    const int m0 = r0 + panel, mext = N - m0;
+                    GemmParams<EpiStoreTr<256>> t{};
+                    RET(make_tmap(h, &t.tmA[0], x.xhT + r0, D, rows, np, BM));
+                    RET(make_tmap_mn(h, &t.tmB[0], P + m0, mext, rows, np));
+                    t.nseg = 1; t.seg_kblocks[0] = (rows + BK - 1) / BK; t.seg_acc[0] = 0;
+                    t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
+                    t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = mext;
+                    t.epi.alpha = 1.f; t.epi.col_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
+                    RET((launch_gemm256<1, 8, true>(h, t, st)));
+                }
+            } else {
+                // single-CTA kernels: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]
+                GemmParams<EpiStoreT<256>> q{};
+                RET(make_tmap(h, &q.tmA[0], P + c0, rows, np - c0, np, BM));
+                RET(make_tmap(h, &q.tmB[0], x.xhT + c0, D, np - c0, np, 256));
+                q.nseg = 1; q.seg_kblocks[0] = (np - c0) / BK; q.seg_acc[0] = 0;
+                q.tiles_m = (rows + BM - 1) / BM; q.tiles_n = (D + 255) / 256;
+                q.a_row0 = 0; q.b_row0 = 0;
+                q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
+                q.epi.alpha = 1.f; q.epi.row_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
+                RET((launch_gemm<256, 1, 4>(h, q, st)));
+                if (sym && r0 + panel < N) {
+                    // stage 2b: ss2[rows right of the panel] += P[panel, those columns]^T . x^[panel rows]  (MN-major A)
+                    const int m0 = r0 + panel, mext = N - m0;
+                    GemmParams<EpiStoreT<256>> t{};
+                    RET(make_tmap_mn(h, &t.tmA[0], P + m0, mext, rows, np));
+                    RET(make_tmap(h, &t.tmB[0], x.xhT + r0, D, rows, np, 256));
+                    t.nseg = 1; t.seg_kblocks[0] = (rows + BK - 1) / BK; t.seg_acc[0] = 0;
+                    t.tiles_m = (mext + BM - 1) / BM; t.tiles_n = (D + 255) / 256;
+                    t.a_row0 = 0; t.b_row0 = 0;
+                    t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = mext; t.epi.cols = D;
+                    t.epi.alpha = 1.f; t.epi.row_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
+                    RET((launch_gemm<256, 1, 4, 4, true>(h, t, st)));
+                }
             }
         }
     }

@@ -154,11 +154,11 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
     return d;
 }
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M x N tile; B K-major, A K- or MN-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false) {
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
     return (1u << 4)                 // D format  = F32
          | (1u << 7)                 // A format  = BF16
          | (1u << 10)                // B format  = BF16
-         | ((a_mn_major ? 1u : 0u) << 15) | (0u << 16)
+         | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
          | (static_cast<uint32_t>(N >> 3) << 17)
          | (static_cast<uint32_t>(M >> 4) << 24);
 }

@@ -33,7 +33,9 @@ struct PairCfg {
 };
 
 // tiles_m of GemmParams counts 256-row tiles here.
-template <int NACC, int STAGES, int EPI_WARPS, class Epi>
+// B_MN: the B operand is read from a matrix stored K x N (N contiguous) through MN-major descriptors; its tensor
+// map has dims {N, K} and box {64, 64} (each CTA stages its 128 columns of B as two 64-wide chunks).
+template <int NACC, int STAGES, int EPI_WARPS, class Epi, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
 gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
@@ -88,7 +90,12 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
                         tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
-                        tma_load_2d_2cta(sB, &p.tmB[s], lead_full, kb * BK, brow);
+                        if constexpr (B_MN) {
+                            tma_load_2d_2cta(sB, &p.tmB[s], lead_full, brow, kb * BK);
+                            tma_load_2d_2cta(sB + Cfg::B_BYTES / 2, &p.tmB[s], lead_full, brow + 64, kb * BK);
+                        } else {
+                            tma_load_2d_2cta(sB, &p.tmB[s], lead_full, kb * BK, brow);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -96,7 +103,7 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM2, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM2, BN, false, B_MN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
@@ -111,10 +118,12 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                        const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+                        const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(a_addr + Cfg::A_BYTES, Cfg::B_BYTES / 2)
+                                                    : make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+                        constexpr uint32_t b_step = B_MN ? (16 * 128) >> 4 : 2;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc,
+                            umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,
                                            ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
                         touched |= (1u << acc);
                         umma_commit_2cta(&empty[stage], 3);

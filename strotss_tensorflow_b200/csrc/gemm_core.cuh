@@ -231,12 +231,17 @@ struct EpiStore {
             if (rvalid) {
                 if (col + 32 <= P.cols && (P.ldc & 3) == 0) {
 #pragma unroll
+                    float4 o[8];
+                    if (P.accumulate) {          // loads first, then stores (see EpiStoreTr)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = *reinterpret_cast<const float4*>(crow + col + 4 * e);
+                    }
+#pragma unroll
                     for (int e = 0; e < 32; e += 4) {
                         float4 v = make_float4(__uint_as_float(r[e]) * P.alpha, __uint_as_float(r[e + 1]) * P.alpha,
                                                __uint_as_float(r[e + 2]) * P.alpha, __uint_as_float(r[e + 3]) * P.alpha);
-                        float4* dst = reinterpret_cast<float4*>(crow + col + e);
-                        if (P.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                        *dst = v;
+                        if (P.accumulate) { v.x += o[e >> 2].x; v.y += o[e >> 2].y; v.z += o[e >> 2].z; v.w += o[e >> 2].w; }
+                        *reinterpret_cast<float4*>(crow + col + e) = v;
                     }
                 } else {
 #pragma unroll
@@ -250,6 +255,48 @@ struct EpiStore {
 };
 template <int BN> struct EpiStoreT : EpiStore {
     __device__ static void run(State& s, const Params& P, const TileInfo& ti, uint8_t* sm) { run_bn<BN>(s, P, ti, sm); }
+};
+
+// ---- transposed store:  C[col][row] (+)= alpha * acc  (fp32, row stride ldc along the B index) ----------
+// Used with the operand roles swapped (A = the matrix whose rows are output COLUMNS): thread = accumulator row,
+// so for a fixed register (one B row = one output row) the 32 lanes of a warp write 32 consecutive floats --
+// a coalesced 128-byte line per instruction instead of 32 lines.
+template <int BN>
+struct EpiStoreTr {
+    static constexpr int SMEM_BYTES = 0;
+    struct Params { float* C; long long ldc; int rows, cols; float alpha; int col_off; int accumulate; };
+    struct State {};
+    __device__ static void init(State&, const Params&, int, int) {}
+    __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
+    __device__ static void finish(State&, const Params&, int, int) {}
+    __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t*) {
+        const int row = ti.row0 + ti.q * 32 + ti.lane;            // index along the contiguous output dimension
+        const bool rvalid = row < P.rows;
+#pragma unroll 1
+        for (int c = ti.c0; c < ti.c1; ++c) {
+            uint32_t r[32];
+            tmem_ld32(ti.taddr + c * 32, r);
+            tmem_ld_wait();
+            const int colbase = ti.col0 + c * 32;
+            if (rvalid && colbase < P.cols) {
+                float* dst = P.C + static_cast<long long>(colbase - P.col_off) * P.ldc + row;
+                if (P.accumulate) {
+                    // all 32 loads are issued before the first store: a load-add-store per element would be
+                    // serialised by the compiler (it cannot prove the 32 addresses distinct) -- 32 round trips
+                    float old[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) old[e] = (colbase + e < P.cols) ? dst[e * P.ldc] : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (colbase + e < P.cols) dst[e * P.ldc] = old[e] + __uint_as_float(r[e]) * P.alpha;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (colbase + e < P.cols) dst[e * P.ldc] = __uint_as_float(r[e]) * P.alpha;
+                }
+            }
+        }
+    }
 };
 
 // ---- relaxed EMD: best (max dot = min cosine distance) per A row and per B row ---------
