@@ -309,6 +309,7 @@ def main():
             "traffic_unit": "bytes per step (all launches of the kernel)", "algorithmic_bytes": 1.512e9,
             "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": ss1_n / args.steps if ss1_n else None,
+            "achieved_executed": (ach * 1.5 * visited) if ach else None,
             "executed_over_algorithmic": 1.5 * visited,
             "note": "algorithmic = 2 Gram GEMMs (Xd, Yd); executed = 3 bf16 K-passes over the visited tiles "
                     "(symmetry halves the visited tiles on a single GPU)"}

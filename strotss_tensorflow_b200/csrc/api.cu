@@ -246,7 +246,8 @@ int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     }
     GemmParams<Epi> q = p;
     q.tiles_m = (p.tiles_m + 1) / 2;
-    const int tiles = q.tiles_m * q.tiles_n;
+    if (q.tri && q.tiles_m != q.tiles_n) { h->err = "internal: triangular walk needs a square tile grid"; return STROTSS_ERR_STATE; }
+    const int tiles = q.tri ? q.tiles_n * (q.tiles_n + 1) / 2 : q.tiles_m * q.tiles_n;
     if (tiles <= 0) return 0;
     {
         long long kbytes = 0;
@@ -308,7 +309,6 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
 int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long long ldx, const float* y, long long ldy, int n, int D,
                       int Dp, bool want_grad, cudaStream_t st) {
     PhaseTimer _pt(h, PH_PREP, st);
-    if (Dp > 2560) { h->err = "prep: feature width above 2560 is not supported by the fused row pass"; return STROTSS_ERR_UNSUPPORTED; }
     fx.x = x; fx.ld = ldx; fx.n = n; fx.np = round_up(n, 64);
     fy.x = y; fy.ld = ldy; fy.n = n; fy.np = fx.np;
     RET(ensure(h, "pred.inv", (size_t)n, &fx.inv));
@@ -536,6 +536,9 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     RET(ensure(h, "mom.part", (size_t)npart, &part));
     p.epi.Vx = Vx; p.epi.ldv = Dp; p.epi.Sg = Sg; p.epi.lds = Dp; p.epi.part = part; p.epi.inv_n = 1.f / N; p.epi.D = D;
     p.epi.tiles_n = p.tiles_n;
+    // V is symmetric: with CTA pairs the tile grid is square (256 x 256 tiles), so only the upper triangle is
+    // computed; off-diagonal tiles count twice in the loss and write both Sg blocks
+    p.tri = pair_enabled() ? 1 : 0; p.epi.sym = p.tri; p.epi.diag_cols = 256;
     CK(cudaMemsetAsync(part, 0, sizeof(float) * npart, st));
     { PhaseTimer _pt(h, PH_COV_FWD, st); RET((launch_gemm256<1>(h, p, st))); }
     RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
@@ -934,8 +937,15 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaEventRecord(h->ev_join, h->side));
     }
 
-    if (with_content) {
+    if (with_content && Dp <= 2560) {
         RET(prep_pred_content(h, fp, fc, pred, ld_pred, content, ld_content, N, D, Dp, want_grad, st));
+    } else if (with_content) {
+        // very wide features: the fused row pass keeps 10 columns per thread; use the general two-kernel path
+        PrepWant wc{}; wc.sumhat = true; wc.xh = true;
+        RET(prep_features(h, "content", fc, content, ld_content, N, D, Dp, wc, nullptr, 0, st));
+        PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true; wp.sumhat = true; wp.dlt = true;
+        wp.cen = want_grad; wp.xhT = want_grad;
+        RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, &fc, 1, st));
     } else {
         PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true; wp.cen = want_grad;
         RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, nullptr, 1, st));

@@ -72,7 +72,7 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = num_tiles_of(p);
 
     if (warp == 0) {
         if (lane == 0) {

@@ -41,6 +41,7 @@ struct GemmParams {
     int seg_acc[kMaxSeg];
     int tiles_m, tiles_n;
     int group_n;                 // raster: column tiles are swept in groups of group_n (L2 blocking)
+    int tri;                     // 1: square tile grid of a symmetric product, only tiles with tn >= tm are visited
     int a_row0, b_row0;          // element row where tile (0,0) starts in A / B
     typename Epi::Params epi;
 };
@@ -61,7 +62,18 @@ struct TileInfo {
 // CTAs that run concurrently then share a few A row blocks and one group of B column blocks, so
 // both stay L2-resident instead of B being re-streamed from HBM for every row block.
 template <class P>
+__device__ __forceinline__ int num_tiles_of(const P& p) {
+    return p.tri ? p.tiles_n * (p.tiles_n + 1) / 2 : p.tiles_m * p.tiles_n;
+}
+
+template <class P>
 __device__ __forceinline__ void decode_tile(const P& p, int t, int& tm, int& tn) {
+    if (p.tri) {                 // row-major walk over the upper triangle (tiles_m == tiles_n)
+        int row = 0, len = p.tiles_n;
+        while (t >= len) { t -= len; ++row; --len; }
+        tm = row; tn = row + t;
+        return;
+    }
     const int gsz = p.tiles_m * p.group_n;
     const int tg = t / gsz;
     const int r = t - tg * gsz;
@@ -109,7 +121,7 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = num_tiles_of(p);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -464,6 +476,8 @@ struct EpiCovFwd {
         float* part;                           // [num_tiles * 4] partial sums of |V - Vx|
         float inv_n; int D;
         int tiles_n;
+        int sym;                               // tiles right of the diagonal also stand for their mirror images
+        int diag_cols;                         // width of a diagonal block in columns (256)
     };
     struct State {};
     __device__ static void init(State&, const Params&, int, int) {}
@@ -474,6 +488,8 @@ struct EpiCovFwd {
         const bool rvalid = row < P.D;
         const float* vrow = P.Vx + static_cast<long long>(row) * P.ldv;
         __nv_bfloat16* srow = P.Sg + static_cast<long long>(row) * P.lds;
+        // symmetric mode: a tile strictly right of the diagonal block counts twice and also writes Sg^T
+        const bool mirror = P.sym && (ti.col0 >= (ti.row0 / P.diag_cols + 1) * P.diag_cols);
         float part = 0.f;
 #pragma unroll 1
         for (int c = ti.c0; c < ti.c1; ++c) {
@@ -495,6 +511,11 @@ struct EpiCovFwd {
                         auto sg = [](float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); };
                         packed[e >> 1] = pack_bf16x2(sg(d0), sg(d1));
                         packed[(e >> 1) + 1] = pack_bf16x2(sg(d2), sg(d3));
+                        if (mirror) {          // Sg[col][row]: 32 lanes write 32 consecutive bf16 of one row
+                            __nv_bfloat16* t = P.Sg + static_cast<long long>(colbase + e) * P.lds + row;
+                            t[0] = __float2bfloat16(sg(d0)); t[P.lds] = __float2bfloat16(sg(d1));
+                            t[2 * P.lds] = __float2bfloat16(sg(d2)); t[3 * P.lds] = __float2bfloat16(sg(d3));
+                        }
                     }
                     uint4* dst = reinterpret_cast<uint4*>(srow + colbase);
 #pragma unroll
@@ -506,13 +527,16 @@ struct EpiCovFwd {
                         if (colbase + e < P.D) {
                             const float d = fmaf(__uint_as_float(r[e]), P.inv_n, -vrow[colbase + e]);
                             part += fabsf(d);
-                            srow[colbase + e] = __float2bfloat16((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
+                            const __nv_bfloat16 sv = __float2bfloat16((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
+                            srow[colbase + e] = sv;
+                            if (mirror) P.Sg[static_cast<long long>(colbase + e) * P.lds + row] = sv;
                         }
                     }
                 }
             }
         }
         part = warp_sum(part);
+        if (mirror) part *= 2.f;
         if (ti.lane == 0) P.part[(static_cast<long long>(ti.tm) * P.tiles_n + ti.tn) * ti.nw + ti.w] = part;
     }
 };

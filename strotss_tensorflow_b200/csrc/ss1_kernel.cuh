@@ -31,6 +31,7 @@ struct Ss1Params {
     CUtensorMap tmB[3];          // segment 0: (y^, y^) -> acc1 ; 1: (delta, x^) -> acc0 ; 2: (y^, delta) -> acc0
     int kblocks;                 // K blocks per segment
     int tiles_m, tiles_n, group_n;
+    int tri;                     // always 0 here (decode_tile's triangular walk is used by the covariance kernel)
     int a_row0, b_row0;
     Ss1Epi::Params epi;
 };
@@ -80,7 +81,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = num_tiles_of(p);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");

@@ -245,6 +245,16 @@ def test_modules_match_reference_wrappers(S, cuda_device, alpha):
     _gcheck(p2.grad, gref, cos_min=0.99)
 
 
+def test_wide_features_take_the_general_preparation_path(S, cuda_device):
+    """D > 2560 exceeds the fused row pass (10 columns per thread) and must fall back, not fail."""
+    st, co, pr = O.synth_problem(200, 180, 2700, eps=0.1, seed=51)
+    mod = S.StrotssLoss(_t(st, cuda_device), 4.0)
+    sc, grad, _, _ = mod.handle.eval(_t(pr, cuda_device), _t(co, cuda_device), 4.0, True)
+    ref, gref, _ = O.total_loss(st, co, pr, 4.0, np.float64, True)
+    assert abs(sc[0].item() - ref) / ref <= LOSS_RTOL
+    _gcheck(grad, gref, cos_min=0.99)
+
+
 def test_region_sizes_of_masked_mode(S, cuda_device):
     """Config 3 (masked transfer): R independent ragged problems (N_r, M_r), averaged (run_strotss.py:114-121)."""
     total, ref_total = 0.0, 0.0
