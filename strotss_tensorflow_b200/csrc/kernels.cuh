@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
 constexpr int kPrGroup = 2;               // rows per staging group
 constexpr int kPrRowsPerBlock = 32;
 
-__global__ void __launch_bounds__(256) prep_pair_rows_kernel(const float* __restrict__ x, long long ldx,
+__global__ void __launch_bounds__(256, 4) prep_pair_rows_kernel(const float* __restrict__ x, long long ldx,
                                                              const float* __restrict__ y, long long ldy, int n, int D, int Dp,
                                                              float* __restrict__ inv_x, float* __restrict__ inv_y,
                                                              __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ yh,
@@ -210,11 +210,14 @@ __global__ void __launch_bounds__(256) prep_pair_rows_kernel(const float* __rest
 
     for (int g = 0; g < kPrRowsPerBlock; g += kPrGroup) {
         __syncthreads();                    // previous group fully consumed
+#pragma unroll
         for (int rr = 0; rr < kPrGroup; ++rr) {
             const int r = row_base + g + rr;
             const bool live = r < n;
             const float* xr = x + static_cast<long long>(r) * ldx;
             const float* yr = y + static_cast<long long>(r) * ldy;
+            // unrolled so that ~10 independent loads per thread are in flight (the kernel is latency-bound otherwise)
+#pragma unroll 5
             for (int d = threadIdx.x; d < Dp; d += 256) {
                 const bool ok = live && d < D;
                 sx[rr * Dp + d] = ok ? xr[d] : 0.f;
