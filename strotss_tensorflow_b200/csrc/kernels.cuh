@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __res
     const int rows = min(kRowsPerBlock, n - r0);
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float a = 0.f;
+#pragma unroll 8
         for (int rr = 0; rr < rows; ++rr) a = fmaf(x[static_cast<long long>(r0 + rr) * ld + d], s_w[rr], a);
         part[static_cast<long long>(blockIdx.x) * D + d] = a;
     }
@@ -736,9 +737,14 @@ struct FinalizeArgs {
     float* grad; long long ldg;
 };
 
+// The row is processed in batches of kFinU x 256 elements whose loads are all issued before the first use:
+// with one load group per loop iteration the kernel is latency-bound (ncu: 80 % long-scoreboard stalls).
+constexpr int kFinU = 9;                    // 9 x 256 = 2304 >= 2179: one batch per row at the reference's width
+
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a) {
     extern __shared__ float sg[];       // D floats: g^
     __shared__ float sh[8];
+    __shared__ float sh2[8];
     __shared__ float s_dot;
     const int li = blockIdx.x;                // local row (ss2, gremd, Q, gpal)
     const int i = a.r0 + li;                  // global row (x, inv, coef, grad)
@@ -747,24 +753,45 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a
     const float invN = 1.f / static_cast<float>(a.N);
     const float ci = a.ss2 ? a.coef[i] : 0.f;
     const bool remd_gather = a.gremd && a.scalars[a.slot_branch] == 0.f;
-    const float* gsrc = nullptr; float gsc = 0.f;
-    if (remd_gather) {
-        const int it = static_cast<int>(best_idx(a.remd_colbest[i]));
-        gsrc = a.remd_xs + static_cast<long long>(it) * a.remd_ldxs;
-        gsc = -a.remd_inv_s[it] * invN;
+    // second gradient source of the relaxed EMD: either the scatter buffer row or the matched target row
+    const float* g2 = nullptr; float g2s = 0.f;
+    if (a.gremd) {
+        if (remd_gather) {
+            const int it = static_cast<int>(best_idx(a.remd_colbest[i]));
+            g2 = a.remd_xs + static_cast<long long>(it) * a.remd_ldxs;
+            g2s = -a.remd_inv_s[it] * invN * a.w_remd;
+        } else {
+            g2 = a.gremd + static_cast<long long>(li) * a.ld_gremd;
+            g2s = a.w_remd;
+        }
     }
+    const float* s2 = a.ss2 ? a.ss2 + static_cast<long long>(li) * a.ld_ss2 : nullptr;
+    const float wss = a.w_ss;
     float dot = 0.f, ssq = 0.f;
-    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
-        float g = 0.f;
-        if (a.ss2) g += a.w_ss * (-a.ss2[static_cast<long long>(li) * a.ld_ss2 + d] * invN + a.v[d] + ci * a.sumhat[d]);
-        if (a.gremd) g += a.w_remd * (remd_gather ? gsrc[d] * gsc : a.gremd[static_cast<long long>(li) * a.ld_gremd + d]);
-        sg[d] = g;
-        const float xv = xr[d];
-        dot = fmaf(g, xv, dot);
-        ssq = fmaf(xv, xv, ssq);
+    for (int base = 0; base < a.D; base += kFinU * 256) {
+        float v_s2[kFinU], v_g2[kFinU], v_x[kFinU], v_v[kFinU], v_sh[kFinU];
+#pragma unroll
+        for (int k = 0; k < kFinU; ++k) {
+            const int d = base + threadIdx.x + 256 * k;
+            const bool ok = d < a.D;
+            v_x[k] = ok ? xr[d] : 0.f;
+            v_s2[k] = (ok && s2) ? s2[d] : 0.f;
+            v_v[k] = (ok && s2) ? a.v[d] : 0.f;
+            v_sh[k] = (ok && s2) ? a.sumhat[d] : 0.f;
+            v_g2[k] = (ok && g2) ? g2[d] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kFinU; ++k) {
+            const int d = base + threadIdx.x + 256 * k;
+            if (d < a.D) {
+                const float g = wss * (-v_s2[k] * invN + v_v[k] + ci * v_sh[k]) + g2s * v_g2[k];
+                sg[d] = g;
+                dot = fmaf(g, v_x[k], dot);
+                ssq = fmaf(v_x[k], v_x[k], ssq);
+            }
+        }
     }
     dot = warp_sum(dot); ssq = warp_sum(ssq);
-    __shared__ float sh2[8];
     if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = dot; sh2[threadIdx.x >> 5] = ssq; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -776,11 +803,27 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a
     __syncthreads();
     const float pd = s_dot;
     float* gr = a.grad + static_cast<long long>(i) * a.ldg;
-    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
-        float o = sg[d] * iv - xr[d] * pd;
-        if (a.Q) o += a.w_mom * (a.q_scale * a.Q[static_cast<long long>(li) * a.ldq + d] + a.gmu[d] * invN);
-        if (a.gpal && d < 3) o += a.w_pal * a.gpal[static_cast<long long>(li) * 4 + d];
-        gr[d] = o;
+    const float* qr = a.Q ? a.Q + static_cast<long long>(li) * a.ldq : nullptr;
+    for (int base = 0; base < a.D; base += kFinU * 256) {
+        float v_q[kFinU], v_x[kFinU], v_m[kFinU];
+#pragma unroll
+        for (int k = 0; k < kFinU; ++k) {
+            const int d = base + threadIdx.x + 256 * k;
+            const bool ok = d < a.D;
+            v_x[k] = ok ? xr[d] : 0.f;
+            v_q[k] = (ok && qr) ? qr[d] : 0.f;
+            v_m[k] = (ok && qr) ? a.gmu[d] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kFinU; ++k) {
+            const int d = base + threadIdx.x + 256 * k;
+            if (d < a.D) {
+                float o = sg[d] * iv - v_x[k] * pd;
+                if (qr) o += a.w_mom * (a.q_scale * v_q[k] + v_m[k] * invN);
+                if (a.gpal && d < 3) o += a.w_pal * a.gpal[static_cast<long long>(li) * 4 + d];
+                gr[d] = o;
+            }
+        }
     }
 }
 
