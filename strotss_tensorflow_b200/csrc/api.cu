@@ -64,7 +64,8 @@ struct Feat {
     const float* x = nullptr; long long ld = 0; int n = 0; int np = 0;
     float* inv = nullptr; float* mean = nullptr; float* sumhat = nullptr;
     bf16* xh = nullptr; bf16* cen = nullptr; bf16* dlt = nullptr; bf16* xhT = nullptr; bf16* cenT = nullptr;
-    float* rec = nullptr;
+    float* rec = nullptr;       // palette records for the backward pass
+    float* srec = nullptr;      // palette records for the candidate search
 };
 
 struct strotss_ctx {
@@ -298,7 +299,8 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
     }
     if (w.rec) {
         RET(ensure(h, (t + ".rec").c_str(), (size_t)n * 8, &f.rec));
-        pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, rec_convert, f.rec);
+        RET(ensure(h, (t + ".srec").c_str(), (size_t)n * 8, &f.srec));
+        pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, rec_convert, f.rec, f.srec);
         CKL();
     }
     return 0;
@@ -348,7 +350,8 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
 int prep_rec(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long ld, int n, int convert, cudaStream_t st) {
     PhaseTimer _pt(h, PH_PREP, st);
     RET(ensure(h, (std::string(tag) + ".rec").c_str(), (size_t)n * 8, &f.rec));
-    pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, convert, f.rec);
+    RET(ensure(h, (std::string(tag) + ".srec").c_str(), (size_t)n * 8, &f.srec));
+    pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, convert, f.rec, f.srec);
     CKL();
     return 0;
 }
@@ -486,15 +489,15 @@ int pal_launch(strotss_ctx* h, const float* q, int nq, const float* k, int nk, i
     return 0;
 }
 
-int pal_local(strotss_ctx* h, const float* arec, int M, const float* brec, int N, Shard sh, int mode, PalState& ps,
+int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int N, Shard sh, int mode, PalState& ps,
               float* ry_partial, cudaStream_t st) {
     PhaseTimer _pt(h, PH_PALETTE, st);
     RET(ensure(h, "pal.colbest", (size_t)N, &ps.colbest));
     CK(cudaMemsetAsync(ps.rowbest, 0, sizeof(unsigned long long) * M, st));
     CK(cudaMemsetAsync(ps.colbest, 0, sizeof(unsigned long long) * N, st));
     // target rows (all) against this rank's prediction rows; this rank's prediction rows against all target rows
-    RET(pal_launch(h, arec, M, brec + (size_t)sh.r0 * 8, sh.n(), sh.r0, mode, ps.rowbest, st));
-    RET(pal_launch(h, brec + (size_t)sh.r0 * 8, sh.n(), arec, M, 0, mode, ps.colbest + sh.r0, st));
+    RET(pal_launch(h, asrec, M, bsrec + (size_t)sh.r0 * 8, sh.n(), sh.r0, mode, ps.rowbest, st));
+    RET(pal_launch(h, bsrec + (size_t)sh.r0 * 8, sh.n(), asrec, M, 0, mode, ps.colbest + sh.r0, st));
     best_partial_kernel<<<1, 1024, 0, st>>>(ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
     CKL();
     return 0;
@@ -927,16 +930,17 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     // the palette search (CUDA cores, K = 3) only needs the YUV records of the prediction
     RET(prep_rec(h, "pred", fp, pred, ld_pred, N, 1, st));
     float* pal_rec = fp.rec;
+    float* pal_srec = fp.srec;
     // The palette search can run on a side stream underneath the preparation and the first GEMMs (STROTSS_SIDE=1).
     // Measured on B200 the total changes by -2 %..+3 % run to run (the part is power-limited and the palette kernel
     // competes with the GEMM epilogue warps for issue slots), so the default keeps everything on the caller's stream.
     static const bool no_side = (getenv("STROTSS_SIDE") == nullptr);
     if (no_side) {
-        RET(pal_local(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, st));
+        RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, st));
     } else {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        RET(pal_local(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, h->side));
+        RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, h->side));
         CK(cudaEventRecord(h->ev_join, h->side));
     }
 
@@ -953,7 +957,7 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         PrepWant wp{}; wp.mean = true; wp.xh = true; wp.cenT = true; wp.cen = want_grad;
         RET(prep_features(h, "pred", fp, pred, ld_pred, N, D, Dp, wp, nullptr, 1, st));
     }
-    fp.rec = pal_rec;
+    fp.rec = pal_rec; fp.srec = pal_srec;
 
     RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, st));
     RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, st));
@@ -1066,7 +1070,7 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
         RET(prep_features(h, "fn.x", fx, x, ldx, M, D, round_up(D, BK), w, nullptr, 0, st));
         RET(prep_features(h, "fn.y", fy, y, ldy, N, D, round_up(D, BK), w, nullptr, 0, st));
         PalState ps; ps.rowbest = best;
-        RET(pal_local(h, fx.rec, M, fy.rec, N, sh, distance, ps, partials + PS_PAL_RY, st));
+        RET(pal_local(h, fx.srec, M, fy.srec, N, sh, distance, ps, partials + PS_PAL_RY, st));
         RET(pal_finish(h, fx.rec, M, fy.rec, N, sh, distance, 0, ps, partials + PS_PAL_RY, sc, S_LPAL, S_PAL_RX, S_PAL_RY,
                        S_PAL_BRANCH, want_grad, row_argmin, col_argmin, st));
         if (want_grad) {

@@ -462,7 +462,11 @@ __constant__ float c_rgb2yuv[9] = {0.299f, -0.14714119f, 0.61497538f,
                                    0.587f, -0.28886916f, -0.51496512f,
                                    0.114f, 0.43601035f, -0.10001026f};
 
-__global__ void pal_prep_kernel(const float* __restrict__ x, long long ld, int n, int convert, float* __restrict__ rec) {
+// srec = { y^,u^,v^, c*y,c*u,c*v, |yuv|^2/3, 0 } with c = sqrt(2/3): the candidate search evaluates
+//   cost = 1 - a^.b^ + sqrt(max(|a|^2/3 + |b|^2/3 - (c a).(c b), 1e-6/3))      (= nn/losses.py:12-28 'both', D = 3)
+// in 13 instructions per pair.
+__global__ void pal_prep_kernel(const float* __restrict__ x, long long ld, int n, int convert, float* __restrict__ rec,
+                                float* __restrict__ srec) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const float* xr = x + static_cast<long long>(r) * ld;
@@ -477,6 +481,11 @@ __global__ void pal_prep_kernel(const float* __restrict__ x, long long ld, int n
     const float iv = rsqrtf(fmaxf(sq, kL2NEps));
     float* o = rec + static_cast<long long>(r) * 8;
     o[0] = y; o[1] = u; o[2] = v; o[3] = y * iv; o[4] = u * iv; o[5] = v * iv; o[6] = sq; o[7] = iv;
+    if (srec) {
+        const float c = 0.81649658092772603f;          // sqrt(2/3)
+        float* s = srec + static_cast<long long>(r) * 8;
+        s[0] = y * iv; s[1] = u * iv; s[2] = v * iv; s[3] = c * y; s[4] = c * u; s[5] = c * v; s[6] = sq * (1.f / 3.f); s[7] = 0.f;
+    }
 }
 
 // best[q] = max over keys of -cost(q, key)  (packed; ties -> lowest key index).
@@ -519,14 +528,14 @@ __global__ void __launch_bounds__(kPalThreads) pal_min_kernel(const float* __res
         __syncthreads();
 #pragma unroll 2
         for (int k = 0; k < cnt; ++k) {
-            const float4 b0 = sk[2 * k], b1 = sk[2 * k + 1];       // (y,u,v,y^) (u^,v^,|.|^2,inv)
+            const float4 b0 = sk[2 * k], b1 = sk[2 * k + 1];       // (y^,u^,v^,c*y) (c*u,c*v,|.|^2/3,0)
 #pragma unroll
             for (int t = 0; t < kPalQT; ++t) {
                 float c = 0.f;
-                if (mode != 1) c = 1.f - (a[t][3] * b0.w + a[t][4] * b1.x + a[t][5] * b1.y);
+                if (mode != 1) c = fmaf(-a[t][2], b0.z, fmaf(-a[t][1], b0.y, fmaf(-a[t][0], b0.x, 1.f)));
                 if (mode != 0) {
-                    const float m = a[t][6] + b1.z - 2.f * (a[t][0] * b0.x + a[t][1] * b0.y + a[t][2] * b0.z);
-                    c += fast_sqrt(fmaxf(m, kL2DClamp) * (1.f / 3.f));
+                    const float m = fmaf(-a[t][5], b1.y, fmaf(-a[t][4], b1.x, fmaf(-a[t][3], b0.w, a[t][6] + b1.z)));
+                    c += fast_sqrt(fmaxf(m, kL2DClamp * (1.f / 3.f)));
                 }
                 if (c < bv[t]) { bv[t] = c; bi[t] = kb + k; }
             }
