@@ -27,7 +27,9 @@ WORKLOADS = {
     # name: (N, M)
     "large": (16384, 16384),     # BASELINE.json configs[3]: large-sample loss microbench (the metric's config)
     "default": (1024, 1024),     # reference default sample count (run_strotss.py:68)
+    "masked": (1024, 1024),      # BASELINE.json configs[2]: R = 3 regions (N_r, M_r) of SURVEY 8d, grouped evaluation
 }
+MASKED_REGIONS = [(1024, 1024), (700, 1024), (333, 517)]
 
 
 def f_alg(N, M, D=D_FEAT):
@@ -159,6 +161,45 @@ def run_reference(args, N, M):
     print(json.dumps(line), flush=True)
 
 
+def run_masked(args, dev, S, _lib):
+    """BASELINE configs[2] (masked region-guided transfer): one step = the loss + gradient of one masked train_step
+    (run_strotss.py:112-124) over R = 3 ragged regions, grouped (one C-ABI call, regions on concurrent streams)
+    against the same regions evaluated one after the other through strotss_eval."""
+    import torch
+    probs = [synth_torch(N, M, D_FEAT, args.eps, 100 + r, dev) for r, (N, M) in enumerate(MASKED_REGIONS)]
+    styles = [p[0] for p in probs]; contents = [p[1] for p in probs]; preds = [p[2] for p in probs]
+    h = S.Handle(dev)
+    h.set_style_targets_grouped(styles)
+    singles = []
+    for st in styles:
+        hs = S.Handle(dev); hs.set_style_target(st); singles.append(hs)
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, out
+
+    l0 = h.launch_count
+    ms_g, out = timed(lambda: h.eval_grouped(preds, contents, ALPHA, True))
+    launches = (h.launch_count - l0) // (args.steps + max(args.warmup, 3))
+    ms_s, _ = timed(lambda: [hs.eval(p, c, ALPHA, True) for hs, p, c in zip(singles, preds, contents)])
+    line = {"metric": "masked train_step loss+grad evals/sec, R=3 regions", "value": 1000.0 / ms_g, "unit": "evals/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_g, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"masked transfer, regions (N_r, M_r) = {MASKED_REGIONS}, D={D_FEAT}, alpha={ALPHA}",
+                       "l2": "inputs fit in L2 (launch-bound regime)"},
+            "gpu_launches_per_step": int(launches), "sequential_ms_per_step": ms_s,
+            "loss": float(out[0][_lib.S_TOTAL].item())}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -206,6 +247,10 @@ def main():
         t = torch.tensor([x], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.workload == "masked":
+        run_masked(args, dev, S, _lib)
+        return
 
     # rowshard: every rank holds the same (replicated) inputs and computes its rows of ONE evaluation;
     # replicas: every rank evaluates its own (seeded per rank) problem of the full size.

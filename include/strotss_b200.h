@@ -103,6 +103,24 @@ int strotss_eval(strotss_handle h, const float* pred, long long ld_pred, const f
                  int N, float alpha, float* scalars, float* grad_pred, long long ld_grad,
                  int32_t* remd_row_argmin, int32_t* remd_col_argmin, void* stream);
 
+/* Masked (region-guided) transfer, run_strotss.py:97-125 (--content_mask / --style_mask): R regions, each with its
+ * own StyleLoss target drawn under the style mask (:99-101) and its own content/prediction samples drawn under the
+ * content mask (:115); the per-region losses are averaged (:118-124).  Region r owns rows
+ * [offsets[r], offsets[r+1]) of the concatenated matrices; offsets are HOST arrays of R+1 ints starting at 0, every
+ * region non-empty (N_r is dynamic per iteration, nn/strotss_utils.py:113,120; M_r is fixed per scale).
+ * strotss_set_style_targets_grouped replaces the StyleLoss constructions of :99-101 (once per scale).
+ * strotss_eval_grouped replaces the loop of :114-121:
+ *     loss = (1/R) * sum_r (alpha * self_similarity(pred_r, content_r) + StyleLoss_r(pred_r)) / loss_denom
+ * scalars: device float[STROTSS_NUM_SCALARS], every slot the mean over regions (TOTAL, LOSS_C, LOSS_S are the three
+ * values train_step returns, :123-125).  region_scalars: optional device float[R][STROTSS_NUM_SCALARS].
+ * grad_pred: device (sum_r N_r) x D or NULL; rows of region r receive d loss / d pred_r (including the 1/R).
+ * The regions run concurrently on per-region streams forked from / joined to `stream`.  Single GPU only. */
+int strotss_set_style_targets_grouped(strotss_handle h, const float* style, long long ld, const int* offsets_M, int R, int D,
+                                      void* stream);
+int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,
+                         const int* offsets_N, int R, float alpha, float* scalars, float* region_scalars, float* grad_pred,
+                         long long ld_grad, void* stream);
+
 /* Same evaluation with HOST buffers (pinned memory recommended): copies pred and content to the
  * device, runs strotss_eval, copies scalars (and grad if non-NULL) back and synchronises the stream.
  * This is the call bench.py times as `e2e`. */

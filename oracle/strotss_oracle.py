@@ -312,6 +312,25 @@ def total_loss(style, content, pred, alpha: float = 16.0, dtype=np.float64, want
     return loss, grad, info
 
 
+def masked_total_loss(styles, contents, preds, alpha: float = 16.0, dtype=np.float64, want_grad: bool = False):
+    """The masked train_step (run_strotss.py:112-124): per region r, `(alpha * loss_c_r + loss_s_r) / loss_denom`
+    with that region's StyleLoss target (:99-101); the sum is divided by the number of regions (:121).
+    Returns loss (and the list of per-region gradients, and info with the averaged loss_c / loss_s of :122-123)."""
+    R = len(styles)
+    if not (R == len(contents) == len(preds)) or R == 0:
+        raise ValueError("one style / content / prediction matrix per region")
+    if not want_grad:
+        return sum(total_loss(s, c, p, alpha, dtype) for s, c, p in zip(styles, contents, preds)) / R
+    loss, grads, lc, ls = 0.0, [], 0.0, 0.0
+    for s, c, p in zip(styles, contents, preds):
+        l, g, info = total_loss(s, c, p, alpha, dtype, True)
+        loss += l / R
+        grads.append(g / R)
+        lc += info["loss_c"] / R
+        ls += info["loss_s"] / R
+    return loss, grads, dict(loss_c=lc, loss_s=ls)
+
+
 # --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d; seed-0 convention of nn/rand.py:12-21)
 # --------------------------------------------------------------------------------------

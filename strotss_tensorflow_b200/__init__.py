@@ -6,10 +6,10 @@ the host-side mirror of the reference's Python interface.  Importing it needs on
 anything needs the built library and a B200 -- there is no fallback.
 """
 from .losses import dist_metrics, moment_matching, relaxed_emd, reshape_2d, self_similarity
-from .modules import ContentLoss, StrotssLoss, StyleLoss
+from .modules import ContentLoss, MaskedStrotssLoss, StrotssLoss, StyleLoss
 from .runtime import Handle, shared_handle
 from .sampling import Sampling
 from .strotss_utils import convert_rgb_to_yuv
 
 __all__ = ["relaxed_emd", "moment_matching", "self_similarity", "dist_metrics", "reshape_2d", "convert_rgb_to_yuv",
-           "ContentLoss", "StyleLoss", "StrotssLoss", "Handle", "shared_handle", "Sampling"]
+           "ContentLoss", "StyleLoss", "StrotssLoss", "MaskedStrotssLoss", "Handle", "shared_handle", "Sampling"]

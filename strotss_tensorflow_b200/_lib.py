@@ -34,6 +34,8 @@ SIGNATURES = {
     "strotss_shard_rows": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "strotss_set_style_target": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "strotss_eval": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _f, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "strotss_set_style_targets_grouped": (_i, [_vp, _vp, _ll, C.POINTER(_i), _i, _i, _vp]),
+    "strotss_eval_grouped": (_i, [_vp, _vp, _ll, _vp, _ll, C.POINTER(_i), _i, _f, _vp, _vp, _vp, _ll, _vp]),
     "strotss_eval_host": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "strotss_style_loss": (_i, [_vp, _vp, _ll, _i, _f, _vp, _vp, _ll, _vp]),
     "strotss_relaxed_emd": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _vp]),

@@ -46,6 +46,20 @@ __global__ void yuv_kernel(const float* __restrict__ x, long long ld, int n, flo
     out[3 * r + 2] = R * c_rgb2yuv[2] + G * c_rgb2yuv[5] + B * c_rgb2yuv[8];
 }
 
+// scalars[k] = mean over regions of the per-region scalar blocks (run_strotss.py:118-124); the per-region blocks
+// are optionally copied out as well
+__global__ void mean_scalars_kernel(const float* __restrict__ src, int R, int n, float* __restrict__ mean, float* __restrict__ copy) {
+    const int k = threadIdx.x;
+    if (k >= n) return;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const float v = src[r * n + k];
+        s += v;
+        if (copy) copy[r * n + k] = v;
+    }
+    mean[k] = s / static_cast<float>(R);
+}
+
 __global__ void copy_scalars_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, float* __restrict__ dst) {
     if (threadIdx.x < n) dst[threadIdx.x] = src[idx[threadIdx.x]];
 }
@@ -94,8 +108,12 @@ struct strotss_ctx {
     bool profiling = false;
     std::vector<PhaseRec> recs;
     std::vector<cudaEvent_t> pool;
+    // masked (region-guided) transfer: one child context per region (own workspace, own style target, own stream)
+    std::vector<strotss_ctx*> regions;
+    float* region_scalars = nullptr;      // [R][STROTSS_NUM_SCALARS] device block owned by the parent
 
     ~strotss_ctx() {
+        for (auto* c : regions) delete c;
         for (auto& kv : bufs) cudaFree(kv.second.first);
         if (h_scalars) cudaFreeHost(h_scalars);
         for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -793,12 +811,8 @@ extern "C" {
 
 const char* strotss_version(void) { return "strotss_b200 0.2 (sm_100a, tcgen05/TMA)"; }
 
-int strotss_create(int device, strotss_handle* out) {
-    if (!out) return STROTSS_ERR_ARG;
-    *out = nullptr;
-    strotss_ctx* h = new strotss_ctx();
+static int init_ctx(strotss_ctx* h, int device) {
     h->device = device;
-    *out = h;     // returned even on failure so the caller can read the error text
     int count = 0;
     CK(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) { h->err = "invalid device index " + std::to_string(device); return STROTSS_ERR_ARG; }
@@ -823,6 +837,13 @@ int strotss_create(int device, strotss_handle* out) {
     return 0;
 }
 
+int strotss_create(int device, strotss_handle* out) {
+    if (!out) return STROTSS_ERR_ARG;
+    strotss_ctx* h = new strotss_ctx();
+    *out = h;     // returned even on failure so the caller can read the error text
+    return init_ctx(h, device);
+}
+
 void strotss_destroy(strotss_handle h) {
     if (h && h->nccl_comm && nccl().ok) nccl().CommDestroy(h->nccl_comm);
     delete h;
@@ -830,9 +851,19 @@ void strotss_destroy(strotss_handle h) {
 
 const char* strotss_last_error(strotss_handle h) { return h ? h->err.c_str() : "null handle"; }
 
-size_t strotss_workspace_bytes(strotss_handle h) { return h ? h->ws_bytes : 0; }
+size_t strotss_workspace_bytes(strotss_handle h) {
+    if (!h) return 0;
+    size_t b = h->ws_bytes;
+    for (auto* c : h->regions) b += c->ws_bytes;
+    return b;
+}
 
-long long strotss_launch_count(strotss_handle h) { return h ? h->launches : 0; }
+long long strotss_launch_count(strotss_handle h) {
+    if (!h) return 0;
+    long long n = h->launches;
+    for (auto* c : h->regions) n += c->launches;
+    return n;
+}
 
 int strotss_profile_enable(strotss_handle h, int on) {
     RET(check_handle(h));
@@ -891,11 +922,16 @@ int strotss_shard_rows(strotss_handle h, int N, int* row_begin, int* row_end) {
     return 0;
 }
 
+static int set_style_impl(strotss_handle h, const float* style, int M, int D, long long ld, cudaStream_t st);
+
 int strotss_set_style_target(strotss_handle h, const float* style, int M, int D, long long ld, void* stream) {
     RET(check_handle(h));
     if (!style || M <= 0 || D < 3 || ld < D) { h->err = "set_style_target: bad argument"; return STROTSS_ERR_ARG; }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
+    return set_style_impl(h, style, M, D, ld, static_cast<cudaStream_t>(stream));
+}
+
+static int set_style_impl(strotss_handle h, const float* style, int M, int D, long long ld, cudaStream_t st) {
     h->has_style = false;
     h->M = M; h->D = D; h->Dp = round_up(D, BK); h->Mp = round_up(M, 64);
     // private copy: later evaluations must not depend on the caller keeping `style` alive
@@ -913,7 +949,7 @@ int strotss_set_style_target(strotss_handle h, const float* style, int M, int D,
 // grad (if non-NULL) points at row 0 of an N x D buffer; only rows [r0, r1) of this rank are written.
 static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,
                      int N, float alpha, float* scalars, float* grad, long long ld_grad, int32_t* row_arg, int32_t* col_arg,
-                     bool with_content, bool sharded, cudaStream_t st) {
+                     bool with_content, bool sharded, cudaStream_t st, float grad_scale = 1.f) {
     const int D = h->D, Dp = h->Dp, M = h->M;
     const bool want_grad = grad != nullptr;
     const float inv_alpha = 1.f / (alpha > 1.f ? alpha : 1.f);
@@ -975,12 +1011,12 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     if (want_grad) {
         FinalizeArgs a{};
         a.x = pred; a.ldx = ld_pred; a.inv = fp.inv; a.N = N; a.D = D; a.r0 = sh.r0;
-        if (with_content) { a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = partials + PS_V; a.coef = so.coef; a.sumhat = fp.sumhat; a.w_ss = alpha / denom; }
-        a.gremd = rs.g; a.ld_gremd = rs.ldg; a.w_remd = 1.f / denom;
+        if (with_content) { a.ss2 = so.ss2; a.ld_ss2 = so.ld; a.v = partials + PS_V; a.coef = so.coef; a.sumhat = fp.sumhat; a.w_ss = grad_scale * alpha / denom; }
+        a.gremd = rs.g; a.ld_gremd = rs.ldg; a.w_remd = grad_scale / denom;
         a.remd_colbest = rs.colbest; a.remd_xs = h->style.x; a.remd_ldxs = h->style.ld; a.remd_inv_s = h->style.inv;
         a.scalars = scalars; a.slot_branch = S_REMD_BRANCH;
-        a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = 1.f / denom;
-        a.gpal = ps.g; a.w_pal = inv_alpha / denom;
+        a.Q = mo.Q; a.ldq = mo.ldq; a.q_scale = mo.q_scale; a.gmu = mo.gmu; a.w_mom = grad_scale / denom;
+        a.gpal = ps.g; a.w_pal = grad_scale * inv_alpha / denom;
         a.grad = grad; a.ldg = ld_grad;
         RET(finalize(h, a, sh.n(), st));
     }
@@ -1010,6 +1046,80 @@ int strotss_style_loss(strotss_handle h, const float* pred, long long ld_pred, i
     CK(cudaSetDevice(h->device));
     return eval_impl(h, pred, ld_pred, nullptr, 0, N, alpha, scalars, grad_pred, ld_grad, nullptr, nullptr, false, false,
                      static_cast<cudaStream_t>(stream));
+}
+
+
+// ---- masked (region-guided) transfer: R independent ragged problems per evaluation -------------
+int strotss_set_style_targets_grouped(strotss_handle h, const float* style, long long ld, const int* offsets_M, int R, int D,
+                                      void* stream) {
+    RET(check_handle(h));
+    if (!style || !offsets_M || R <= 0 || D < 3 || ld < D) { h->err = "set_style_targets_grouped: bad argument"; return STROTSS_ERR_ARG; }
+    for (int r = 0; r < R; ++r)
+        if (offsets_M[r + 1] <= offsets_M[r] || offsets_M[0] != 0) {
+            h->err = "set_style_targets_grouped: offsets_M must start at 0 and increase strictly (an empty region has no "
+                     "style samples; the reference falls back to the whole image, nn/strotss_utils.py:107-108)";
+            return STROTSS_ERR_ARG;
+        }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    while (static_cast<int>(h->regions.size()) < R) {
+        strotss_ctx* c = new strotss_ctx();
+        h->regions.push_back(c);
+        const int rc = init_ctx(c, h->device);
+        if (rc != 0) { h->err = "region context: " + c->err; return rc; }
+    }
+    RET(ensure(h, "grouped.scalars", (size_t)R * STROTSS_NUM_SCALARS, &h->region_scalars));
+    // the preparation of each target runs on the caller's stream (once per scale; not worth a fork)
+    for (int r = 0; r < R; ++r) {
+        strotss_ctx* c = h->regions[r];
+        c->profiling = h->profiling;
+        const int rc = set_style_impl(c, style + static_cast<long long>(offsets_M[r]) * ld, offsets_M[r + 1] - offsets_M[r], D, ld, st);
+        if (rc != 0) { h->err = "region " + std::to_string(r) + ": " + c->err; return rc; }
+    }
+    h->D = D; h->Dp = round_up(D, BK);
+    return 0;
+}
+
+int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,
+                         const int* offsets_N, int R, float alpha, float* scalars, float* region_scalars, float* grad_pred,
+                         long long ld_grad, void* stream) {
+    RET(check_handle(h));
+    if (R <= 0 || static_cast<int>(h->regions.size()) < R) {
+        h->err = "strotss_eval_grouped: call strotss_set_style_targets_grouped with the same number of regions first";
+        return STROTSS_ERR_STATE;
+    }
+    for (int r = 0; r < R; ++r)
+        if (!h->regions[r]->has_style) { h->err = "strotss_eval_grouped: region without a style target"; return STROTSS_ERR_STATE; }
+    const int D = h->regions[0]->D;
+    if (!pred || !content || !scalars || !offsets_N || ld_pred < D || ld_content < D || (grad_pred && ld_grad < D)) {
+        h->err = "strotss_eval_grouped: bad argument"; return STROTSS_ERR_ARG;
+    }
+    for (int r = 0; r < R; ++r)
+        if (offsets_N[0] != 0 || offsets_N[r + 1] <= offsets_N[r]) {
+            h->err = "strotss_eval_grouped: offsets_N must start at 0 and increase strictly (every region needs >= 1 sample)";
+            return STROTSS_ERR_ARG;
+        }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    // fork: every region evaluates on its own stream (own workspace), so the small launch-bound kernels of the
+    // regions overlap; join; then the scalars are averaged over regions (run_strotss.py:118-124)
+    CK(cudaEventRecord(h->ev_fork, st));
+    for (int r = 0; r < R; ++r) {
+        strotss_ctx* c = h->regions[r];
+        c->profiling = h->profiling;
+        const int n = offsets_N[r + 1] - offsets_N[r];
+        const long long ro = offsets_N[r];
+        CK(cudaStreamWaitEvent(c->side, h->ev_fork, 0));
+        const int rc = eval_impl(c, pred + ro * ld_pred, ld_pred, content + ro * ld_content, ld_content, n, alpha,
+                                 h->region_scalars + (size_t)r * STROTSS_NUM_SCALARS, grad_pred ? grad_pred + ro * ld_grad : nullptr,
+                                 ld_grad, nullptr, nullptr, true, false, c->side, 1.f / R);
+        if (rc != 0) { h->err = "region " + std::to_string(r) + ": " + c->err; return rc; }
+        CK(cudaEventRecord(c->ev_join, c->side));
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    }
+    mean_scalars_kernel<<<1, 32, 0, st>>>(h->region_scalars, R, STROTSS_NUM_SCALARS, scalars, region_scalars);
+    CKL();
+    return 0;
 }
 
 int strotss_eval_host(strotss_handle h, const float* pred_host, const float* content_host, int N, float alpha,

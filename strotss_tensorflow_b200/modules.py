@@ -83,3 +83,49 @@ class StrotssLoss(torch.nn.Module):
 
     def forward(self, content: torch.Tensor, prediction: torch.Tensor) -> torch.Tensor:
         return _TotalFn.apply(reshape_2d(prediction), reshape_2d(content), self)
+
+
+class _MaskedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, R, *feats):
+        contents, preds = feats[:R], feats[R:]
+        need = any(p.requires_grad for p in preds)
+        scalars, region, grads = module.handle.eval_grouped([p.detach() for p in preds], [c.detach() for c in contents],
+                                                            module.alpha, need)
+        module.last_scalars, module.last_region_scalars = scalars, region
+        ctx.R = R
+        ctx.save_for_backward(*(grads if need else []))
+        return scalars[_lib.S_TOTAL].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.saved_tensors
+        out = tuple(gr * g for gr in grads) if grads else (None,) * ctx.R
+        return (None, None) + (None,) * ctx.R + out
+
+
+class MaskedStrotssLoss(torch.nn.Module):
+    """The masked train_step's loss (run_strotss.py:97-125): one StyleLoss target per region, per-region
+    content/prediction samples, `loss = mean_r (alpha * loss_c_r + loss_s_r) / loss_denom`.
+
+    forward(contents, predictions) takes two lists of (N_r, D) hypercolumn matrices (what
+    `sampling.bilinear(content_feat, pred, mask=content_masks[r])` returns for each region).  After a call
+    `.last_scalars[TOTAL|LOSS_C|LOSS_S]` are the three values train_step reports (:123-125) and
+    `.last_region_scalars` the per-region blocks.
+    """
+
+    def __init__(self, targets, alpha: float):
+        super().__init__()
+        self.alpha = float(alpha)
+        self.targets = [reshape_2d(t).detach() for t in targets]
+        self.handle = Handle(self.targets[0].device)
+        self.handle.set_style_targets_grouped(self.targets)
+        self.last_scalars = None
+        self.last_region_scalars = None
+
+    def forward(self, contents, predictions) -> torch.Tensor:
+        R = len(self.targets)
+        if len(contents) != R or len(predictions) != R:
+            raise ValueError(f"expected {R} regions")
+        feats = [reshape_2d(c) for c in contents] + [reshape_2d(p) for p in predictions]
+        return _MaskedFn.apply(self, R, *feats)

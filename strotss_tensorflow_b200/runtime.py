@@ -126,6 +126,49 @@ class Handle:
                  "strotss_eval")
         return scalars, grad, ra, ca
 
+    # ---- masked (region-guided) transfer: R ragged problems per evaluation ---------------------
+    def set_style_targets_grouped(self, styles):
+        """styles: list of (M_r, D) tensors, one per region (run_strotss.py:99-101)."""
+        styles = [_check_features("style target", reshape_2d(s)) for s in styles]
+        if not styles:
+            raise ValueError("at least one region is required")
+        cat = torch.cat(styles, dim=0).contiguous()
+        offs = [0]
+        for s in styles:
+            offs.append(offs[-1] + int(s.shape[0]))
+        R, D = len(styles), int(cat.shape[1])
+        arr = (C.c_int * (R + 1))(*offs)
+        self._ck(self.lib.strotss_set_style_targets_grouped(self._h, _ptr(cat), cat.stride(0), arr, R, D, _stream(cat.device)),
+                 "strotss_set_style_targets_grouped")
+        self.group_shape = (R, D)
+
+    def eval_grouped(self, preds, contents, alpha: float, want_grad: bool = True):
+        """preds / contents: lists of (N_r, D) tensors (run_strotss.py:114-121).  Returns (mean scalars [16],
+        per-region scalars [R, 16], list of per-region gradients or None)."""
+        if getattr(self, "group_shape", None) is None or len(preds) != self.group_shape[0] or len(contents) != len(preds):
+            raise ValueError("number of regions differs from set_style_targets_grouped")
+        preds = [_check_features("prediction", reshape_2d(p)) for p in preds]
+        contents = [_check_features("content", reshape_2d(c)) for c in contents]
+        offs = [0]
+        for p, c in zip(preds, contents):
+            if p.shape != c.shape:
+                raise ValueError(f"prediction {tuple(p.shape)} and content {tuple(c.shape)} must have the same shape")
+            offs.append(offs[-1] + int(p.shape[0]))
+        pcat = torch.cat(preds, dim=0).contiguous()
+        ccat = torch.cat(contents, dim=0).contiguous()
+        R, D = self.group_shape
+        if pcat.shape[1] != D:
+            raise ValueError("feature width differs from the style targets'")
+        arr = (C.c_int * (R + 1))(*offs)
+        scalars = torch.empty(_lib.NUM_SCALARS, device=pcat.device, dtype=torch.float32)
+        region = torch.empty(R, _lib.NUM_SCALARS, device=pcat.device, dtype=torch.float32)
+        grad = torch.empty_like(pcat) if want_grad else None
+        self._ck(self.lib.strotss_eval_grouped(self._h, _ptr(pcat), pcat.stride(0), _ptr(ccat), ccat.stride(0), arr, R, float(alpha),
+                                               _ptr(scalars), _ptr(region), _ptr(grad), D, _stream(pcat.device)),
+                 "strotss_eval_grouped")
+        grads = list(torch.split(grad, [b - a for a, b in zip(offs[:-1], offs[1:])], dim=0)) if want_grad else None
+        return scalars, region, grads
+
     def eval_host(self, pred_host: torch.Tensor, content_host: torch.Tensor, alpha: float, grad_host: Optional[torch.Tensor],
                   scalars_host: torch.Tensor):
         """Host-buffer evaluation (bench e2e): tensors are CPU float32, ideally pinned."""

@@ -267,6 +267,48 @@ def test_region_sizes_of_masked_mode(S, cuda_device):
     assert abs(total - ref_total) / ref_total <= LOSS_RTOL
 
 
+def test_grouped_masked_evaluation(S, cuda_device):
+    """SURVEY 8(f) next #2 / BASELINE config 3: strotss_eval_grouped == the masked train_step loop
+    (run_strotss.py:112-124): mean over regions of the per-region totals, gradients carry the 1/R."""
+    from strotss_tensorflow_b200 import _lib
+    alpha = 8.0
+    sizes = [(1024, 1024), (700, 1024), (333, 517), (5, 40)]       # N_r = 1 is degenerate: Xd = [~0] / clamp 1e-12
+    probs = [O.synth_problem(N, M, 2179, eps=0.1, seed=40 + r) for r, (N, M) in enumerate(sizes)]
+    styles, contents, preds = zip(*probs)
+    mod = S.MaskedStrotssLoss([_t(s, cuda_device) for s in styles], alpha)
+    pts = [_t(p, cuda_device).requires_grad_(True) for p in preds]
+    loss = mod([_t(c, cuda_device) for c in contents], pts)
+    loss.backward()
+    ref, grefs, info = O.masked_total_loss(styles, contents, preds, alpha, np.float64, True)
+    assert abs(loss.item() - ref) / ref <= LOSS_RTOL
+    s = mod.last_scalars.cpu().numpy()
+    assert abs(s[_lib.S_LOSS_C] - info["loss_c"]) / info["loss_c"] <= LOSS_RTOL
+    assert abs(s[_lib.S_LOSS_S] - info["loss_s"]) / info["loss_s"] <= LOSS_RTOL
+    for r, (p, g) in enumerate(zip(pts, grefs)):
+        _gcheck(p.grad, g, cos_min=0.99)
+    # each region agrees with the single-region entry point (same kernels, different stream / workspace)
+    reg = mod.last_region_scalars.cpu().numpy()
+    for r in range(len(sizes)):
+        one = S.StrotssLoss(_t(styles[r], cuda_device), alpha)
+        sc, gr, _, _ = one.handle.eval(_t(preds[r], cuda_device), _t(contents[r], cuda_device), alpha, True)
+        assert abs(reg[r, _lib.S_TOTAL] - sc[0].item()) <= 1e-6 * abs(sc[0].item())
+        assert torch.allclose(pts[r].grad * len(sizes), gr, rtol=1e-5, atol=1e-9)
+    # the number of prediction samples per region is dynamic (nn/strotss_utils.py:113): re-evaluate with other sizes
+    probs2 = [O.synth_problem(N, M, 2179, eps=0.1, seed=60 + r) for r, (N, M) in enumerate([(900, 1024), (1024, 1024), (64, 517), (300, 40)])]
+    l2 = mod([_t(p[1], cuda_device) for p in probs2], [_t(p[2], cuda_device) for p in probs2])
+    ref2 = O.masked_total_loss(styles, [p[1] for p in probs2], [p[2] for p in probs2], alpha, np.float64)
+    assert abs(l2.item() - ref2) / ref2 <= LOSS_RTOL
+
+
+def test_grouped_argument_errors(S, cuda_device):
+    st, co, pr = O.synth_problem(64, 48, 67, eps=0.1, seed=1)
+    mod = S.MaskedStrotssLoss([_t(st, cuda_device), _t(st[:20], cuda_device)], 4.0)
+    with pytest.raises(ValueError):
+        mod([_t(co, cuda_device)], [_t(pr, cuda_device)])                       # wrong number of regions
+    with pytest.raises(ValueError):
+        mod.handle.eval_grouped([_t(pr, cuda_device), _t(pr[:0], cuda_device)], [_t(co, cuda_device), _t(co[:0], cuda_device)], 4.0)
+
+
 # ------------------------------------------------------------------------------ hypercolumn sampler (8f next #1)
 _SAMPLER_SHAPES = [(85, 128, 3), (85, 128, 64), (85, 128, 64), (42, 64, 128), (42, 64, 128), (21, 32, 256), (21, 32, 256),
                    (21, 32, 256), (10, 16, 512), (10, 16, 512)]                 # content at scale 128 (SURVEY 8d)

@@ -176,3 +176,23 @@ def test_oracle_reproduces_golden(name):
     assert np.array_equal(info["remd"]["col_argmin"], z["remd_col_argmin"])
     assert np.linalg.norm(grad) == pytest.approx(float(z["grad_norm"]), rel=1e-9)
     assert np.allclose(grad[:8, :16], z["grad_head"], rtol=1e-8, atol=1e-14)
+
+
+def test_masked_total_is_mean_of_region_totals():
+    """run_strotss.py:112-124: per-region totals are summed and divided by the number of regions."""
+    probs = [O.synth_problem(N, M, 35, eps=0.2, seed=70 + r) for r, (N, M) in enumerate([(40, 30), (17, 30), (5, 9)])]
+    styles, contents, preds = zip(*probs)
+    loss, grads, info = O.masked_total_loss(styles, contents, preds, 4.0, np.float64, True)
+    singles = [O.total_loss(s, c, p, 4.0, np.float64, True) for s, c, p in probs]
+    assert abs(loss - sum(t[0] for t in singles) / 3) < 1e-15
+    for g, t in zip(grads, singles):
+        assert np.allclose(g, t[1] / 3, rtol=0, atol=1e-18)
+    assert abs(info["loss_c"] - sum(t[2]["loss_c"] for t in singles) / 3) < 1e-15
+    # central difference on one entry of the second region
+    h = 1e-6
+    p2 = [p.astype(np.float64).copy() for p in preds]
+    p2[1][3, 7] += h
+    up = O.masked_total_loss(styles, contents, p2, 4.0, np.float64)
+    p2[1][3, 7] -= 2 * h
+    dn = O.masked_total_loss(styles, contents, p2, 4.0, np.float64)
+    assert abs((up - dn) / (2 * h) - grads[1][3, 7]) < 1e-6 * max(1.0, abs(grads[1][3, 7]))
