@@ -287,20 +287,43 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total = float(scalars[_lib.S_TOTAL].item())
 
-    # ---- end to end through the host-buffer entry point ---------------------------------
+    # ---- end to end through the host-buffer entry points ---------------------------------
+    # every step copies that step's inputs from pinned host memory and reads its scalars + gradient back to the host;
+    # (a) serial: strotss_eval_host, one blocking call per step; (b) pipelined: strotss_eval_host_submit/_wait with two
+    # evaluations in flight, so the PCIe copies of neighbouring steps overlap the kernels (independent evaluations --
+    # BASELINE "throughput mode").  (b) is the headline e2e; (a) is reported beside it.
     ph = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory(); ph.copy_(pred)
     ch = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory(); ch.copy_(content)
-    gh = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory()
-    sh = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32)
+    gh = [torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory() for _ in range(2)]
+    sh = [torch.empty(_lib.NUM_SCALARS, dtype=torch.float32) for _ in range(2)]
     for _ in range(2):
-        h.eval_host(ph, ch, ALPHA, gh, sh)
+        h.eval_host(ph, ch, ALPHA, gh[0], sh[0])
     e2e_steps = max(3, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        h.eval_host(ph, ch, ALPHA, gh, sh)
+        h.eval_host(ph, ch, ALPHA, gh[0], sh[0])
+    torch.cuda.synchronize()
+    e2e_serial_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    barrier()
+
+    def pipelined(nsteps):
+        prev = None
+        for k in range(nsteps):
+            t = h.eval_host_submit(ph, ch, ALPHA, gh[k & 1], sh[k & 1])
+            if prev is not None:
+                h.eval_host_wait(prev)
+            prev = t
+        h.eval_host_wait(prev)
+
+    pipelined(3)
+    e2e_steps = max(4, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    e2e_loss = float(sh[(e2e_steps - 1) & 1][_lib.S_TOTAL])
     barrier()
 
     # ---- N>1, replicas mode: also time ONE evaluation row-sharded over all GPUs (same inputs everywhere) ----
@@ -373,7 +396,11 @@ def main():
                    "precision": "bf16 operands (delta-form self-similarity), fp32 accumulate/reductions"},
         "clocks": clocks,
         "e2e": {"value": jobs * 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 2 * N * D_FEAT * 4, "d2h_bytes_per_step": own_rows * D_FEAT * 4 + _lib.NUM_SCALARS * 4},
+                "h2d_bytes_per_step": 2 * N * D_FEAT * 4, "d2h_bytes_per_step": own_rows * D_FEAT * 4 + _lib.NUM_SCALARS * 4,
+                "mode": "strotss_eval_host_submit/_wait, 2 evaluations in flight (host<->device copies of neighbouring steps "
+                        "overlap the kernels); every step copies its inputs from pinned host memory and reads scalars + gradient back",
+                "serial_value": jobs * 1000.0 / e2e_serial_ms, "serial_ms_per_step": e2e_serial_ms,
+                "serial_mode": "strotss_eval_host, one blocking call per step", "loss": e2e_loss},
         "gpu_launches": int(launches),
         "roofline": roof,
         "whole_eval": {"f_alg": f_alg(N, M), "tflops_alg": f_alg(N, M) / (ms_step * 1e-3) / 1e12,

@@ -127,6 +127,15 @@ int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred,
 int strotss_eval_host(strotss_handle h, const float* pred_host, const float* content_host, int N, float alpha,
                       float* scalars_host, float* grad_host, void* stream);
 
+/* Pipelined form of strotss_eval_host for throughput over independent evaluations (BASELINE configs[4], "throughput
+ * mode"): submit enqueues the input copies, the evaluation and the read-back on three internal streams and returns
+ * a ticket at once; up to two evaluations are in flight, so the PCIe transfers of neighbouring evaluations overlap
+ * the kernels (submitting a third collects the oldest first).  wait blocks until that evaluation's scalars_host /
+ * grad_host are complete.  Host buffers must stay valid (and should be pinned) until the ticket is collected. */
+int strotss_eval_host_submit(strotss_handle h, const float* pred_host, const float* content_host, int N, float alpha,
+                             float* scalars_host, float* grad_host, long long* ticket);
+int strotss_eval_host_wait(strotss_handle h, long long ticket);
+
 /* StyleLoss.__call__(prediction) alone (run_strotss.py:33-40): scalars slots L_M, L_REMD, L_PALETTE,
  * LOSS_S are written; grad (if non-NULL) is d loss_s / d pred. */
 int strotss_style_loss(strotss_handle h, const float* pred, long long ld_pred, int N, float alpha,

@@ -37,6 +37,8 @@ SIGNATURES = {
     "strotss_set_style_targets_grouped": (_i, [_vp, _vp, _ll, C.POINTER(_i), _i, _i, _vp]),
     "strotss_eval_grouped": (_i, [_vp, _vp, _ll, _vp, _ll, C.POINTER(_i), _i, _f, _vp, _vp, _vp, _ll, _vp]),
     "strotss_eval_host": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),
+    "strotss_eval_host_submit": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, C.POINTER(_ll)]),
+    "strotss_eval_host_wait": (_i, [_vp, _ll]),
     "strotss_style_loss": (_i, [_vp, _vp, _ll, _i, _f, _vp, _vp, _ll, _vp]),
     "strotss_relaxed_emd": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _vp]),
     "strotss_moment_matching": (_i, [_vp, _vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp]),

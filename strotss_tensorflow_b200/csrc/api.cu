@@ -108,12 +108,28 @@ struct strotss_ctx {
     bool profiling = false;
     std::vector<PhaseRec> recs;
     std::vector<cudaEvent_t> pool;
+    // pipelined host-buffer evaluation (strotss_eval_host_submit / _wait): two slots in flight on three streams
+    cudaStream_t pipe_h2d = nullptr, pipe_compute = nullptr, pipe_d2h = nullptr;
+    cudaEvent_t pipe_in[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr}, pipe_out[2] = {nullptr, nullptr};
+    float* pipe_scalars_host[2] = {nullptr, nullptr};      // pinned
+    float* pipe_user_scalars[2] = {nullptr, nullptr};
+    long long pipe_ticket[2] = {-1, -1};
+    long long pipe_next = 0;
     // masked (region-guided) transfer: one child context per region (own workspace, own style target, own stream)
     std::vector<strotss_ctx*> regions;
     float* region_scalars = nullptr;      // [R][STROTSS_NUM_SCALARS] device block owned by the parent
 
     ~strotss_ctx() {
         for (auto* c : regions) delete c;
+        for (int i = 0; i < 2; ++i) {
+            if (pipe_in[i]) cudaEventDestroy(pipe_in[i]);
+            if (pipe_done[i]) cudaEventDestroy(pipe_done[i]);
+            if (pipe_out[i]) cudaEventDestroy(pipe_out[i]);
+            if (pipe_scalars_host[i]) cudaFreeHost(pipe_scalars_host[i]);
+        }
+        if (pipe_h2d) cudaStreamDestroy(pipe_h2d);
+        if (pipe_compute) cudaStreamDestroy(pipe_compute);
+        if (pipe_d2h) cudaStreamDestroy(pipe_d2h);
         for (auto& kv : bufs) cudaFree(kv.second.first);
         if (h_scalars) cudaFreeHost(h_scalars);
         for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1146,6 +1162,82 @@ int strotss_eval_host(strotss_handle h, const float* pred_host, const float* con
     }
     CK(cudaStreamSynchronize(st));
     memcpy(scalars_host, h->h_scalars, sizeof(float) * STROTSS_NUM_SCALARS);
+    return 0;
+}
+
+
+// ---- pipelined host-buffer evaluation ---------------------------------------------------------
+// Three internal streams (H2D, compute, D2H) and two staging slots: the input copy of evaluation k+1 and the
+// gradient read-back of evaluation k-1 overlap the kernels of evaluation k (PCIe is full duplex).
+static int pipe_init(strotss_handle h) {
+    if (h->pipe_h2d) return 0;
+    CK(cudaStreamCreateWithFlags(&h->pipe_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->pipe_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->pipe_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&h->pipe_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->pipe_out[i], cudaEventDisableTiming));
+        CK(cudaMallocHost(&h->pipe_scalars_host[i], sizeof(float) * STROTSS_NUM_SCALARS));
+    }
+    return 0;
+}
+
+int strotss_eval_host_wait(strotss_handle h, long long ticket) {
+    RET(check_handle(h));
+    for (int s = 0; s < 2; ++s) {
+        if (h->pipe_ticket[s] != ticket || ticket < 0) continue;
+        CK(cudaEventSynchronize(h->pipe_out[s]));
+        memcpy(h->pipe_user_scalars[s], h->pipe_scalars_host[s], sizeof(float) * STROTSS_NUM_SCALARS);
+        h->pipe_ticket[s] = -1;
+        return 0;
+    }
+    h->err = "strotss_eval_host_wait: unknown or already collected ticket";
+    return STROTSS_ERR_STATE;
+}
+
+int strotss_eval_host_submit(strotss_handle h, const float* pred_host, const float* content_host, int N, float alpha,
+                             float* scalars_host, float* grad_host, long long* ticket) {
+    RET(check_handle(h));
+    if (!h->has_style) { h->err = "strotss_eval_host_submit: call strotss_set_style_target first"; return STROTSS_ERR_STATE; }
+    if (!pred_host || !content_host || !scalars_host || !ticket || N <= 0) {
+        h->err = "strotss_eval_host_submit: bad argument"; return STROTSS_ERR_ARG;
+    }
+    CK(cudaSetDevice(h->device));
+    RET(pipe_init(h));
+    const long long t = h->pipe_next;
+    const int s = static_cast<int>(t & 1);
+    if (h->pipe_ticket[s] >= 0) RET(strotss_eval_host_wait(h, h->pipe_ticket[s]));      // slot still owned: collect it first
+    const size_t elems = (size_t)N * h->D;
+    float *dp, *dc, *dg = nullptr, *ds;
+    const std::string tag = s ? "pipe1." : "pipe0.";
+    RET(ensure(h, (tag + "pred").c_str(), elems, &dp));
+    RET(ensure(h, (tag + "content").c_str(), elems, &dc));
+    RET(ensure(h, (tag + "scalars").c_str(), (size_t)STROTSS_NUM_SCALARS, &ds));
+    if (grad_host) RET(ensure(h, (tag + "grad").c_str(), elems, &dg));
+    const Shard sh = shard_of(h, N, true);
+    // inputs of this slot were last read by the evaluation two tickets ago (pipe_done[s] covers it)
+    CK(cudaStreamWaitEvent(h->pipe_h2d, h->pipe_done[s], 0));
+    CK(cudaMemcpyAsync(dp, pred_host, elems * sizeof(float), cudaMemcpyHostToDevice, h->pipe_h2d));
+    CK(cudaMemcpyAsync(dc, content_host, elems * sizeof(float), cudaMemcpyHostToDevice, h->pipe_h2d));
+    CK(cudaEventRecord(h->pipe_in[s], h->pipe_h2d));
+    // compute: after the inputs arrived and after this slot's previous gradient left the device
+    CK(cudaStreamWaitEvent(h->pipe_compute, h->pipe_in[s], 0));
+    CK(cudaStreamWaitEvent(h->pipe_compute, h->pipe_out[s], 0));
+    RET(eval_impl(h, dp, h->D, dc, h->D, N, alpha, ds, dg, h->D, nullptr, nullptr, true, true, h->pipe_compute));
+    CK(cudaEventRecord(h->pipe_done[s], h->pipe_compute));
+    // read-back
+    CK(cudaStreamWaitEvent(h->pipe_d2h, h->pipe_done[s], 0));
+    CK(cudaMemcpyAsync(h->pipe_scalars_host[s], ds, sizeof(float) * STROTSS_NUM_SCALARS, cudaMemcpyDeviceToHost, h->pipe_d2h));
+    if (grad_host && sh.n() > 0) {
+        const size_t off = (size_t)sh.r0 * h->D;
+        CK(cudaMemcpyAsync(grad_host + off, dg + off, (size_t)sh.n() * h->D * sizeof(float), cudaMemcpyDeviceToHost, h->pipe_d2h));
+    }
+    CK(cudaEventRecord(h->pipe_out[s], h->pipe_d2h));
+    h->pipe_ticket[s] = t;
+    h->pipe_user_scalars[s] = scalars_host;
+    h->pipe_next = t + 1;
+    *ticket = t;
     return 0;
 }
 

@@ -177,6 +177,17 @@ class Handle:
         self._ck(self.lib.strotss_eval_host(self._h, _ptr(pred_host), _ptr(content_host), N, float(alpha), _ptr(scalars_host),
                                             _ptr(grad_host), _stream(dev)), "strotss_eval_host")
 
+    def eval_host_submit(self, pred_host, content_host, alpha: float, grad_host, scalars_host) -> int:
+        """Pipelined host-buffer evaluation: returns a ticket; results are valid after eval_host_wait(ticket)."""
+        N, D = pred_host.shape
+        t = C.c_longlong(-1)
+        self._ck(self.lib.strotss_eval_host_submit(self._h, _ptr(pred_host), _ptr(content_host), N, float(alpha), _ptr(scalars_host),
+                                                   _ptr(grad_host), C.byref(t)), "strotss_eval_host_submit")
+        return int(t.value)
+
+    def eval_host_wait(self, ticket: int):
+        self._ck(self.lib.strotss_eval_host_wait(self._h, int(ticket)), "strotss_eval_host_wait")
+
     def style_loss(self, pred: torch.Tensor, alpha: float, want_grad: bool = True):
         pred = _check_features("prediction", reshape_2d(pred)).contiguous()
         N, D = pred.shape

@@ -267,6 +267,34 @@ def test_region_sizes_of_masked_mode(S, cuda_device):
     assert abs(total - ref_total) / ref_total <= LOSS_RTOL
 
 
+def test_pipelined_host_evaluation_matches_blocking_call(S, cuda_device):
+    """strotss_eval_host_submit/_wait (two evaluations in flight) returns what strotss_eval_host returns."""
+    from strotss_tensorflow_b200 import _lib
+    probs = [O.synth_problem(300 + 40 * k, 260, 2179, eps=0.1, seed=80 + k) for k in range(5)]
+    h = S.Handle(cuda_device)
+    h.set_style_target(_t(probs[0][0], cuda_device))
+    want = []
+    for _, co, pr in probs:
+        g = torch.empty(pr.shape, dtype=torch.float32).pin_memory()
+        sc = torch.empty(_lib.NUM_SCALARS, dtype=torch.float32)
+        h.eval_host(torch.tensor(pr).pin_memory(), torch.tensor(co).pin_memory(), 16.0, g, sc)
+        want.append((sc.clone(), g.clone()))
+    ins = [(torch.tensor(pr).pin_memory(), torch.tensor(co).pin_memory()) for _, co, pr in probs]
+    outs = [(torch.empty(_lib.NUM_SCALARS, dtype=torch.float32), torch.zeros(pr.shape, dtype=torch.float32).pin_memory()) for _, _, pr in probs]
+    tickets = []
+    for k, ((p, c), (sc, g)) in enumerate(zip(ins, outs)):
+        tickets.append(h.eval_host_submit(p, c, 16.0, g, sc))
+        if k >= 1:
+            h.eval_host_wait(tickets[k - 1])
+    h.eval_host_wait(tickets[-1])
+    for (sc, g), (wsc, wg) in zip(outs, want):
+        assert torch.equal(sc[:6], wsc[:6])
+        # the relaxed-EMD scatter branch uses float atomics: allow their reordering noise only
+        assert torch.allclose(g, wg, rtol=1e-4, atol=1e-9)
+    with pytest.raises(S.runtime._lib.StrotssError):
+        h.eval_host_wait(tickets[0])                     # already collected
+
+
 def test_grouped_masked_evaluation(S, cuda_device):
     """SURVEY 8(f) next #2 / BASELINE config 3: strotss_eval_grouped == the masked train_step loop
     (run_strotss.py:112-124): mean over regions of the per-region totals, gradients carry the 1/R."""
