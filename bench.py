@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--eps", type=float, default=1.0, help="pred = content + eps*noise (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the evaluation from a CUDA graph captured around the C-ABI call (launch-bound small workloads)")
     ap.add_argument("--mode", default="replicas", choices=["rowshard", "replicas"],
                     help="N>1: 'replicas' = one problem per GPU, no collective (throughput mode, weak scaling; the headline); "
                          "'rowshard' = ONE evaluation sharded by prediction rows over all GPUs (latency mode, strong scaling). "
@@ -270,19 +272,34 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    h.profile_enable(True)
-    h.profile_read()
+    graph = None
+    if args.graph:
+        # stream capture of the library's launch sequence (branch streams fork from / join to the capture stream)
+        l0 = h.launch_count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            scalars, grad, _, _ = h.eval(pred, content, ALPHA, True, False)
+        per_eval = h.launch_count - l0
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+    else:
+        h.profile_enable(True)
+        h.profile_read()
     l0 = h.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        scalars, grad, _, _ = h.eval(pred, content, ALPHA, True, False)
+        if graph is not None:
+            graph.replay()
+        else:
+            scalars, grad, _, _ = h.eval(pred, content, ALPHA, True, False)
     e1.record()
     barrier()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launches = h.launch_count - l0
-    phases = h.profile_read()
+    launches = (per_eval * args.steps) if graph is not None else (h.launch_count - l0)
+    phases = h.profile_read() if graph is None else {}
     h.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     total = float(scalars[_lib.S_TOTAL].item())
@@ -393,7 +410,8 @@ def main():
                        else f"{world} independent replicas (one problem per GPU, no collective)"),
                    "l2": "inputs (3 x %.0f MB fp32) exceed the 126 MB L2; no flush" % (N * D_FEAT * 4 / 1e6)
                    if N * D_FEAT * 4 * 3 > 126e6 else "inputs fit in L2 (launch-bound regime)",
-                   "precision": "bf16 operands (delta-form self-similarity), fp32 accumulate/reductions"},
+                   "precision": "bf16 operands (delta-form self-similarity), fp32 accumulate/reductions",
+                   "launch": "CUDA graph replay of one captured strotss_eval" if args.graph else "direct C-ABI calls"},
         "clocks": clocks,
         "e2e": {"value": jobs * 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 2 * N * D_FEAT * 4, "d2h_bytes_per_step": own_rows * D_FEAT * 4 + _lib.NUM_SCALARS * 4,

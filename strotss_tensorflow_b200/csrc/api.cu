@@ -101,6 +101,17 @@ struct strotss_ctx {
     // and the tensor-core GEMMs of the main stream (fork/join with events, no host sync)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // second GEMM stream: stage 2 of self-similarity panel p runs underneath stage 1 of panel p+1 (two P buffers),
+    // so the tail wave of one persistent kernel is filled by the CTAs of the other
+    cudaStream_t aux = nullptr;
+    std::vector<cudaEvent_t> ev_seq;
+    int opt_overlap = 0;      // measured +1 % at N = 16384 (the part is power-limited, idle tail SMs are not a loss): off by default
+    // branch-parallel evaluation for small (launch/latency-bound) problems: palette on `side`, relaxed EMD + moments on
+    // `aux`, preparation + self-similarity on the caller's stream; joined before the gradient assembly
+    int opt_branches = 1;
+    int branch_max_n = 4096;
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaStream_t own = nullptr;          // launch stream of a region context (grouped evaluation)
     // multi-GPU row sharding (NCCL through dlopen; see strotss_comm_*)
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
@@ -137,6 +148,11 @@ struct strotss_ctx {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (side) cudaStreamDestroy(side);
+        if (aux) cudaStreamDestroy(aux);
+        if (own) cudaStreamDestroy(own);
+        if (ev_fork2) cudaEventDestroy(ev_fork2);
+        if (ev_join2) cudaEventDestroy(ev_join2);
+        for (auto& e : ev_seq) cudaEventDestroy(e);
     }
 };
 
@@ -299,6 +315,15 @@ int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     return 0;
 }
 
+// rows per block of the column-partial kernels: at most `cap` (32), fewer when that leaves SMs without a block
+int rows_per_block(const strotss_ctx* h, int n, int cap, int mult) {
+    int r = (n + 2 * h->num_sms - 1) / (2 * h->num_sms);
+    r = (r + mult - 1) / mult * mult;
+    if (r < mult) r = mult;
+    if (r > cap) r = cap;
+    return r;
+}
+
 // ---- operand preparation --------------------------------------------------------------
 struct PrepWant { bool mean, sumhat, xh, cen, dlt, xhT, cenT, rec; };
 
@@ -307,12 +332,13 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
     PhaseTimer _pt(h, PH_PREP, st);
     f.x = x; f.ld = ld; f.n = n; f.np = round_up(n, 64);
     const std::string t(tag);
-    const int nblk = (n + kRowsPerBlock - 1) / kRowsPerBlock;
+    const int rpb = rows_per_block(h, n, kRowsPerBlock, 8);
+    const int nblk = (n + rpb - 1) / rpb;
     float *part_raw = nullptr, *part_hat = nullptr;
     RET(ensure(h, (t + ".inv").c_str(), n, &f.inv));
     if (w.mean) { RET(ensure(h, (t + ".mean").c_str(), D, &f.mean)); RET(ensure(h, (t + ".praw").c_str(), (size_t)nblk * D, &part_raw)); }
     if (w.sumhat) { RET(ensure(h, (t + ".sumhat").c_str(), D, &f.sumhat)); RET(ensure(h, (t + ".phat").c_str(), (size_t)nblk * D, &part_hat)); }
-    row_stats_kernel<<<nblk, 256, 0, st>>>(x, ld, n, D, f.inv, part_raw, part_hat);
+    row_stats_kernel<<<nblk, 256, 0, st>>>(x, ld, n, D, f.inv, part_raw, part_hat, rpb);
     CKL();
     if (w.mean) { colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(part_raw, nblk, D, 1.f / n, f.mean); CKL(); }
     if (w.sumhat) { colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(part_hat, nblk, D, 1.f, f.sumhat); CKL(); }
@@ -355,7 +381,8 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
     RET(ensure(h, "pred.mean", (size_t)D, &fx.mean));
     RET(ensure(h, "pred.sumhat", (size_t)D, &fx.sumhat));
     RET(ensure(h, "content.sumhat", (size_t)D, &fy.sumhat));
-    const int nblk = (n + kPrRowsPerBlock - 1) / kPrRowsPerBlock;
+    const int rpb = rows_per_block(h, n, kPrRowsPerBlock, kPrGroup);
+    const int nblk = (n + rpb - 1) / rpb;
     float* part;
     RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
     const int smem = 2 * kPrGroup * Dp * (int)sizeof(float);
@@ -365,7 +392,7 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
         CK(cudaFuncSetAttribute(prep_pair_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    prep_pair_rows_kernel<<<nblk, 256, smem, st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh, fy.xh, fx.dlt, part);
+    prep_pair_rows_kernel<<<nblk, 256, smem, st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh, fy.xh, fx.dlt, part, rpb);
     CKL();
     colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
     CKL();
@@ -617,6 +644,16 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
 
 struct SsOut { float* ss2 = nullptr; long long ld = 0; float* coef = nullptr; };
 
+int seq_event(strotss_ctx* h, size_t i, cudaEvent_t* out) {
+    while (h->ev_seq.size() <= i) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_seq.push_back(e);
+    }
+    *out = h->ev_seq[i];
+    return 0;
+}
+
 // x = prediction (gradient side), y = content.  Needs x.{xh,xhT,dlt,sumhat}, y.{xh,sumhat}.
 // Leaves: sum of this rank's row losses in *loss_partial, this rank's part of v in v_partial[D]
 // (both to be summed over ranks), ss2 rows (local), coef (global indexing, this rank's rows valid).
@@ -640,7 +677,8 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     RET(ensure(h, "ss.coef", (size_t)N, &out.coef));
     const int np = x.np;
     // row panel of P (bf16), sized to stay L2-resident between its producer and consumer GEMMs
-    int panel = 2048;
+    static const int panel_rows = getenv("STROTSS_PANEL") ? atoi(getenv("STROTSS_PANEL")) : 2048;
+    int panel = panel_rows;
     if (panel > round_up(sh.n() > 0 ? sh.n() : 1, BM)) panel = round_up(sh.n() > 0 ? sh.n() : 1, BM);
     // Symmetric mode (this rank owns every row): Xd and Yd are symmetric, so a panel only computes the
     // column tiles at or right of its own rows; tiles strictly right of the panel also account for their
@@ -648,15 +686,27 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     const bool sym = (sh.r0 == 0 && sh.r1 == N);
     float* rcol_part = nullptr;
     if (sym) RET(ensure(h, "ss.rcol_part", (size_t)((N + BM - 1) / BM) * 4 * N, &rcol_part));
-    bf16* P = nullptr;
+    bf16* Pbuf[2] = {nullptr, nullptr};
     out.ss2 = nullptr; out.ld = 0;
+    const int npanels = sh.n() > 0 ? (sh.n() + panel - 1) / panel : 0;
+    // two-stream pipelining: stage 2 of panel p (stream `aux`) under stage 1 of panel p+1 (caller's stream)
+    const bool overlap = want_grad && npanels > 1 && h->opt_overlap != 0 && st != h->aux && N > h->branch_max_n;
     if (want_grad && sh.n() > 0) {
-        RET(ensure(h, "ss.P", (size_t)panel * np, &P));
+        RET(ensure(h, "ss.P", (size_t)panel * np, &Pbuf[0]));
+        if (overlap) RET(ensure(h, "ss.P1", (size_t)panel * np, &Pbuf[1]));
         RET(ensure(h, "ss.ss2", (size_t)sh.n() * Dp, &out.ss2));
         out.ld = Dp;
     }
-    for (int r0 = sh.r0; r0 < sh.r1; r0 += panel) {
+    cudaStream_t st2 = overlap ? h->aux : st;
+    int pidx = 0;
+    for (int r0 = sh.r0; r0 < sh.r1; r0 += panel, ++pidx) {
         const int rows = (sh.r1 - r0 < panel) ? (sh.r1 - r0) : panel;
+        bf16* P = Pbuf[overlap ? (pidx & 1) : 0];
+        if (overlap && pidx >= 2) {
+            // this P buffer was last read by stage 2 of panel pidx-2
+            cudaEvent_t e; RET(seq_event(h, 2 * (pidx - 2) + 1, &e));
+            CK(cudaStreamWaitEvent(st, e, 0));
+        }
         GemmParams<EpiSS1<kSsBN, kSsEpiWarps>> p{};
         // segment 0: delta_I . x^_J ; segment 1: y^_I . delta_J  (both into acc 0) ; segment 2: y^_I . y^_J (acc 1)
         RET(make_tmap(h, &p.tmA[0], x.dlt, N, Dp, Dp, BM));
@@ -720,7 +770,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             }
         }
         if (want_grad) {
-            PhaseTimer _pt(h, PH_SS2, st);
+            if (overlap) {
+                cudaEvent_t e; RET(seq_event(h, 2 * pidx, &e));
+                CK(cudaEventRecord(e, st));
+                CK(cudaStreamWaitEvent(st2, e, 0));
+            }
+            PhaseTimer _pt(h, PH_SS2, st2);
             if (pair_enabled()) {
                 // Operand roles swapped (A = x^T rows d, B = P rows): thread = feature d, so every epilogue store
                 // instruction writes 32 consecutive floats of one ss2 row (coalesced), also for the accumulating 2b.
@@ -732,7 +787,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                 q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (rows + 255) / 256;
                 q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = rows;
                 q.epi.alpha = 1.f; q.epi.col_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
-                RET((launch_gemm256<1, 8>(h, q, st)));
+                RET((launch_gemm256<1, 8>(h, q, st2)));
                 if (sym && r0 + panel < N) {
                     // stage 2b: ss2[j][d] += sum_{i in panel} P[i][j] x^[i][d] for the rows j right of the panel;
                     // B = P^T is read from the row-major panel through MN-major descriptors
@@ -744,7 +799,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
                     t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = mext;
                     t.epi.alpha = 1.f; t.epi.col_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
-                    RET((launch_gemm256<1, 8, true>(h, t, st)));
+                    RET((launch_gemm256<1, 8, true>(h, t, st2)));
                 }
             } else {
                 // single-CTA kernels: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]
@@ -756,7 +811,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                 q.a_row0 = 0; q.b_row0 = 0;
                 q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = rows; q.epi.cols = D;
                 q.epi.alpha = 1.f; q.epi.row_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
-                RET((launch_gemm<256, 1, 4>(h, q, st)));
+                RET((launch_gemm<256, 1, 4>(h, q, st2)));
                 if (sym && r0 + panel < N) {
                     // stage 2b: ss2[rows right of the panel] += P[panel, those columns]^T . x^[panel rows]  (MN-major A)
                     const int m0 = r0 + panel, mext = N - m0;
@@ -768,10 +823,18 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     t.a_row0 = 0; t.b_row0 = 0;
                     t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = mext; t.epi.cols = D;
                     t.epi.alpha = 1.f; t.epi.row_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
-                    RET((launch_gemm<256, 1, 4, 4, true>(h, t, st)));
+                    RET((launch_gemm<256, 1, 4, 4, true>(h, t, st2)));
                 }
             }
+            if (overlap) {
+                cudaEvent_t e; RET(seq_event(h, 2 * pidx + 1, &e));
+                CK(cudaEventRecord(e, st2));
+            }
         }
+    }
+    if (overlap) {                         // join: the rest of the evaluation needs every ss2 row
+        cudaEvent_t e; RET(seq_event(h, 2 * (npanels - 1) + 1, &e));
+        CK(cudaStreamWaitEvent(st, e, 0));
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
@@ -783,11 +846,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     CKL();
     if (want_grad) {
         if (sh.n() > 0) {
-            const int nblk = (sh.n() + kRowsPerBlock - 1) / kRowsPerBlock;
+            const int rpb = rows_per_block(h, sh.n(), kRowsPerBlock, 4);
+            const int nblk = (sh.n() + rpb - 1) / rpb;
             float* vpart;
             RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
             weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
-                                                         out.coef + sh.r0, vpart);
+                                                         out.coef + sh.r0, vpart, rpb);
             CKL();
             colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(vpart, nblk, D, 1.f, v_partial);
             CKL();
@@ -848,6 +912,12 @@ static int init_ctx(strotss_ctx* h, int device) {
     h->encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
     CK(cudaMallocHost(&h->h_scalars, sizeof(float) * STROTSS_NUM_SCALARS));
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+    if (const char* e = getenv("STROTSS_OVERLAP")) h->opt_overlap = atoi(e);
+    if (const char* e = getenv("STROTSS_BRANCHES")) h->opt_branches = atoi(e);
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return 0;
@@ -983,17 +1053,21 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     RET(prep_rec(h, "pred", fp, pred, ld_pred, N, 1, st));
     float* pal_rec = fp.rec;
     float* pal_srec = fp.srec;
-    // The palette search can run on a side stream underneath the preparation and the first GEMMs (STROTSS_SIDE=1).
-    // Measured on B200 the total changes by -2 %..+3 % run to run (the part is power-limited and the palette kernel
-    // competes with the GEMM epilogue warps for issue slots), so the default keeps everything on the caller's stream.
-    static const bool no_side = (getenv("STROTSS_SIDE") == nullptr);
-    if (no_side) {
-        RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, st));
-    } else {
+    // Large problems are tensor-pipe / power bound: everything stays on the caller's stream (running the palette search
+    // underneath the GEMMs measured -2 %..+3 %).  Small problems (the reference's default 1024 samples, the masked
+    // regions) are latency-bound chains of short kernels: there the independent terms run as parallel branches.
+    const bool exch = sharded && h->world > 1 && h->nccl_comm;
+    const bool par = h->opt_branches != 0 && !exch && N <= h->branch_max_n && M <= h->branch_max_n && st != h->side && st != h->aux;
+    cudaStream_t s_pal = par ? h->side : st, s_aux = par ? h->aux : st;
+    if (par) {
         CK(cudaEventRecord(h->ev_fork, st));
-        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, h->side));
-        CK(cudaEventRecord(h->ev_join, h->side));
+        CK(cudaStreamWaitEvent(s_pal, h->ev_fork, 0));
+    }
+    RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, s_pal));
+    if (par) {
+        RET(pal_finish(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
+                       S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, s_pal));
+        CK(cudaEventRecord(h->ev_join, s_pal));
     }
 
     if (with_content && Dp <= 2560) {
@@ -1011,16 +1085,28 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     }
     fp.rec = pal_rec; fp.srec = pal_srec;
 
-    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, st));
-    RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, st));
+    if (par) {
+        CK(cudaEventRecord(h->ev_fork2, st));
+        CK(cudaStreamWaitEvent(s_aux, h->ev_fork2, 0));
+    }
+    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, s_aux));
+    if (par)
+        RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
+                        want_grad, row_arg, col_arg, s_aux));
+    RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_aux));
+    if (par) CK(cudaEventRecord(h->ev_join2, s_aux));
     if (with_content)
         RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
-    if (!no_side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));          // join
-    if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
-    RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
-                    want_grad, row_arg, col_arg, st));
-    RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
-                   S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st));
+    if (par) {
+        CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+        CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
+    } else {
+        if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
+        RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
+                        want_grad, row_arg, col_arg, st));
+        RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
+                       S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st));
+    }
     combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom,
                                              with_content ? partials + PS_SS_LOSS : nullptr, 1.f / N);
     CKL();
@@ -1125,13 +1211,13 @@ int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred,
         c->profiling = h->profiling;
         const int n = offsets_N[r + 1] - offsets_N[r];
         const long long ro = offsets_N[r];
-        CK(cudaStreamWaitEvent(c->side, h->ev_fork, 0));
+        CK(cudaStreamWaitEvent(c->own, h->ev_fork, 0));
         const int rc = eval_impl(c, pred + ro * ld_pred, ld_pred, content + ro * ld_content, ld_content, n, alpha,
                                  h->region_scalars + (size_t)r * STROTSS_NUM_SCALARS, grad_pred ? grad_pred + ro * ld_grad : nullptr,
-                                 ld_grad, nullptr, nullptr, true, false, c->side, 1.f / R);
+                                 ld_grad, nullptr, nullptr, true, false, c->own, 1.f / R);
         if (rc != 0) { h->err = "region " + std::to_string(r) + ": " + c->err; return rc; }
-        CK(cudaEventRecord(c->ev_join, c->side));
-        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        CK(cudaEventRecord(c->ev_join2, c->own));
+        CK(cudaStreamWaitEvent(st, c->ev_join2, 0));
     }
     mean_scalars_kernel<<<1, 32, 0, st>>>(h->region_scalars, R, STROTSS_NUM_SCALARS, scalars, region_scalars);
     CKL();

@@ -27,11 +27,11 @@ enum Scalar {
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, long long ld, int n, int D,
                                                         float* __restrict__ inv, float* __restrict__ part_raw,
-                                                        float* __restrict__ part_hat) {
+                                                        float* __restrict__ part_hat, int rpb) {
     __shared__ float s_inv[kRowsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r0 = blockIdx.x * kRowsPerBlock;
-    for (int rr = warp; rr < kRowsPerBlock; rr += 8) {
+    const int r0 = blockIdx.x * rpb;
+    for (int rr = warp; rr < rpb; rr += 8) {
         const int r = r0 + rr;
         float ss = 0.f;
         if (r < n) {
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
         }
     }
     __syncthreads();
-    const int rows = min(kRowsPerBlock, n - r0);
+    const int rows = min(rpb, n - r0);
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float a = 0.f, h = 0.f;
         for (int rr = 0; rr < rows; ++rr) {
@@ -62,15 +62,15 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
 // weighted sum of normalised rows: part[b][d] = sum_{r in block b} coef[r] * inv[r] * x[r][d]
 __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __restrict__ x, long long ld, int n, int D,
                                                               const float* __restrict__ inv, const float* __restrict__ coef,
-                                                              float* __restrict__ part) {
+                                                              float* __restrict__ part, int rpb) {
     __shared__ float s_w[kRowsPerBlock];
-    const int r0 = blockIdx.x * kRowsPerBlock;
-    if (threadIdx.x < kRowsPerBlock) {
+    const int r0 = blockIdx.x * rpb;
+    if (threadIdx.x < rpb) {
         const int r = r0 + threadIdx.x;
         s_w[threadIdx.x] = (r < n) ? coef[r] * inv[r] : 0.f;
     }
     __syncthreads();
-    const int rows = min(kRowsPerBlock, n - r0);
+    const int rows = min(rpb, n - r0);
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float a = 0.f;
 #pragma unroll 8
@@ -191,25 +191,26 @@ __global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
 // and the loads of some blocks overlap the arithmetic/stores of the others.
 // --------------------------------------------------------------------------------------
 constexpr int kPrGroup = 2;               // rows per staging group
-constexpr int kPrRowsPerBlock = 32;
+constexpr int kPrRowsPerBlock = 32;      // upper bound; small inputs use fewer rows per block to fill the chip
 
 __global__ void __launch_bounds__(256, 4) prep_pair_rows_kernel(const float* __restrict__ x, long long ldx,
                                                              const float* __restrict__ y, long long ldy, int n, int D, int Dp,
                                                              float* __restrict__ inv_x, float* __restrict__ inv_y,
                                                              __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ yh,
-                                                             __nv_bfloat16* __restrict__ dlt, float* __restrict__ part) {
+                                                             __nv_bfloat16* __restrict__ dlt, float* __restrict__ part,
+                                                             int rows_per_block) {
     extern __shared__ float sm[];          // [2][kPrGroup][Dp]
     __shared__ float s_inv[2][kPrGroup];
     float* sx = sm;
     float* sy = sm + kPrGroup * Dp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_base = blockIdx.x * kPrRowsPerBlock;
+    const int row_base = blockIdx.x * rows_per_block;
     constexpr int kMaxCols = 10;           // columns per thread: Dp <= 2560
     float ax[kMaxCols], ahx[kMaxCols], ahy[kMaxCols];
 #pragma unroll
     for (int c = 0; c < kMaxCols; ++c) { ax[c] = 0.f; ahx[c] = 0.f; ahy[c] = 0.f; }
 
-    for (int g = 0; g < kPrRowsPerBlock; g += kPrGroup) {
+    for (int g = 0; g < rows_per_block; g += kPrGroup) {
         __syncthreads();                    // previous group fully consumed
 #pragma unroll
         for (int rr = 0; rr < kPrGroup; ++rr) {
