@@ -110,7 +110,8 @@ struct strotss_ctx {
     // `aux`, preparation + self-similarity on the caller's stream; joined before the gradient assembly
     int opt_branches = 1;
     int branch_max_n = 4096;
-    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
+    cudaStream_t aux2 = nullptr;
     cudaStream_t own = nullptr;          // launch stream of a region context (grouped evaluation)
     // multi-GPU row sharding (NCCL through dlopen; see strotss_comm_*)
     int rank = 0, world = 1;
@@ -150,6 +151,8 @@ struct strotss_ctx {
         if (side) cudaStreamDestroy(side);
         if (aux) cudaStreamDestroy(aux);
         if (own) cudaStreamDestroy(own);
+        if (aux2) cudaStreamDestroy(aux2);
+        if (ev_join3) cudaEventDestroy(ev_join3);
         if (ev_fork2) cudaEventDestroy(ev_fork2);
         if (ev_join2) cudaEventDestroy(ev_join2);
         for (auto& e : ev_seq) cudaEventDestroy(e);
@@ -489,11 +492,14 @@ struct RemdState {
     float* g = nullptr; long long ldg = 0;   // [n_local x D] gradient w.r.t. normalised prediction rows
 };
 
+// zeroed: rs.rowbest / rs.colbest were assigned and cleared by the caller (one memset for the whole evaluation)
 int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int N, Shard sh, int Dp, RemdState& rs,
-               float* ry_partial, cudaStream_t st) {
-    RET(ensure(h, "remd.colbest", (size_t)N, &rs.colbest));
-    CK(cudaMemsetAsync(rs.rowbest, 0, sizeof(unsigned long long) * M, st));
-    CK(cudaMemsetAsync(rs.colbest, 0, sizeof(unsigned long long) * N, st));
+               float* ry_partial, cudaStream_t st, bool zeroed = false) {
+    if (!zeroed) {
+        RET(ensure(h, "remd.colbest", (size_t)N, &rs.colbest));
+        CK(cudaMemsetAsync(rs.rowbest, 0, sizeof(unsigned long long) * M, st));
+        CK(cudaMemsetAsync(rs.colbest, 0, sizeof(unsigned long long) * N, st));
+    }
     if (sh.n() > 0) {
         GemmParams<EpiRemd<256>> p{};
         RET(make_tmap(h, &p.tmA[0], target.xh, M, Dp, Dp, BM));
@@ -503,7 +509,19 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
         p.a_row0 = 0; p.b_row0 = sh.r0;
         p.epi.rowbest = rs.rowbest; p.epi.colbest = rs.colbest; p.epi.M = M; p.epi.N = sh.r1;
         PhaseTimer _pt(h, PH_REMD_GEMM, st);
-        RET((launch_gemm256<1>(h, p, st)));
+        if (M <= 2048 && sh.n() <= 2048) {
+            // few 256-wide tiles: 128 x 128 single-CTA tiles fill four times as many SMs
+            GemmParams<EpiRemd<128>> q{};
+            q.tmA[0] = p.tmA[0];
+            RET(make_tmap(h, &q.tmB[0], pred.xh, N, Dp, Dp, 128));
+            q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
+            q.tiles_m = p.tiles_m; q.tiles_n = (sh.n() + 127) / 128;
+            q.a_row0 = 0; q.b_row0 = sh.r0;
+            q.epi.rowbest = rs.rowbest; q.epi.colbest = rs.colbest; q.epi.M = M; q.epi.N = sh.r1;
+            RET((launch_gemm<128, 1, 6>(h, q, st)));
+        } else {
+            RET((launch_gemm256<1>(h, p, st)));
+        }
     }
     PhaseTimer _pm(h, PH_REMD_MISC, st);
     best_partial_kernel<<<1, 1024, 0, st>>>(rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
@@ -551,11 +569,13 @@ int pal_launch(strotss_ctx* h, const float* q, int nq, const float* k, int nk, i
 }
 
 int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int N, Shard sh, int mode, PalState& ps,
-              float* ry_partial, cudaStream_t st) {
+              float* ry_partial, cudaStream_t st, bool zeroed = false) {
     PhaseTimer _pt(h, PH_PALETTE, st);
-    RET(ensure(h, "pal.colbest", (size_t)N, &ps.colbest));
-    CK(cudaMemsetAsync(ps.rowbest, 0, sizeof(unsigned long long) * M, st));
-    CK(cudaMemsetAsync(ps.colbest, 0, sizeof(unsigned long long) * N, st));
+    if (!zeroed) {
+        RET(ensure(h, "pal.colbest", (size_t)N, &ps.colbest));
+        CK(cudaMemsetAsync(ps.rowbest, 0, sizeof(unsigned long long) * M, st));
+        CK(cudaMemsetAsync(ps.colbest, 0, sizeof(unsigned long long) * N, st));
+    }
     // target rows (all) against this rank's prediction rows; this rank's prediction rows against all target rows
     RET(pal_launch(h, asrec, M, bsrec + (size_t)sh.r0 * 8, sh.n(), sh.r0, mode, ps.rowbest, st));
     RET(pal_launch(h, bsrec + (size_t)sh.r0 * 8, sh.n(), asrec, M, 0, mode, ps.colbest + sh.r0, st));
@@ -566,15 +586,19 @@ int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int
 
 int pal_finish(strotss_ctx* h, const float* arec, int M, const float* brec, int N, Shard sh, int mode, int convert, PalState& ps,
                const float* ry_sum, float* scalars, int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad,
-               int32_t* row_arg, int32_t* col_arg, cudaStream_t st) {
+               int32_t* row_arg, int32_t* col_arg, cudaStream_t st, float* g_zeroed = nullptr) {
     PhaseTimer _pt(h, PH_PALETTE, st);
     remd_finish_kernel<<<1, 1024, 0, st>>>(ps.rowbest, M, ry_sum, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
                                            row_arg, ps.colbest, sh.r0, sh.r1, col_arg);
     CKL();
     ps.g = nullptr;
     if (want_grad && sh.n() > 0) {
-        RET(ensure(h, "pal.g", (size_t)sh.n() * 4, &ps.g));
-        CK(cudaMemsetAsync(ps.g, 0, sizeof(float) * (size_t)sh.n() * 4, st));
+        if (g_zeroed) {
+            ps.g = g_zeroed;
+        } else {
+            RET(ensure(h, "pal.g", (size_t)sh.n() * 4, &ps.g));
+            CK(cudaMemsetAsync(ps.g, 0, sizeof(float) * (size_t)sh.n() * 4, st));
+        }
         const int rows = M > sh.n() ? M : sh.n();
         pal_backward_kernel<<<(rows + 127) / 128, 128, 0, st>>>(ps.rowbest, M, ps.colbest, N, sh.r0, sh.r1, arec, brec, mode,
                                                                 convert, scalars, slot_branch, ps.g);
@@ -587,8 +611,10 @@ struct MomOut { float* Q = nullptr; long long ldq = 0; float q_scale = 0.f; floa
 
 // Target mean / covariance given explicitly (mu_x, Vx with row stride Dp).  The covariance forward is
 // replicated on every rank (3 % of the work); the backward GEMM covers this rank's rows only.
+int mom_nparts(int D) { return (((D + BM - 1) / BM + 1) / 2 * 2) * ((D + 255) / 256) * 4; }
+
 int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred, int N, Shard sh, int D, int Dp, float* scalars,
-            bool want_grad, MomOut& out, cudaStream_t st) {
+            bool want_grad, MomOut& out, cudaStream_t st, float* part_zeroed = nullptr) {
     bf16* Sg; float* part;
     RET(ensure(h, "mom.Sg", (size_t)Dp * Dp, &Sg, /*zero_on_alloc=*/true));
     GemmParams<EpiCovFwd<256>> p{};
@@ -597,14 +623,15 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     p.nseg = 1; p.seg_kblocks[0] = pred.np / BK; p.seg_acc[0] = 0;
     p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
     // one partial per (128-row block, column tile, epilogue warp); a pair tile always has two row blocks
-    const int npart = ((p.tiles_m + 1) / 2 * 2) * p.tiles_n * 4;
-    RET(ensure(h, "mom.part", (size_t)npart, &part));
+    const int npart = mom_nparts(D);
+    if (part_zeroed) part = part_zeroed;
+    else RET(ensure(h, "mom.part", (size_t)npart, &part));
     p.epi.Vx = Vx; p.epi.ldv = Dp; p.epi.Sg = Sg; p.epi.lds = Dp; p.epi.part = part; p.epi.inv_n = 1.f / N; p.epi.D = D;
     p.epi.tiles_n = p.tiles_n;
     // V is symmetric: with CTA pairs the tile grid is square (256 x 256 tiles), so only the upper triangle is
     // computed; off-diagonal tiles count twice in the loss and write both Sg blocks
     p.tri = pair_enabled() ? 1 : 0; p.epi.sym = p.tri; p.epi.diag_cols = 256;
-    CK(cudaMemsetAsync(part, 0, sizeof(float) * npart, st));
+    if (!part_zeroed) CK(cudaMemsetAsync(part, 0, sizeof(float) * npart, st));
     { PhaseTimer _pt(h, PH_COV_FWD, st); RET((launch_gemm256<1>(h, p, st))); }
     RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
     {
@@ -654,6 +681,30 @@ int seq_event(strotss_ctx* h, size_t i, cudaEvent_t* out) {
     return 0;
 }
 
+// Stage 1 with 128 x 128 single-CTA tiles (two double-buffered accumulators): used when the whole problem is a
+// handful of 256-wide tiles (the reference's default 1024 samples), where the 256 x 256 CTA-pair kernel would leave
+// most SMs without a tile.
+template <class EpiP>
+int ss1_small(strotss_ctx* h, const Feat& x, const Feat& y, int N, int Dp, int r0, int c0, int rows, const EpiP& e, cudaStream_t st) {
+    GemmParams<EpiSS1<128, 4>> p{};
+    RET(make_tmap(h, &p.tmA[0], x.dlt, N, Dp, Dp, BM));
+    RET(make_tmap(h, &p.tmB[0], x.xh, N, Dp, Dp, 128));
+    RET(make_tmap(h, &p.tmA[1], y.xh, N, Dp, Dp, BM));
+    RET(make_tmap(h, &p.tmB[1], x.dlt, N, Dp, Dp, 128));
+    RET(make_tmap(h, &p.tmA[2], y.xh, N, Dp, Dp, BM));
+    RET(make_tmap(h, &p.tmB[2], y.xh, N, Dp, Dp, 128));
+    p.nseg = 3;
+    for (int s = 0; s < 3; ++s) p.seg_kblocks[s] = Dp / BK;
+    p.seg_acc[0] = 0; p.seg_acc[1] = 0; p.seg_acc[2] = 1;
+    p.tiles_m = (rows + BM - 1) / BM; p.tiles_n = (N - c0 + 127) / 128;
+    p.a_row0 = r0; p.b_row0 = c0;
+    p.epi.u = e.u; p.epi.w = e.w; p.epi.P = e.P; p.epi.ldp = e.ldp; p.epi.panel_row0 = e.panel_row0;
+    p.epi.loss_part = e.loss_part; p.epi.r_part = e.r_part; p.epi.N = e.N; p.epi.row_end = e.row_end;
+    p.epi.write_p = e.write_p; p.epi.sym = e.sym; p.epi.panel_end = e.panel_end; p.epi.rcol_part = e.rcol_part;
+    PhaseTimer _pt(h, PH_SS1, st);
+    return launch_gemm<128, 2, 6, 4>(h, p, st);
+}
+
 // x = prediction (gradient side), y = content.  Needs x.{xh,xhT,dlt,sumhat}, y.{xh,sumhat}.
 // Leaves: sum of this rank's row losses in *loss_partial, this rank's part of v in v_partial[D]
 // (both to be summed over ranks), ss2 rows (local), coef (global indexing, this rank's rows valid).
@@ -669,8 +720,11 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         CKL();
     }
     constexpr int kSsBN = 256, kSsEpiWarps = 8, kSsSplit = kSsEpiWarps / 4;
-    const int tiles_n = (N + kSsBN - 1) / kSsBN;
-    const int nslots = tiles_n * kSsSplit;
+    static const int small_max = getenv("STROTSS_SS1_SMALL_MAX") ? atoi(getenv("STROTSS_SS1_SMALL_MAX")) : 2048;
+    const bool small = sh.n() <= small_max && N <= small_max;           // single panel, few tiles
+    const int ss_bn = small ? 128 : kSsBN, ss_split = small ? 1 : kSsSplit;
+    const int tiles_n = (N + ss_bn - 1) / ss_bn;
+    const int nslots = tiles_n * ss_split;
     RET(ensure(h, "ss.loss_part", (size_t)nslots * N, &loss_part));
     RET(ensure(h, "ss.r_part", (size_t)nslots * N, &r_part));
     RET(ensure(h, "ss.rowloss", (size_t)N, &rowloss));
@@ -727,7 +781,9 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.row_end = sh.r1;
         p.epi.write_p = (want_grad ? 1 : 0);
         p.epi.sym = sym ? 1 : 0; p.epi.panel_end = r0 + panel; p.epi.rcol_part = rcol_part;
-        if (generic_ss1) {
+        if (small) {
+            RET(ss1_small(h, x, y, N, Dp, r0, c0, rows, p.epi, st));
+        } else if (generic_ss1) {
             PhaseTimer _pt(h, PH_SS1, st);
             RET((launch_gemm<kSsBN, 2, 4, kSsEpiWarps>(h, p, st)));
         } else {
@@ -839,7 +895,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
         ss_rows_kernel<<<(sh.n() + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
-                                                             sym ? 1 : 0, panel, (panel / kSsBN) * kSsSplit, rcol_part, (panel / BM) * 4);
+                                                             sym ? 1 : 0, panel, (panel / ss_bn) * ss_split, rcol_part, (panel / BM) * 4);
         CKL();
     }
     reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss + sh.r0, sh.n(), 1.f, loss_partial);
@@ -914,6 +970,8 @@ static int init_ctx(strotss_ctx* h, int device) {
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->aux2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     if (const char* e = getenv("STROTSS_OVERLAP")) h->opt_overlap = atoi(e);
@@ -1042,13 +1100,21 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     const float denom = with_content ? (2.f + alpha + inv_alpha) : 1.f;
     const Shard sh = shard_of(h, N, sharded);
     CK(cudaMemsetAsync(scalars, 0, sizeof(float) * STROTSS_NUM_SCALARS, st));
+    // one cleared block per evaluation: packed minima [2M + 2N] u64 | partial sums [PS_V + D] | covariance partials | palette grad [4N]
     unsigned long long* best; float* partials;
-    RET(ensure(h, "eval.best", (size_t)2 * M, &best));
-    RET(ensure(h, "eval.partials", (size_t)PS_V + D, &partials));
-    CK(cudaMemsetAsync(partials, 0, sizeof(float) * (PS_V + D), st));
+    const size_t nbest = (size_t)2 * M + 2 * N;
+    const size_t nfl = (size_t)PS_V + D + mom_nparts(D) + 4 * (size_t)N;
+    unsigned char* zblock;
+    RET(ensure(h, "eval.zero", nbest * 8 + nfl * 4, &zblock));
+    CK(cudaMemsetAsync(zblock, 0, nbest * 8 + nfl * 4, st));
+    best = reinterpret_cast<unsigned long long*>(zblock);
+    partials = reinterpret_cast<float*>(zblock + nbest * 8);
+    float* mom_part = partials + PS_V + D;
+    float* pal_g = mom_part + mom_nparts(D);
     Feat fp, fc;
     RemdState rs; PalState ps; MomOut mo; SsOut so;
     rs.rowbest = best; ps.rowbest = best + M;
+    rs.colbest = best + 2 * M; ps.colbest = best + 2 * M + N;
     // the palette search (CUDA cores, K = 3) only needs the YUV records of the prediction
     RET(prep_rec(h, "pred", fp, pred, ld_pred, N, 1, st));
     float* pal_rec = fp.rec;
@@ -1058,15 +1124,15 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     // regions) are latency-bound chains of short kernels: there the independent terms run as parallel branches.
     const bool exch = sharded && h->world > 1 && h->nccl_comm;
     const bool par = h->opt_branches != 0 && !exch && N <= h->branch_max_n && M <= h->branch_max_n && st != h->side && st != h->aux;
-    cudaStream_t s_pal = par ? h->side : st, s_aux = par ? h->aux : st;
+    cudaStream_t s_pal = par ? h->side : st, s_aux = par ? h->aux : st, s_mom = par ? h->aux2 : st;
     if (par) {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(s_pal, h->ev_fork, 0));
     }
-    RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, s_pal));
+    RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, s_pal, true));
     if (par) {
         RET(pal_finish(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
-                       S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, s_pal));
+                       S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, s_pal, pal_g));
         CK(cudaEventRecord(h->ev_join, s_pal));
     }
 
@@ -1088,24 +1154,27 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     if (par) {
         CK(cudaEventRecord(h->ev_fork2, st));
         CK(cudaStreamWaitEvent(s_aux, h->ev_fork2, 0));
+        CK(cudaStreamWaitEvent(s_mom, h->ev_fork2, 0));
     }
-    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, s_aux));
+    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, s_aux, true));
     if (par)
         RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, s_aux));
-    RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_aux));
     if (par) CK(cudaEventRecord(h->ev_join2, s_aux));
+    RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_mom, mom_part));
+    if (par) CK(cudaEventRecord(h->ev_join3, s_mom));
     if (with_content)
         RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
     if (par) {
         CK(cudaStreamWaitEvent(st, h->ev_join, 0));
         CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
+        CK(cudaStreamWaitEvent(st, h->ev_join3, 0));
     } else {
         if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
         RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, st));
         RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
-                       S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st));
+                       S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st, pal_g));
     }
     combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom,
                                              with_content ? partials + PS_SS_LOSS : nullptr, 1.f / N);
@@ -1203,21 +1272,27 @@ int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred,
         }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    // fork: every region evaluates on its own stream (own workspace), so the small launch-bound kernels of the
-    // regions overlap; join; then the scalars are averaged over regions (run_strotss.py:118-124)
-    CK(cudaEventRecord(h->ev_fork, st));
+    // The regions are evaluated one after the other on the caller's stream, each as a branch-parallel launch sequence
+    // (palette / relaxed EMD / moments / self-similarity on the region context's own forked streams).  Measured on B200
+    // (R = 3, N_r <= 1024): 0.54 ms; additionally forking the regions onto concurrent streams was slower (0.63-0.94 ms,
+    // the evaluation is bound by the launching thread, not by the GPU).  Then the scalars are averaged (run_strotss.py:118-124).
+    static const bool fork_regions = (getenv("STROTSS_GROUP_FORK") != nullptr);
+    if (fork_regions) CK(cudaEventRecord(h->ev_fork, st));
     for (int r = 0; r < R; ++r) {
         strotss_ctx* c = h->regions[r];
         c->profiling = h->profiling;
         const int n = offsets_N[r + 1] - offsets_N[r];
         const long long ro = offsets_N[r];
-        CK(cudaStreamWaitEvent(c->own, h->ev_fork, 0));
+        cudaStream_t sr = fork_regions ? c->own : st;
+        if (fork_regions) CK(cudaStreamWaitEvent(sr, h->ev_fork, 0));
         const int rc = eval_impl(c, pred + ro * ld_pred, ld_pred, content + ro * ld_content, ld_content, n, alpha,
                                  h->region_scalars + (size_t)r * STROTSS_NUM_SCALARS, grad_pred ? grad_pred + ro * ld_grad : nullptr,
-                                 ld_grad, nullptr, nullptr, true, false, c->own, 1.f / R);
+                                 ld_grad, nullptr, nullptr, true, false, sr, 1.f / R);
         if (rc != 0) { h->err = "region " + std::to_string(r) + ": " + c->err; return rc; }
-        CK(cudaEventRecord(c->ev_join2, c->own));
-        CK(cudaStreamWaitEvent(st, c->ev_join2, 0));
+        if (fork_regions) {
+            CK(cudaEventRecord(c->ev_join2, sr));
+            CK(cudaStreamWaitEvent(st, c->ev_join2, 0));
+        }
     }
     mean_scalars_kernel<<<1, 32, 0, st>>>(h->region_scalars, R, STROTSS_NUM_SCALARS, scalars, region_scalars);
     CKL();
