@@ -106,6 +106,7 @@ def main():
     ap.add_argument("--level", type=int, default=4)
     ap.add_argument("--sample", type=int, default=1024)
     ap.add_argument("--lr", type=float, default=2e-3)
+    ap.add_argument("--eager", action="store_true", help="launch every iteration op by op instead of replaying a CUDA graph")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -122,6 +123,14 @@ def main():
         return _run(args, content, style, sampling, feats, max_iter)
 
     run(3)                                       # warm-up: cuDNN autotune, workspace growth, module load
+    if not args.eager:
+        # the warm-up pass's last graph is torn down lazily at the next capture in the pool (hundreds of ms of cudaFree);
+        # pay that here, not inside the timed image
+        g = torch.cuda.CUDAGraph()
+        t = torch.zeros(8, device=dev)
+        with torch.cuda.graph(g, pool=_graph_pool()):
+            t.add_(1.0)
+        del g
     torch.cuda.synchronize()
     t_all = time.perf_counter()
     per_scale = run(args.max_iter)
@@ -133,8 +142,30 @@ def main():
         "config": {"level": args.level, "max_iter": args.max_iter, "sample_size": args.sample, "optimizer": "RMSprop(0.99, 1e-8)",
                    "vgg": "torch/cuDNN conv stack, fp32 tensors, channels_last (stand-in for the reference's TF/cuDNN path)",
                    "loss_path": "strotss_tensorflow_b200 (fused sampler + loss/grad kernels)",
+                   "launch": "eager (op by op)" if args.eager else
+                             "one CUDA graph per scale: fold + VGG fwd + sampler + loss/grad + VGG bwd + RMSprop captured once "
+                             "(capture inside the timed region), replayed every iteration; sample indices drawn on the host and "
+                             "copied into the graph's index buffer each iteration; the loss scalar is read back every iteration",
                    "warmup": "one untimed pass of 3 iterations per scale"},
         "per_scale": per_scale}))
+
+
+_POOL = None
+_POOL_KEEPER = None
+
+
+def _graph_pool():
+    """One memory pool shared by the per-scale graphs, so a later image (or the timed pass after the warm-up pass) reuses the
+    activations' memory instead of cudaMalloc-ing it again.  A trivial graph that lives for the whole process keeps the pool
+    alive while the per-scale graphs come and go."""
+    global _POOL, _POOL_KEEPER
+    if _POOL is None:
+        _POOL = torch.cuda.graph_pool_handle()
+        keep = torch.zeros(8, device="cuda")
+        _POOL_KEEPER = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(_POOL_KEEPER, pool=_POOL):
+            keep.add_(1.0)
+    return _POOL
 
 
 def _run(args, content, style, sampling, feats, max_iter):
@@ -143,6 +174,8 @@ def _run(args, content, style, sampling, feats, max_iter):
     stylized = None
     for i in range(args.level):
         scl = 2 << (5 + i)
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter()
         sc, ss = resize_long(content, scl), resize_long(style, scl)
         lap = make_laplacian(sc)
         lr = args.lr
@@ -154,37 +187,85 @@ def _run(args, content, style, sampling, feats, max_iter):
             stylized = F.interpolate(stylized, size=sc.shape[-2:], mode="bilinear", align_corners=False)
             lr = args.lr / 2
         variables = [torch.nn.Parameter(v.clone()) for v in make_pyramid(stylized)]
-        opt = torch.optim.RMSprop(variables, lr=lr, alpha=0.99, eps=1e-8)
         with torch.no_grad():
             content_feat = feats(sc)
             style_feat = feats(ss)
             loss_fn = S.StrotssLoss(sampling(style_feat), alpha)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         t_vgg = t_loss = 0.0
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         last = None
-        for it in range(max_iter):
-            opt.zero_grad(set_to_none=True)
-            ev[0].record()
+        if args.eager:
+            opt = torch.optim.RMSprop(variables, lr=lr, alpha=0.99, eps=1e-8)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for it in range(max_iter):
+                opt.zero_grad(set_to_none=True)
+                ev[0].record()
+                img = fold_pyramid(variables)
+                pred = feats(img)
+                ev[1].record()
+                c_feat, p_feat = sampling.bilinear(content_feat, pred)
+                loss = loss_fn(c_feat, p_feat)
+                ev[2].record()
+                loss.backward()
+                opt.step()
+                ev[3].record()
+                last = float(loss.item())       # the reference formats three scalars per iteration (run_strotss.py:150-152)
+                t_vgg += ev[0].elapsed_time(ev[1])
+                t_loss += ev[1].elapsed_time(ev[2])
+        else:
+            # RMSprop(rho 0.99, eps 1e-8) state (run_strotss.py:63); the update is part of the captured graph
+            sq = [torch.zeros_like(v) for v in variables]
+            idx = sampling._make_indices(content_feat[0], True)
+            static_idx = idx.clone()
+
+            def iteration():
+                img = fold_pyramid(variables)
+                pred = feats(img)
+                c_feat = sampling._sample(content_feat, static_idx, True)
+                p_feat = sampling._sample(pred, static_idx, True)
+                loss = loss_fn(c_feat, p_feat)
+                grads = torch.autograd.grad(loss, variables)
+                with torch.no_grad():
+                    torch._foreach_mul_(sq, 0.99)
+                    torch._foreach_addcmul_(sq, grads, grads, value=0.01)
+                    den = torch._foreach_sqrt(sq)
+                    torch._foreach_add_(den, 1e-8)
+                    torch._foreach_addcdiv_(variables, grads, den, value=-lr)
+                return loss
+
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            # one eager forward + backward without an update, so that cuDNN plans/workspaces and the library workspace
+            # exist before capture (no device allocation is allowed inside a capture)
             img = fold_pyramid(variables)
             pred = feats(img)
-            ev[1].record()
-            c_feat, p_feat = sampling.bilinear(content_feat, pred)
-            loss = loss_fn(c_feat, p_feat)
-            ev[2].record()
-            loss.backward()
-            opt.step()
-            ev[3].record()
-            last = float(loss.item())           # the reference formats three scalars per iteration (run_strotss.py:150-152)
-            t_vgg += ev[0].elapsed_time(ev[1])
-            t_loss += ev[1].elapsed_time(ev[2])
+            l0 = loss_fn(sampling._sample(content_feat, static_idx, True), sampling._sample(pred, static_idx, True))
+            torch.autograd.grad(l0, variables)
+            del img, pred, l0
+            torch.cuda.synchronize()
+            t_warm = time.perf_counter() - t0
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=_graph_pool()):
+                static_loss = iteration()
+            torch.cuda.synchronize()
+            t_capture = time.perf_counter() - t0
+            base_cpu = torch.empty(content_feat[0].shape)          # shape carrier: indices are drawn on the host
+            nxt = None
+            for it in range(max_iter):
+                if nxt is not None:
+                    static_idx.copy_(nxt, non_blocking=True)
+                graph.replay()
+                nxt = sampling._make_indices(base_cpu, True).pin_memory()      # next iteration's draw, under the GPU work
+                last = float(static_loss.item())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         with torch.no_grad():
             stylized = fold_pyramid(variables).detach()
         per_scale.append({"scale": scl, "content_hw": list(sc.shape[-2:]), "style_hw": list(ss.shape[-2:]), "alpha": alpha,
-                          "seconds": dt, "ms_per_iter": dt / max_iter * 1e3,
+                          "seconds": dt, "ms_per_iter": dt / max_iter * 1e3, "setup_seconds": t0 - t_setup,
+                          "capture_seconds": (t_capture - t_warm if not args.eager else 0.0),
+                          "eager_first_iteration_seconds": (t_warm if not args.eager else 0.0),
                           "fold_vgg_fwd_ms_per_iter": t_vgg / max_iter,
                           "sample_loss_fwd_ms_per_iter": t_loss / max_iter, "last_loss": last})
         alpha /= 2.0

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from .losses import self_similarity
-from .runtime import Handle, reshape_2d
+from .runtime import acquire_handle, release_handle, reshape_2d
 
 
 class ContentLoss(torch.nn.Module):
@@ -43,9 +43,12 @@ class StyleLoss(torch.nn.Module):
         self.target = reshape_2d(target)
         self.alpha = float(alpha)
         self.inv_alpha = 1 / max(alpha, 1)
-        self.handle = Handle(self.target.device)
+        self.handle = acquire_handle(self.target.device)
         self.handle.set_style_target(self.target)
         self.last_scalars = None
+
+    def __del__(self):
+        release_handle(getattr(self, "handle", None))
 
     def forward(self, prediction: torch.Tensor) -> torch.Tensor:
         return _StyleLossFn.apply(reshape_2d(prediction), self)
@@ -77,9 +80,12 @@ class StrotssLoss(torch.nn.Module):
         super().__init__()
         self.alpha = float(alpha)
         self.style_features = reshape_2d(target).detach()
-        self.handle = Handle(self.style_features.device)
+        self.handle = acquire_handle(self.style_features.device)
         self.handle.set_style_target(self.style_features)
         self.last_scalars = None
+
+    def __del__(self):
+        release_handle(getattr(self, "handle", None))
 
     def forward(self, content: torch.Tensor, prediction: torch.Tensor) -> torch.Tensor:
         return _TotalFn.apply(reshape_2d(prediction), reshape_2d(content), self)
@@ -118,10 +124,13 @@ class MaskedStrotssLoss(torch.nn.Module):
         super().__init__()
         self.alpha = float(alpha)
         self.targets = [reshape_2d(t).detach() for t in targets]
-        self.handle = Handle(self.targets[0].device)
+        self.handle = acquire_handle(self.targets[0].device)
         self.handle.set_style_targets_grouped(self.targets)
         self.last_scalars = None
         self.last_region_scalars = None
+
+    def __del__(self):
+        release_handle(getattr(self, "handle", None))
 
     def forward(self, contents, predictions) -> torch.Tensor:
         R = len(self.targets)

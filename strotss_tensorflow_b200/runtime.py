@@ -279,6 +279,27 @@ class Handle:
 
 
 _shared: Dict[int, Handle] = {}
+_pool: Dict[int, list] = {}
+
+
+def acquire_handle(device: torch.device) -> Handle:
+    """A handle for a loss module.  The reference builds a new StyleLoss per scale (run_strotss.py:100,128); handles
+    released by collected modules are reused so that their device workspace is not re-allocated every scale."""
+    if device.type != "cuda":
+        raise RuntimeError(f"tensor is on {device}: strotss_tensorflow_b200 runs on CUDA sm_100 only (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    free = _pool.get(idx)
+    if free:
+        return free.pop()
+    return Handle(torch.device("cuda", idx))
+
+
+def release_handle(h: Optional[Handle]) -> None:
+    if h is None or getattr(h, "_h", None) is None or _pool is None:
+        return
+    if h.world != 1:            # attached to a communicator: not reusable by an unrelated module
+        return
+    _pool.setdefault(h.index, []).append(h)
 
 
 def shared_handle(device: torch.device) -> Handle:
