@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--eps", type=float, default=1.0, help="pred = content + eps*noise (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--samples", type=int, default=0,
+                    help="override the sample count N = M of the workload (SURVEY 8d sweep: 1024 ... 16384)")
     ap.add_argument("--graph", action="store_true",
                     help="replay the evaluation from a CUDA graph captured around the C-ABI call (launch-bound small workloads)")
     ap.add_argument("--mode", default="replicas", choices=["rowshard", "replicas"],
@@ -218,6 +220,8 @@ def main():
                          "In replicas mode the row-sharded latency is measured as well and reported under 'rowshard'.")
     args = ap.parse_args()
     N, M = WORKLOADS[args.workload]
+    if args.samples > 0:
+        N = M = args.samples
 
     if args.impl == "reference":
         run_reference(args, N, M)
@@ -390,7 +394,7 @@ def main():
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
             # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 8 launches of one step of this workload
             # (profiles/r01_v7_ss1_pair_ncu_raw.csv); algorithmic: operands 220 + 990 MB, P panel 302 MB
-            "traffic": 1.7148e9 if (world == 1 and args.workload == "large") else None,
+            "traffic": 1.7148e9 if (world == 1 and N == 16384) else None,
             "traffic_unit": "bytes per step (all launches of the kernel)", "algorithmic_bytes": 1.512e9,
             "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": ss1_n / args.steps if ss1_n else None,
@@ -439,8 +443,16 @@ def main():
         times = cpu_eval_seconds(n_s, reps, 0, threads)
         t = sum(times) / len(times)
         scale = f_ref(N, M) / f_ref(n_s, n_s)
+        # the reference pins TensorFlow to one intra-op / one inter-op thread (nn/rand.py:16-17): time that setting too,
+        # on a smaller sample (N = M = 1024, one evaluation)
+        n_1 = min(N, 1024)
+        t_1 = cpu_eval_seconds(n_1, 1, 1, 1)[0]
+        one_thread = 1.0 / (t_1 * f_ref(N, M) / f_ref(n_1, n_1))
         line["cpu_baseline"] = {
             "value": 1.0 / (t * scale), "unit": "evals/s", "cores": threads, "kind": "port",
+            "value_1_thread": one_thread,
+            "sample_1_thread": f"same port pinned to 1 thread (the reference's own setting, nn/rand.py:16-17), one evaluation at "
+                               f"N=M={n_1} ({t_1:.2f} s), scaled by the reference FLOP ratio",
             "sample": f"torch-CPU port of the reference op sequence (fp32, materialised matrices, autograd), {reps} evaluations at "
                       f"N=M={n_s} ({t:.2f} s each), scaled to N=M={N} by the reference FLOP ratio {scale:.2f}"}
     print(json.dumps(line), flush=True)

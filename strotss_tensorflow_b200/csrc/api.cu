@@ -577,8 +577,30 @@ int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int
         CK(cudaMemsetAsync(ps.colbest, 0, sizeof(unsigned long long) * N, st));
     }
     // target rows (all) against this rank's prediction rows; this rank's prediction rows against all target rows
-    RET(pal_launch(h, asrec, M, bsrec + (size_t)sh.r0 * 8, sh.n(), sh.r0, mode, ps.rowbest, st));
-    RET(pal_launch(h, bsrec + (size_t)sh.r0 * 8, sh.n(), asrec, M, 0, mode, ps.colbest + sh.r0, st));
+    static const bool two_pass = (getenv("STROTSS_PAL_TWO_PASS") != nullptr);
+    if (two_pass) {
+        RET(pal_launch(h, asrec, M, bsrec + (size_t)sh.r0 * 8, sh.n(), sh.r0, mode, ps.rowbest, st));
+        RET(pal_launch(h, bsrec + (size_t)sh.r0 * 8, sh.n(), asrec, M, 0, mode, ps.colbest + sh.r0, st));
+    } else if (sh.n() > 0) {
+        // one pass: queries = all target rows (row minima), keys = this rank's prediction rows (column minima)
+        const int nq = M, nk = sh.n();
+        const int qblocks = (nq + kPalThreads * kPalQT - 1) / (kPalThreads * kPalQT);
+        int ks = (4 * h->num_sms + qblocks - 1) / qblocks;
+        const int maxks = (nk + kPalKeyTile - 1) / kPalKeyTile;
+        if (ks > maxks) ks = maxks;
+        if (ks < 1) ks = 1;
+        const int kchunk = round_up((nk + ks - 1) / ks, kPalKeyTile);
+        ks = (nk + kchunk - 1) / kchunk;
+        const dim3 grid(qblocks, ks);
+        const float* keys = bsrec + (size_t)sh.r0 * 8;
+        if (mode == STROTSS_DIST_BOTH)
+            pal_min2_kernel<2><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
+        else if (mode == STROTSS_DIST_L2)
+            pal_min2_kernel<1><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
+        else
+            pal_min2_kernel<0><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
+        CKL();
+    }
     best_partial_kernel<<<1, 1024, 0, st>>>(ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
     CKL();
     return 0;

@@ -551,6 +551,74 @@ __global__ void __launch_bounds__(kPalThreads) pal_min_kernel(const float* __res
     }
 }
 
+// Both directions of the same cost matrix in ONE pass: every (query, key) cost is evaluated once and feeds the
+// per-thread minimum over keys (qbest, as above) and the minimum over queries of each key (kbest): minimum over the
+// thread's own queries, then redux.sync over the warp, one packed atomicMax per (warp, key).  Ties -> lowest index,
+// exactly as two separate passes would resolve them.
+template <int mode>
+__global__ void __launch_bounds__(kPalThreads) pal_min2_kernel(const float* __restrict__ qrec, int nq, const float* __restrict__ krec, int nk,
+                                                               int kchunk, int kidx_base,
+                                                               unsigned long long* __restrict__ qbest,
+                                                               unsigned long long* __restrict__ kbest) {
+    __shared__ float4 sk[kPalKeyTile * 2];
+    float a[kPalQT][7];
+    float one[kPalQT];
+    float bv[kPalQT];
+    int bi[kPalQT];
+    const int qbase = blockIdx.x * (kPalThreads * kPalQT) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int t = 0; t < kPalQT; ++t) {
+        const int q = qbase + t * kPalThreads;
+        const bool valid = q < nq;
+        const float4* src = reinterpret_cast<const float4*>(qrec + static_cast<long long>(valid ? q : 0) * 8);
+        const float4 v0 = src[0], v1 = src[1];
+        a[t][0] = v0.x; a[t][1] = v0.y; a[t][2] = v0.z; a[t][3] = v0.w;
+        a[t][4] = v1.x; a[t][5] = v1.y;
+        // a query beyond nq must never win a key's minimum: its costs are +inf in every mode
+        a[t][6] = valid ? v1.z : INFINITY;
+        one[t] = valid ? 1.f : INFINITY;
+        bv[t] = INFINITY; bi[t] = 0;
+    }
+    const int k0 = blockIdx.y * kchunk, k1 = min(nk, k0 + kchunk);
+    for (int kb = k0; kb < k1; kb += kPalKeyTile) {
+        const int cnt = min(kPalKeyTile, k1 - kb);
+        __syncthreads();
+        const float4* ksrc = reinterpret_cast<const float4*>(krec + static_cast<long long>(kb) * 8);
+        for (int e = threadIdx.x; e < cnt * 2; e += kPalThreads) sk[e] = ksrc[e];
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const float4 b0 = sk[2 * k], b1 = sk[2 * k + 1];
+            float cm = INFINITY; int tm = 0;
+#pragma unroll
+            for (int t = 0; t < kPalQT; ++t) {
+                float c = 0.f;
+                if (mode != 1) c = fmaf(-a[t][2], b0.z, fmaf(-a[t][1], b0.y, fmaf(-a[t][0], b0.x, one[t])));
+                if (mode != 0) {
+                    const float m = fmaf(-a[t][5], b1.y, fmaf(-a[t][4], b1.x, fmaf(-a[t][3], b0.w, a[t][6] + b1.z)));
+                    c += fast_sqrt(fmaxf(m, kL2DClamp * (1.f / 3.f)));
+                }
+                if (c < bv[t]) { bv[t] = c; bi[t] = kb + k; }
+                if (c < cm) { cm = c; tm = t; }               // ties keep the lower t == the lower query index
+            }
+            const uint32_t ord = f2ord(-cm);
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, ord);
+            const uint32_t cand = (ord == wmax) ? static_cast<uint32_t>(qbase + tm * kPalThreads) : 0xffffffffu;
+            const uint32_t qmin = __reduce_min_sync(0xffffffffu, cand);
+            if (lane == 0 && qmin < static_cast<uint32_t>(nq))
+                atomicMax(kbest + kb + k, (static_cast<unsigned long long>(wmax) << 32) | static_cast<unsigned long long>(~qmin));
+        }
+    }
+    if (k1 > k0) {
+#pragma unroll
+        for (int t = 0; t < kPalQT; ++t) {
+            const int q = qbase + t * kPalThreads;
+            if (q < nq) atomicMax(qbest + q, pack_best(-bv[t], static_cast<uint32_t>(kidx_base + bi[t])));
+        }
+    }
+}
+
 // Sparse backward of the 3-channel relaxed EMD w.r.t. the prediction's RGB (through the YUV matrix).
 // gpal[j - r0][0..2] += gradient for prediction rows owned by this rank; one thread per selected pair.
 __global__ void pal_backward_kernel(const unsigned long long* __restrict__ rowbest, int M,
