@@ -153,7 +153,8 @@ def run_reference(args, N, M):
         "impl": "reference", "metric": f"loss+grad evals/sec at N=M={N}, D={D_FEAT}", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA}", "sampled_as": f"N=M={n_s}"},
+        "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}"
+                   if N > 1024 else f"default sample count N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}", "sampled_as": f"N=M={n_s}"},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -916,7 +916,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
-        ss_rows_kernel<<<(sh.n() + 255) / 256, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
+        ss_rows_kernel<<<(sh.n() + 31) / 32, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
                                                              sym ? 1 : 0, panel, (panel / ss_bn) * ss_split, rcol_part, (panel / BM) * 4);
         CKL();
     }

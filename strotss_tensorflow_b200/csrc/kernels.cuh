@@ -334,26 +334,37 @@ __global__ void __launch_bounds__(256) ss_vectors_kernel(const float* __restrict
 // r_i = (1/N) sum of the row-form partials (+ in symmetric mode the column-form partials written by the
 // panels left of row i's panel);  coef_i = r_i u_i^2 [s_i >= clamp];  rowloss_i = sum of loss partials.
 // In symmetric mode a panel only wrote the slots of column tiles >= its first row.
-__global__ void ss_rows_kernel(const float* __restrict__ loss_part, const float* __restrict__ r_part, int nslots, int N,
+// Block = 32 rows x 8 partial-sum groups (fixed interleaved order, then a fixed tree: deterministic).
+__global__ void __launch_bounds__(256) ss_rows_kernel(const float* __restrict__ loss_part, const float* __restrict__ r_part, int nslots, int N,
                                int r0, int r1, const float* __restrict__ u, const float* __restrict__ sclamp,
                                float* __restrict__ coef, float* __restrict__ rowloss,
                                int sym, int panel_rows, int slots_per_panel, const float* __restrict__ rcol_part,
                                int colparts_per_panel) {
-    const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r1) return;
-    const int pi = sym ? i / panel_rows : 0;
+    __shared__ float sl[8][33], sr[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int i = r0 + blockIdx.x * 32 + c;
     float l = 0.f, r = 0.f;
-    for (int t = pi * slots_per_panel * sym; t < nslots; ++t) {
-        l += loss_part[static_cast<long long>(t) * N + i];
-        r += r_part[static_cast<long long>(t) * N + i];
+    if (i < r1) {
+        const int pi = sym ? i / panel_rows : 0;
+        for (int t = pi * slots_per_panel * sym + g; t < nslots; t += 8) {
+            l += loss_part[static_cast<long long>(t) * N + i];
+            r += r_part[static_cast<long long>(t) * N + i];
+        }
+        if (sym) {
+            const int nb = pi * colparts_per_panel;
+            for (int b = g; b < nb; b += 8) r += rcol_part[static_cast<long long>(b) * N + i];
+        }
     }
-    if (sym) {
-        const int nb = pi * colparts_per_panel;
-        for (int b = 0; b < nb; ++b) r += rcol_part[static_cast<long long>(b) * N + i];
+    sl[g][c] = l; sr[g][c] = r;
+    __syncthreads();
+    if (g == 0 && i < r1) {
+        float lt = 0.f, rt = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { lt += sl[k][c]; rt += sr[k][c]; }
+        rowloss[i] = lt;
+        const float ui = u[i];
+        coef[i] = (rt / static_cast<float>(N)) * ui * ui * sclamp[i];
     }
-    rowloss[i] = l;
-    const float ui = u[i];
-    coef[i] = (r / static_cast<float>(N)) * ui * ui * sclamp[i];
 }
 
 // out[slot] = scale * sum_i in[i]      (single block, fixed order)
