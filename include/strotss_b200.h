@@ -177,6 +177,28 @@ int strotss_sample_backward(strotss_handle h, int nmaps, float* const* grad_maps
                             const int* cs, const float* indices, int n, int bilinear, const float* grad_out,
                             long long ld, void* stream);
 
+/* ---- pixel-side step (SURVEY 8f "next #3"): images are NHWC fp32 with batch 1, element (y, x, ch) at (y*w + x)*c + ch ----
+ *
+ * tf.image.resize(x, (oh, ow)) with the default bilinear method (TF2: half-pixel centres, no antialiasing), as used by
+ * utils.resize / utils.resize_like (nn/utils.py:32-41) and by the pyramid functions below. */
+int strotss_resize_bilinear(strotss_handle h, const float* src, int sh, int sw, int c, float* out, int oh, int ow, void* stream);
+/* make_laplacian(x, return_downscale=True) (nn/strotss_utils.py:139-146): down = resize(x, max(hw//2, 1)) (device buffer of
+ * max(h//2,1) x max(w//2,1) x c), pyr = x - resize(down, hw).  make_laplacian_pyramid (:149-156) is `levels` such calls. */
+int strotss_make_laplacian(strotss_handle h, const float* x, int hh, int ww, int c, float* pyr, float* down, void* stream);
+/* fold_laplacian_pyramid(xs) (nn/strotss_utils.py:159-163): ret = xs[-1]; for x in reversed(xs[:-1]): ret = x + resize(ret,
+ * shape(x)).  xs / hs / ws are HOST arrays over the nlev (<= 8) levels, finest first; out is hs[0] x ws[0] x c. */
+int strotss_pyramid_fold(strotss_handle h, int nlev, const float* const* xs, const int* hs, const int* ws, int c, float* out,
+                         void* stream);
+/* What tape.gradient does for the fold (run_strotss.py:122,141): grad_xs[k] (device, shaped like xs[k]) = d loss / d xs[k]
+ * given grad_out = d loss / d image.  Deterministic (gather form of the transposed resize, no atomics). */
+int strotss_pyramid_fold_backward(strotss_handle h, int nlev, const int* hs, const int* ws, int c, const float* grad_out,
+                                  float* const* grad_xs, void* stream);
+/* opt.apply_gradients(zip(grads, st_variables)) with tf.keras.optimizers.RMSprop(rho, epsilon, learning_rate)
+ * (run_strotss.py:63,148; momentum 0, not centred): rms = rho*rms + (1-rho)*g^2; var -= lr*g/(sqrt(rms) + eps), for all
+ * nvars (<= 8) variables in one launch.  vars / rms / grads / counts are HOST arrays; counts = elements per variable. */
+int strotss_rmsprop_step(strotss_handle h, int nvars, float* const* vars, float* const* rms, const float* const* grads,
+                         const long long* counts, float lr, float rho, float eps, void* stream);
+
 /* Test hook: C[m][n] = alpha * sum_k bf16(A[m][k]) * bf16(B[n][k]) through the tcgen05 GEMM core
  * (fp32 in, fp32 out; tile_n is 128 or 256).  Not part of the reference interface. */
 int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha,

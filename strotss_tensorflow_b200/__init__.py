@@ -9,7 +9,9 @@ from .losses import dist_metrics, moment_matching, relaxed_emd, reshape_2d, self
 from .modules import ContentLoss, MaskedStrotssLoss, StrotssLoss, StyleLoss
 from .runtime import Handle, shared_handle
 from .sampling import Sampling
-from .strotss_utils import convert_rgb_to_yuv
+from .strotss_utils import (RMSprop, convert_rgb_to_yuv, fold_laplacian_pyramid, make_laplacian, make_laplacian_pyramid,
+                            resize, resize_like)
 
 __all__ = ["relaxed_emd", "moment_matching", "self_similarity", "dist_metrics", "reshape_2d", "convert_rgb_to_yuv",
-           "ContentLoss", "StyleLoss", "StrotssLoss", "MaskedStrotssLoss", "Handle", "shared_handle", "Sampling"]
+           "ContentLoss", "StyleLoss", "StrotssLoss", "MaskedStrotssLoss", "Handle", "shared_handle", "Sampling", "fold_laplacian_pyramid", "make_laplacian",
+           "make_laplacian_pyramid", "resize", "resize_like", "RMSprop"]

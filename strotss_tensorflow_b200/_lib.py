@@ -46,6 +46,11 @@ SIGNATURES = {
     "strotss_convert_rgb_to_yuv": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "strotss_sample": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp, _ll, _vp]),
     "strotss_sample_backward": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp, _ll, _vp]),
+    "strotss_resize_bilinear": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "strotss_make_laplacian": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "strotss_pyramid_fold": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp]),
+    "strotss_pyramid_fold_backward": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), _i, _vp, C.POINTER(_vp), _vp]),
+    "strotss_rmsprop_step": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _f, _f, _f, _vp]),
     "strotss_debug_gemm": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
     "strotss_debug_gemm_ta": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
 }

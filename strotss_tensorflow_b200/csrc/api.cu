@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "gemm2_core.cuh"
 #include "ss1_kernel.cuh"
+#include "pixel_kernels.cuh"
 #include <cstdlib>
 
 using namespace sb;
@@ -766,7 +767,8 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     out.ss2 = nullptr; out.ld = 0;
     const int npanels = sh.n() > 0 ? (sh.n() + panel - 1) / panel : 0;
     // two-stream pipelining: stage 2 of panel p (stream `aux`) under stage 1 of panel p+1 (caller's stream)
-    const bool overlap = want_grad && npanels > 1 && h->opt_overlap != 0 && st != h->aux && N > h->branch_max_n;
+    const bool overlap = want_grad && npanels > 1 && h->opt_overlap != 0 && st != h->aux &&
+                         (h->opt_branches == 0 || N > h->branch_max_n);      // `aux` carries a branch otherwise
     if (want_grad && sh.n() > 0) {
         RET(ensure(h, "ss.P", (size_t)panel * np, &Pbuf[0]));
         if (overlap) RET(ensure(h, "ss.P1", (size_t)panel * np, &Pbuf[1]));
@@ -1606,6 +1608,106 @@ int strotss_sample_backward(strotss_handle h, int nmaps, float* const* grad_maps
     for (int k = 0; k < nmaps; ++k) m.gptr[k] = grad_maps[k];
     CK(cudaSetDevice(h->device));
     sampler_bwd_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, indices, n, bilinear ? 1 : 0, grad_out, ld);
+    CKL();
+    return 0;
+}
+
+
+// ---- pixel-side step -----------------------------------------------------
+static int elem_grid(const strotss_ctx* h, long long total) {
+    long long b = (total + 255) / 256;
+    const long long cap = 8ll * h->num_sms;
+    if (b > cap) b = cap;
+    return static_cast<int>(b < 1 ? 1 : b);
+}
+
+int strotss_resize_bilinear(strotss_handle h, const float* src, int sh, int sw, int c, float* out, int oh, int ow, void* stream) {
+    RET(check_handle(h));
+    if (!src || !out || sh <= 0 || sw <= 0 || c <= 0 || oh <= 0 || ow <= 0) { h->err = "resize_bilinear: bad argument"; return STROTSS_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    resize_add_kernel<<<elem_grid(h, (long long)oh * ow * c), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, sh, sw, c, nullptr, 1.f, out, oh, ow);
+    CKL();
+    return 0;
+}
+
+int strotss_make_laplacian(strotss_handle h, const float* x, int hh, int ww, int c, float* pyr, float* down, void* stream) {
+    RET(check_handle(h));
+    if (!x || !pyr || !down || hh <= 0 || ww <= 0 || c <= 0) { h->err = "make_laplacian: bad argument"; return STROTSS_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    const int hd = hh / 2 > 1 ? hh / 2 : 1, wd = ww / 2 > 1 ? ww / 2 : 1;          // tf.maximum(hw // 2, 1)
+    resize_add_kernel<<<elem_grid(h, (long long)hd * wd * c), 256, 0, st>>>(x, hh, ww, c, nullptr, 1.f, down, hd, wd);
+    CKL();
+    resize_add_kernel<<<elem_grid(h, (long long)hh * ww * c), 256, 0, st>>>(down, hd, wd, c, x, -1.f, pyr, hh, ww);
+    CKL();
+    return 0;
+}
+
+static int pyramid_check(strotss_handle h, const char* who, int nlev, const int* hs, const int* ws, int c) {
+    if (nlev < 1 || nlev > kMaxVars || !hs || !ws || c <= 0) { h->err = std::string(who) + ": bad argument"; return STROTSS_ERR_ARG; }
+    for (int k = 0; k < nlev; ++k)
+        if (hs[k] <= 0 || ws[k] <= 0) { h->err = std::string(who) + ": bad level shape"; return STROTSS_ERR_ARG; }
+    return 0;
+}
+
+int strotss_pyramid_fold(strotss_handle h, int nlev, const float* const* xs, const int* hs, const int* ws, int c, float* out,
+                         void* stream) {
+    RET(check_handle(h));
+    RET(pyramid_check(h, "pyramid_fold", nlev, hs, ws, c));
+    if (!xs || !out) { h->err = "pyramid_fold: bad argument"; return STROTSS_ERR_ARG; }
+    for (int k = 0; k < nlev; ++k) if (!xs[k]) { h->err = "pyramid_fold: null level"; return STROTSS_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    if (nlev == 1) {
+        CK(cudaMemcpyAsync(out, xs[0], sizeof(float) * (size_t)hs[0] * ws[0] * c, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    // ret = xs[-1]; for x in reversed(xs[:-1]): ret = x + resize(ret, shape(x))     (nn/strotss_utils.py:159-163)
+    const float* ret = xs[nlev - 1];
+    int rh = hs[nlev - 1], rw = ws[nlev - 1];
+    for (int k = nlev - 2; k >= 0; --k) {
+        float* dst = out;
+        if (k > 0) RET(ensure(h, ("fold.ret" + std::to_string(k)).c_str(), (size_t)hs[k] * ws[k] * c, &dst));
+        resize_add_kernel<<<elem_grid(h, (long long)hs[k] * ws[k] * c), 256, 0, st>>>(ret, rh, rw, c, xs[k], 1.f, dst, hs[k], ws[k]);
+        CKL();
+        ret = dst; rh = hs[k]; rw = ws[k];
+    }
+    return 0;
+}
+
+int strotss_pyramid_fold_backward(strotss_handle h, int nlev, const int* hs, const int* ws, int c, const float* grad_out,
+                                  float* const* grad_xs, void* stream) {
+    RET(check_handle(h));
+    RET(pyramid_check(h, "pyramid_fold_backward", nlev, hs, ws, c));
+    if (!grad_out || !grad_xs) { h->err = "pyramid_fold_backward: bad argument"; return STROTSS_ERR_ARG; }
+    for (int k = 0; k < nlev; ++k) if (!grad_xs[k]) { h->err = "pyramid_fold_backward: null level"; return STROTSS_ERR_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
+    // d/dx_k = gradient of the running image at level k; it reaches level k+1 through the transposed resize
+    if (grad_xs[0] != grad_out)
+        CK(cudaMemcpyAsync(grad_xs[0], grad_out, sizeof(float) * (size_t)hs[0] * ws[0] * c, cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k + 1 < nlev; ++k) {
+        resize_transpose_kernel<<<elem_grid(h, (long long)hs[k + 1] * ws[k + 1] * c), 256, 0, st>>>(grad_xs[k], hs[k], ws[k], c,
+                                                                                                  grad_xs[k + 1], hs[k + 1], ws[k + 1], 0);
+        CKL();
+    }
+    return 0;
+}
+
+int strotss_rmsprop_step(strotss_handle h, int nvars, float* const* vars, float* const* rms, const float* const* grads,
+                         const long long* counts, float lr, float rho, float eps, void* stream) {
+    RET(check_handle(h));
+    if (nvars < 1 || nvars > kMaxVars || !vars || !rms || !grads || !counts) { h->err = "rmsprop_step: bad argument"; return STROTSS_ERR_ARG; }
+    RmspropArgs a{};
+    long long tot = 0;
+    for (int k = 0; k < nvars; ++k) {
+        if (!vars[k] || !rms[k] || !grads[k] || counts[k] <= 0) { h->err = "rmsprop_step: bad variable"; return STROTSS_ERR_ARG; }
+        a.var[k] = vars[k]; a.rms[k] = rms[k]; a.grad[k] = grads[k];
+        tot += counts[k]; a.end[k] = tot;
+    }
+    a.nvars = nvars; a.lr = lr; a.rho = rho; a.eps = eps;
+    CK(cudaSetDevice(h->device));
+    rmsprop_kernel<<<elem_grid(h, tot), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     CKL();
     return 0;
 }

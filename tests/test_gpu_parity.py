@@ -423,10 +423,14 @@ print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.no
 
 
 @pytest.mark.parametrize("env", [{"STROTSS_NO_PAIR": "1"}, {"STROTSS_SS1_GENERIC": "1"},
-                                 {"STROTSS_NO_PAIR": "1", "STROTSS_SS1_GENERIC": "1"}])
+                                 {"STROTSS_NO_PAIR": "1", "STROTSS_SS1_GENERIC": "1"},
+                                 {"STROTSS_BRANCHES": "0"}, {"STROTSS_PAL_TWO_PASS": "1"},
+                                 {"STROTSS_BRANCHES": "0", "STROTSS_OVERLAP": "1"}])
 def test_alternative_kernel_paths(cuda_device, env):
-    """The single-CTA GEMM kernels (STROTSS_NO_PAIR) and the generic stage-1 epilogue (STROTSS_SS1_GENERIC) stay
-    selectable for A/B measurements; they must give the same answers.  The switches are read once per process."""
+    """The single-CTA GEMM kernels (STROTSS_NO_PAIR), the generic stage-1 epilogue (STROTSS_SS1_GENERIC), the
+    single-stream launch order (STROTSS_BRANCHES=0), the two-pass palette search and the two-stream stage-1/stage-2
+    pipelining (STROTSS_OVERLAP=1) stay selectable for A/B measurements; they must give the same answers.  The
+    switches are read once per process."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
