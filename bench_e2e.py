@@ -7,7 +7,8 @@ What is measured and what is not:
   * loss path (sampler, loss + gradient): this repo's CUDA kernels -- the thing being built;
   * VGG16 forward/backward: torch/cuDNN with RANDOM weights (the reference's weights are fetched from a URL and are
     not available offline) -- a stand-in for "the reference's TF/cuDNN path", timing only;
-  * pyramid fold, RMSprop on the six Laplacian-pyramid variables: torch eager ops.
+  * pyramid fold (+ backward) and RMSprop on the six Laplacian-pyramid variables: this repo's kernels in
+    the default graph mode, torch ops with --eager.
 The stylised image is therefore meaningless; only the time is reported.  One JSON line on stdout.
 
     python bench_e2e.py [--max_iter 200] [--level 4] [--sample 1024]
@@ -93,7 +94,7 @@ def make_pyramid(x, levels=5):                  # nn/strotss_utils.py:149-156
     return out
 
 
-def fold_pyramid(xs):                           # nn/strotss_utils.py:159-163
+def fold_pyramid_torch(xs):                     # nn/strotss_utils.py:159-163 (torch ops, --eager)
     ret = xs[-1]
     for x in reversed(xs[:-1]):
         ret = x + F.interpolate(ret, size=x.shape[-2:], mode="bilinear", align_corners=False)
@@ -120,7 +121,7 @@ def main():
         return [nhwc(img)] + [nhwc(f) for f in vgg(img.contiguous(memory_format=torch.channels_last))]
 
     def run(max_iter):
-        return _run(args, content, style, sampling, feats, max_iter)
+        return _run(args, content, style, sampling, feats, vgg, max_iter)
 
     run(3)                                       # warm-up: cuDNN autotune, workspace growth, module load
     if not args.eager:
@@ -146,6 +147,7 @@ def main():
                              "one CUDA graph per scale: fold + VGG fwd + sampler + loss/grad + VGG bwd + RMSprop captured once "
                              "(capture inside the timed region), replayed every iteration; sample indices drawn on the host and "
                              "copied into the graph's index buffer each iteration; the loss scalar is read back every iteration",
+                   "pixel_side": "torch ops" if args.eager else "strotss_pyramid_fold / _fold_backward / strotss_rmsprop_step (this repo)",
                    "warmup": "one untimed pass of 3 iterations per scale"},
         "per_scale": per_scale}))
 
@@ -168,7 +170,7 @@ def _graph_pool():
     return _POOL
 
 
-def _run(args, content, style, sampling, feats, max_iter):
+def _run(args, content, style, sampling, feats_nchw, vgg_feats, max_iter):
     alpha = 16.0
     per_scale = []
     stylized = None
@@ -187,6 +189,7 @@ def _run(args, content, style, sampling, feats, max_iter):
             stylized = F.interpolate(stylized, size=sc.shape[-2:], mode="bilinear", align_corners=False)
             lr = args.lr / 2
         variables = [torch.nn.Parameter(v.clone()) for v in make_pyramid(stylized)]
+        feats, fold_pyramid = feats_nchw, fold_pyramid_torch
         with torch.no_grad():
             content_feat = feats(sc)
             style_feat = feats(ss)
@@ -214,10 +217,19 @@ def _run(args, content, style, sampling, feats, max_iter):
                 t_vgg += ev[0].elapsed_time(ev[1])
                 t_loss += ev[1].elapsed_time(ev[2])
         else:
-            # RMSprop(rho 0.99, eps 1e-8) state (run_strotss.py:63); the update is part of the captured graph
-            sq = [torch.zeros_like(v) for v in variables]
+            # pixel side on the library kernels: NHWC variables, fused fold (+ backward), one-launch RMSprop(0.99, 1e-8)
+            # (run_strotss.py:63,89,134,148); the update is part of the captured graph
+            variables = [v.clone().requires_grad_(True) for v in S.make_laplacian_pyramid(nhwc(stylized), 5)]
+            opt = S.RMSprop(rho=0.99, epsilon=1e-8, learning_rate=lr)
+            opt.build(variables)
             idx = sampling._make_indices(content_feat[0], True)
             static_idx = idx.clone()
+
+            def fold_pyramid(vs):
+                return S.fold_laplacian_pyramid(vs)
+
+            def feats(img):                      # img: (1, h, w, 3); its NCHW view is channels_last already
+                return [img] + [nhwc(f) for f in vgg_feats(img.permute(0, 3, 1, 2))]
 
             def iteration():
                 img = fold_pyramid(variables)
@@ -226,12 +238,7 @@ def _run(args, content, style, sampling, feats, max_iter):
                 p_feat = sampling._sample(pred, static_idx, True)
                 loss = loss_fn(c_feat, p_feat)
                 grads = torch.autograd.grad(loss, variables)
-                with torch.no_grad():
-                    torch._foreach_mul_(sq, 0.99)
-                    torch._foreach_addcmul_(sq, grads, grads, value=0.01)
-                    den = torch._foreach_sqrt(sq)
-                    torch._foreach_add_(den, 1e-8)
-                    torch._foreach_addcdiv_(variables, grads, den, value=-lr)
+                opt.apply_gradients(zip(grads, variables))
                 return loss
 
             torch.cuda.synchronize()
@@ -262,6 +269,8 @@ def _run(args, content, style, sampling, feats, max_iter):
         dt = time.perf_counter() - t0
         with torch.no_grad():
             stylized = fold_pyramid(variables).detach()
+            if not args.eager:
+                stylized = stylized.permute(0, 3, 1, 2)
         per_scale.append({"scale": scl, "content_hw": list(sc.shape[-2:]), "style_hw": list(ss.shape[-2:]), "alpha": alpha,
                           "seconds": dt, "ms_per_iter": dt / max_iter * 1e3, "setup_seconds": t0 - t_setup,
                           "capture_seconds": (t_capture - t_warm if not args.eager else 0.0),

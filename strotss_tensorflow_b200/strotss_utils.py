@@ -140,6 +140,13 @@ class RMSprop:
         self.rho, self.epsilon, self.lr = float(rho), float(epsilon), float(learning_rate)
         self._slots = {}
 
+    def build(self, var_list):
+        """Create the rms slots now (Keras creates them at the first apply_gradients).  Call this before capturing
+        apply_gradients into a CUDA graph: a slot created inside the capture would be re-zeroed by every replay."""
+        for v in var_list:
+            if id(v) not in self._slots:
+                self._slots[id(v)] = torch.zeros_like(v)
+
     def apply_gradients(self, grads_and_vars):
         pairs = [(g, v) for g, v in grads_and_vars if g is not None]
         if not pairs:
