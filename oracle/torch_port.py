@@ -71,7 +71,7 @@ def relaxed_emd(x, y, distance='cosine'):       # nn/losses.py:69-80
 
 
 def convert_rgb_to_yuv(x):                      # nn/strotss_utils.py:166-167
-    return x[:, :3] @ _RGB_TO_YUV.to(x.dtype)
+    return x[:, :3] @ _RGB_TO_YUV.to(device=x.device, dtype=x.dtype)
 
 
 def style_loss(target, prediction, alpha):      # run_strotss.py:27-40

@@ -476,3 +476,30 @@ def test_full_size_properties(S, cuda_device):
     # self-similarity of a set with itself vanishes, so loss_c -> 0 and only the style terms remain
     sc4, _, _, _ = h.eval(content, content, 16.0, False)
     assert abs(sc4[_lib.S_LOSS_C].item()) <= 1e-6
+
+
+def test_full_size_against_the_fp64_restatement(S, cuda_device):
+    """N = M = 16384, D = 2179 (the bench workload, BASELINE.json configs[3]) against the fp64 restatement of the
+    reference op sequence (oracle/torch_port.py: materialised matrices + autograd), evaluated on the same device in
+    float64 -- the one place where the full size can be checked value by value rather than through invariants."""
+    import bench
+    from oracle import torch_port as T
+    from strotss_tensorflow_b200 import _lib
+    N = M = 16384
+    style, content, pred = bench.synth_torch(N, M, 2179, 1.0, 0, cuda_device)
+    h = S.Handle(cuda_device)
+    h.set_style_target(style)
+    sc, grad, _, _ = h.eval(pred, content, 16.0, True)
+    s = sc.double().cpu().numpy()
+    g = grad.double()
+    del h
+    ref, gref, info = T.total_loss_and_grad(style.double(), content.double(), pred.double(), 16.0)
+    assert abs(s[_lib.S_TOTAL] - ref.item()) / ref.item() <= LOSS_RTOL
+    for slot, key in [(_lib.S_LOSS_C, "loss_c"), (_lib.S_LOSS_S, "loss_s"), (_lib.S_L_M, "l_m"), (_lib.S_L_REMD, "l_remd"),
+                      (_lib.S_L_PALETTE, "l_palette")]:
+        assert abs(s[slot] - info[key].item()) / info[key].item() <= LOSS_RTOL, key
+    gn, rn = g.norm().item(), gref.norm().item()
+    assert abs(gn - rn) / rn <= GRADNORM_RTOL
+    assert (g * gref).sum().item() / (gn * rn) >= 0.99
+    del gref, g
+    torch.cuda.empty_cache()
