@@ -283,17 +283,17 @@ bool pair_enabled() {
 int bbox256() { return pair_enabled() ? 128 : 256; }
 
 // p.tiles_m counts 128-row blocks (as for the single-CTA kernel); converted to 256-row pair tiles here.
-template <int NACC, int EPI_WARPS = 4, bool B_MN = false, class Epi>
+template <int NACC, int EPI_WARPS = 4, int B_MODE = 0, class Epi>
 int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     if (!pair_enabled()) {
-        if constexpr (B_MN) { h->err = "internal: MN-major B needs the CTA-pair kernels"; return STROTSS_ERR_STATE; }
+        if constexpr (B_MODE != 0) { h->err = "internal: MN-major B needs the CTA-pair kernels"; return STROTSS_ERR_STATE; }
         else return launch_gemm<256, NACC, 4, EPI_WARPS>(h, p, st);
     }
     using Cfg = PairCfg<NACC>;
     constexpr int STAGES = 6;
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi, B_MN>;
+    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi, B_MODE>;
     static bool configured = false;
     if (!configured) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -763,6 +763,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     const bool sym = (sh.r0 == 0 && sh.r1 == N);
     float* rcol_part = nullptr;
     if (sym) RET(ensure(h, "ss.rcol_part", (size_t)((N + BM - 1) / BM) * 4 * N, &rcol_part));
+    // Exact block triangle (CTA-pair kernels): inside a panel's own 2048 x 2048 diagonal block only the tiles at or right
+    // of the diagonal are computed as well (P is symmetric: P_ij = P_ji); their mirror images enter the gradient through
+    // stage 2b, which then also covers the panel's own columns.  2304 -> 2080 tiles at N = 16384.
+    static const bool no_trap = (getenv("STROTSS_NO_TRAP") != nullptr);
+    static const bool generic_env = (getenv("STROTSS_SS1_GENERIC") != nullptr);
+    const bool trap = sym && pair_enabled() && !generic_env && !small && !no_trap;
     bf16* Pbuf[2] = {nullptr, nullptr};
     out.ss2 = nullptr; out.ld = 0;
     const int npanels = sh.n() > 0 ? (sh.n() + panel - 1) / panel : 0;
@@ -833,7 +839,9 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             }
             if (pair_enabled()) {
                 sp.tiles_m = (p.tiles_m + 1) / 2;              // 256-row pair tiles
-                const int tiles = sp.tiles_m * sp.tiles_n;
+                sp.trap = trap ? 1 : 0;
+                const int tmx = sp.tiles_m < sp.tiles_n ? sp.tiles_m : sp.tiles_n;
+                const int tiles = trap ? tmx * sp.tiles_n - tmx * (tmx - 1) / 2 : sp.tiles_m * sp.tiles_n;
                 const int max_pairs = h->num_sms / 2;
                 if (tiles > 0) {
                     PhaseTimer _pt(h, PH_SS1, st);
@@ -867,7 +875,20 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                 q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (rows + 255) / 256;
                 q.epi.C = out.ss2 + static_cast<long long>(r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = rows;
                 q.epi.alpha = 1.f; q.epi.col_off = 0; q.epi.accumulate = (sym && r0 > 0) ? 1 : 0;
-                RET((launch_gemm256<1, 8>(h, q, st2)));
+                if (trap) {
+                    // P is symmetric and only its tiles at or right of the diagonal exist.  Row tile tn of the panel:
+                    //   segment 0: sum over the columns from its own diagonal tile on   (P rows, K-major)
+                    //   segment 1: sum over the panel rows above it of P[i][these columns]^T  (same panel read MN-major)
+                    // Both segments accumulate into one TMEM tile and together span N - c0 columns for every tile.
+                    q.kb_lo_mul[0] = 256 / BK;
+                    RET(make_tmap(h, &q.tmA[1], x.xhT + r0, D, rows, np, BM));
+                    RET(make_tmap_mn(h, &q.tmB[1], P + r0, rows, rows, np));
+                    q.nseg = 2; q.seg_kblocks[1] = (rows + BK - 1) / BK; q.seg_acc[1] = 0;
+                    q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
+                    RET((launch_gemm256<1, 8, 2>(h, q, st2)));
+                } else {
+                    RET((launch_gemm256<1, 8>(h, q, st2)));
+                }
                 if (sym && r0 + panel < N) {
                     // stage 2b: ss2[j][d] += sum_{i in panel} P[i][j] x^[i][d] for the rows j right of the panel;
                     // B = P^T is read from the row-major panel through MN-major descriptors
@@ -879,7 +900,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
                     t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = mext;
                     t.epi.alpha = 1.f; t.epi.col_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
-                    RET((launch_gemm256<1, 8, true>(h, t, st2)));
+                    RET((launch_gemm256<1, 8, 1>(h, t, st2)));
                 }
             } else {
                 // single-CTA kernels: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]
@@ -919,7 +940,8 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
         ss_rows_kernel<<<(sh.n() + 31) / 32, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
-                                                             sym ? 1 : 0, panel, (panel / ss_bn) * ss_split, rcol_part, (panel / BM) * 4);
+                                                             sym ? 1 : 0, trap ? 256 : panel, trap ? ss_split : (panel / ss_bn) * ss_split, rcol_part,
+                                                             trap ? (256 / BM) * 4 : (panel / BM) * 4);
         CKL();
     }
     reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss + sh.r0, sh.n(), 1.f, loss_partial);

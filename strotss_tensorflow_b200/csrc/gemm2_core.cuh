@@ -33,9 +33,10 @@ struct PairCfg {
 };
 
 // tiles_m of GemmParams counts 256-row tiles here.
-// B_MN: the B operand is read from a matrix stored K x N (N contiguous) through MN-major descriptors; its tensor
+// B_MODE 1: the B operand is read from a matrix stored K x N (N contiguous) through MN-major descriptors; its tensor
 // map has dims {N, K} and box {64, 64} (each CTA stages its 128 columns of B as two 64-wide chunks).
-template <int NACC, int STAGES, int EPI_WARPS, class Epi, bool B_MN = false>
+// B_MODE 2: chosen per segment at run time (p.seg_bmn[s]); both layouts stage the same 16 KB per CTA and K block.
+template <int NACC, int STAGES, int EPI_WARPS, class Epi, int B_MODE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
 gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
@@ -83,14 +84,17 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
                 const int arow = p.a_row0 + tm * BM2 + static_cast<int>(rank) * 128;
                 const int brow = p.b_row0 + tn * BN + static_cast<int>(rank) * 128;
                 for (int s = 0; s < p.nseg; ++s) {
-                    for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
+                    const int kb0 = p.kb_lo_mul[s] * tn;
+                    const int kb1 = p.kb_hi_mul[s] ? min(p.seg_kblocks[s], p.kb_hi_mul[s] * tn) : p.seg_kblocks[s];
+                    const bool bmn = (B_MODE == 1) || (B_MODE == 2 && p.seg_bmn[s]);
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
                         uint8_t* sB = sA + Cfg::A_BYTES;
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
                         tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
-                        if constexpr (B_MN) {
+                        if (bmn) {
                             tma_load_2d_2cta(sB, &p.tmB[s], lead_full, brow, kb * BK);
                             tma_load_2d_2cta(sB + Cfg::B_BYTES / 2, &p.tmB[s], lead_full, brow + 64, kb * BK);
                         } else {
@@ -103,24 +107,32 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM2, BN, false, B_MN);
+            constexpr uint32_t idesc_k = make_idesc_bf16(BM2, BN, false, false);
+            constexpr uint32_t idesc_mn = make_idesc_bf16(BM2, BN, false, true);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
+                int tm_, tn_ = 0;
+                if constexpr (B_MODE == 2) decode_tile(p, t, tm_, tn_);
+                else if (p.kb_lo_mul[0] | p.kb_hi_mul[0]) decode_tile(p, t, tm_, tn_);
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 uint32_t touched = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const int acc = p.seg_acc[s];
                     const uint32_t d_addr = tmem_base + as * Cfg::ACC_COLS + acc * BN;
-                    for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
+                    const int kb0 = p.kb_lo_mul[s] * tn_;
+                    const int kb1 = p.kb_hi_mul[s] ? min(p.seg_kblocks[s], p.kb_hi_mul[s] * tn_) : p.seg_kblocks[s];
+                    const bool bmn = (B_MODE == 1) || (B_MODE == 2 && p.seg_bmn[s]);
+                    const uint32_t idesc = bmn ? idesc_mn : idesc_k;
+                    const uint32_t b_step = bmn ? (16 * 128) >> 4 : 2;
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                        const uint64_t bdesc = B_MN ? make_mnmajor_sw128_desc(a_addr + Cfg::A_BYTES, Cfg::B_BYTES / 2)
-                                                    : make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
-                        constexpr uint32_t b_step = B_MN ? (16 * 128) >> 4 : 2;
+                        const uint64_t bdesc = bmn ? make_mnmajor_sw128_desc(a_addr + Cfg::A_BYTES, Cfg::B_BYTES / 2)
+                                                   : make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,

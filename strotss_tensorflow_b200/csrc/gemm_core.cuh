@@ -43,6 +43,12 @@ struct GemmParams {
     int group_n;                 // raster: column tiles are swept in groups of group_n (L2 blocking)
     int tri;                     // 1: square tile grid of a symmetric product, only tiles with tn >= tm are visited
     int a_row0, b_row0;          // element row where tile (0,0) starts in A / B
+    // Optional tile-dependent K range per segment (CTA-pair kernel only; all zero = full range): for column tile tn, segment s
+    // runs K blocks [kb_lo_mul[s] * tn, kb_hi_mul[s] ? min(seg_kblocks[s], kb_hi_mul[s] * tn) : seg_kblocks[s]).
+    // Stage 2 of the self-similarity uses it to walk only the upper block triangle of the symmetric P panel.
+    int kb_lo_mul[kMaxSeg], kb_hi_mul[kMaxSeg];
+    // B_MODE == 2 of the pair kernel: segment s reads its B operand MN-major (transposed) iff seg_bmn[s]
+    int seg_bmn[kMaxSeg];
     typename Epi::Params epi;
 };
 
@@ -276,7 +282,8 @@ template <int BN> struct EpiStoreT : EpiStore {
 template <int BN>
 struct EpiStoreTr {
     static constexpr int SMEM_BYTES = 0;
-    struct Params { float* C; long long ldc; int rows, cols; float alpha; int col_off; int accumulate; };
+    // accumulate: add to C everywhere; acc_cols_below: add to C for output rows (B index) below this bound only
+    struct Params { float* C; long long ldc; int rows, cols; float alpha; int col_off; int accumulate; int acc_cols_below; };
     struct State {};
     __device__ static void init(State&, const Params&, int, int) {}
     __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
@@ -284,6 +291,7 @@ struct EpiStoreTr {
     __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t*) {
         const int row = ti.row0 + ti.q * 32 + ti.lane;            // index along the contiguous output dimension
         const bool rvalid = row < P.rows;
+        const bool accumulate = P.accumulate || (ti.col0 < P.acc_cols_below);      // tile-uniform (bounds are tile-aligned)
 #pragma unroll 1
         for (int c = ti.c0; c < ti.c1; ++c) {
             uint32_t r[32];
@@ -292,7 +300,7 @@ struct EpiStoreTr {
             const int colbase = ti.col0 + c * 32;
             if (rvalid && colbase < P.cols) {
                 float* dst = P.C + static_cast<long long>(colbase - P.col_off) * P.ldc + row;
-                if (P.accumulate) {
+                if (accumulate) {
                     // all 32 loads are issued before the first store: a load-add-store per element would be
                     // serialised by the compiler (it cannot prove the 32 addresses distinct) -- 32 round trips
                     float old[32];

@@ -33,8 +33,33 @@ struct Ss1Params {
     int tiles_m, tiles_n, group_n;
     int tri;                     // always 0 here (decode_tile's triangular walk is used by the covariance kernel)
     int a_row0, b_row0;
+    // trap = 1 (CTA-pair kernel, symmetric mode, a_row0 == b_row0): only tiles with tn >= tm are visited -- the block
+    // trapezoid of a row panel of a symmetric matrix -- and every tile right of its own diagonal tile accounts for its
+    // mirror image.  Same L2 raster as decode_tile: groups of group_n column tiles, row tiles swept inside a group.
+    int trap;
     Ss1Epi::Params epi;
 };
+
+__device__ __forceinline__ int ss1_num_tiles(const Ss1Params& p) {
+    if (!p.trap) return num_tiles_of(p);
+    const int tmx = min(p.tiles_m, p.tiles_n);
+    return tmx * p.tiles_n - tmx * (tmx - 1) / 2;
+}
+
+__device__ __forceinline__ void ss1_decode(const Ss1Params& p, int t, int& tm, int& tn) {
+    if (!p.trap) { decode_tile(p, t, tm, tn); return; }
+    for (int c_lo = 0; c_lo < p.tiles_n; c_lo += p.group_n) {
+        const int c_hi = min(p.tiles_n, c_lo + p.group_n);
+        const int rows = min(p.tiles_m, c_hi);              // row tiles that own a tile in this column group
+        for (int r = 0; r < rows; ++r) {
+            const int first = max(c_lo, r);
+            const int len = c_hi - first;
+            if (t < len) { tm = r; tn = first + t; return; }
+            t -= len;
+        }
+    }
+    tm = 0; tn = 0;                                         // unreachable for t < ss1_num_tiles(p)
+}
 
 constexpr int kSs1PairStages = 6;
 constexpr int kSs1SmemBytes = kSs1Stages * TileCfg<kSs1BN, 2>::STAGE_BYTES + Ss1Epi::SMEM_BYTES + (2 * kSs1Stages + 4) * 8 + 16 + 1024;
@@ -81,7 +106,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int num_tiles = num_tiles_of(p);
+    const int num_tiles = ss1_num_tiles(p);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -89,7 +114,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             int stage = 0; uint32_t phase = 0;
             for (int t = first; t < num_tiles; t += stride) {
                 int tm, tn;
-                decode_tile(p, t, tm, tn);
+                ss1_decode(p, t, tm, tn);
                 const int arow = p.a_row0 + tm * TILE_M + rank * 128, brow = p.b_row0 + tn * BN + rank * 128;
                 for (int s = 0; s < 3; ++s) {
                     for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -154,7 +179,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
         int seq = 0;
         for (int t = first; t < num_tiles; t += stride, ++seq) {
             int tm, tn;
-            decode_tile(p, t, tm, tn);
+            ss1_decode(p, t, tm, tn);
             const int row0 = p.a_row0 + tm * TILE_M + rank * 128, col0 = p.b_row0 + tn * BN;
             // per-column vectors u, w of this tile -> shared memory (double-buffered across tiles)
             float* buf = reinterpret_cast<float*>(epi_smem) + (seq & 1) * 2 * BN;
@@ -170,7 +195,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             const bool rvalid = row < P.row_end;
             const float ui = rvalid ? P.u[row] : 0.f;
             const float wi = rvalid ? P.w[row] : 0.f;
-            const bool both = P.sym && (col0 >= P.panel_end);
+            const bool both = P.sym && (p.trap ? (tn > tm) : (col0 >= P.panel_end));
 
             // ---- accumulator 1 (y^.y^T): stash Yd = 1 - acc1, then hand the columns back to the MMA warp
             float yd[kChunks * 32];

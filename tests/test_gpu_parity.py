@@ -176,7 +176,8 @@ def test_self_similarity(handle, cuda_device, N, eps, seed):
     assert abs(same) <= 1e-6 * max(l64, 1e-4) * 100
 
 
-@pytest.mark.parametrize("N,D,eps,seed", [(4500, 515, 0.1, 31), (2300, 2179, 0.1, 32), (4096, 259, 1.0, 33)])
+@pytest.mark.parametrize("N,D,eps,seed", [(4500, 515, 0.1, 31), (2300, 2179, 0.1, 32), (4096, 259, 1.0, 33), (2049, 131, 0.1, 34),
+                                          (4700, 67, 0.1, 35)])
 def test_self_similarity_multi_panel(handle, cuda_device, N, D, eps, seed):
     """N > 2048: several row panels; exercises the symmetric path (mirror accounting, transposed stage 2b)."""
     st, co, pr = O.synth_problem(N, 8, D, eps=eps, seed=seed)
@@ -425,11 +426,11 @@ print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.no
 @pytest.mark.parametrize("env", [{"STROTSS_NO_PAIR": "1"}, {"STROTSS_SS1_GENERIC": "1"},
                                  {"STROTSS_NO_PAIR": "1", "STROTSS_SS1_GENERIC": "1"},
                                  {"STROTSS_BRANCHES": "0"}, {"STROTSS_PAL_TWO_PASS": "1"},
-                                 {"STROTSS_BRANCHES": "0", "STROTSS_OVERLAP": "1"}])
+                                 {"STROTSS_BRANCHES": "0", "STROTSS_OVERLAP": "1"}, {"STROTSS_NO_TRAP": "1"}])
 def test_alternative_kernel_paths(cuda_device, env):
     """The single-CTA GEMM kernels (STROTSS_NO_PAIR), the generic stage-1 epilogue (STROTSS_SS1_GENERIC), the
     single-stream launch order (STROTSS_BRANCHES=0), the two-pass palette search and the two-stream stage-1/stage-2
-    pipelining (STROTSS_OVERLAP=1) stay selectable for A/B measurements; they must give the same answers.  The
+    pipelining (STROTSS_OVERLAP=1) and the rectangular panel walk (STROTSS_NO_TRAP) stay selectable for A/B measurements; they must give the same answers.  The
     switches are read once per process."""
     import subprocess
     import sys
