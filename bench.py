@@ -401,9 +401,11 @@ def main():
             "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
             # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 8 launches of one step of this workload
-            # (profiles/r01_v7_ss1_pair_ncu_raw.csv); algorithmic: operands 220 + 990 MB, P panel 302 MB
-            "traffic": 1.7148e9 if (world == 1 and N == 16384) else None,
-            "traffic_unit": "bytes per step (all launches of the kernel)", "algorithmic_bytes": 1.512e9,
+            # (profiles/r01_v14_ss1_trap_ncu_summary.txt; rectangular panels, STROTSS_NO_TRAP=1: r01_v7_ss1_pair_ncu_raw.csv);
+            # algorithmic: operands 220 + 990 MB, P panels 272 MB (302 MB rectangular)
+            "traffic": (1.7148e9 if os.environ.get("STROTSS_NO_TRAP") else 2.183e9) if (world == 1 and N == 16384) else None,
+            "traffic_unit": "bytes per step (all launches of the kernel)",
+            "algorithmic_bytes": 1.512e9 if os.environ.get("STROTSS_NO_TRAP") else 1.482e9,
             "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": ss1_n / args.steps if ss1_n else None,
             "achieved_executed": (ach * 1.5 * visited) if ach else None,
