@@ -991,7 +991,7 @@ int check_handle(strotss_handle h) { return h ? 0 : STROTSS_ERR_ARG; }
 // ======================================================================================
 extern "C" {
 
-const char* strotss_version(void) { return "strotss_b200 0.2 (sm_100a, tcgen05/TMA)"; }
+const char* strotss_version(void) { return "strotss_b200 0.3 (sm_100a, tcgen05/TMA)"; }
 
 static int init_ctx(strotss_ctx* h, int device) {
     h->device = device;
