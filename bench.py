@@ -72,7 +72,7 @@ def synth_torch(N, M, D, eps, seed, device):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -83,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -205,7 +205,7 @@ def run_masked(args, dev, S, _lib):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
@@ -449,19 +449,21 @@ def main():
         t_probe = cpu_eval_seconds(n_s, 1, 1, threads)[0]
         if N >= 4096 and t_probe * (f_ref(4096, 4096) / f_ref(n_s, n_s)) < 12.0:
             n_s = 4096
-        reps = 2 if n_s == 4096 else 5
+        t_one = t_probe * (f_ref(n_s, n_s) / f_ref(min(N, 2048), min(N, 2048)))
+        reps = max(2, min(24, int(10.0 / max(t_one, 1e-3))))          # ~10 s of all-core CPU work
         times = cpu_eval_seconds(n_s, reps, 0, threads)
         t = sum(times) / len(times)
         scale = f_ref(N, M) / f_ref(n_s, n_s)
         # the reference pins TensorFlow to one intra-op / one inter-op thread (nn/rand.py:16-17): time that setting too,
         # on a smaller sample (N = M = 1024, one evaluation)
         n_1 = min(N, 1024)
-        t_1 = cpu_eval_seconds(n_1, 1, 1, 1)[0]
+        t_1s = cpu_eval_seconds(n_1, 5, 1, 1)
+        t_1 = sum(t_1s) / len(t_1s)
         one_thread = 1.0 / (t_1 * f_ref(N, M) / f_ref(n_1, n_1))
         line["cpu_baseline"] = {
             "value": 1.0 / (t * scale), "unit": "evals/s", "cores": threads, "kind": "port",
             "value_1_thread": one_thread,
-            "sample_1_thread": f"same port pinned to 1 thread (the reference's own setting, nn/rand.py:16-17), one evaluation at "
+            "sample_1_thread": f"same port pinned to 1 thread (the reference's own setting, nn/rand.py:16-17), 5 evaluations at "
                                f"N=M={n_1} ({t_1:.2f} s), scaled by the reference FLOP ratio",
             "sample": f"torch-CPU port of the reference op sequence (fp32, materialised matrices, autograd), {reps} evaluations at "
                       f"N=M={n_s} ({t:.2f} s each), scaled to N=M={N} by the reference FLOP ratio {scale:.2f}"}

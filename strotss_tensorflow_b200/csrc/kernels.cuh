@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __res
     }
     __syncthreads();
     const int rows = min(rpb, n - r0);
+#pragma unroll 3
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float a = 0.f;
 #pragma unroll 8
@@ -316,8 +317,17 @@ __global__ void __launch_bounds__(256) ss_vectors_kernel(const float* __restrict
     if (j >= N) return;
     const float* xr = x + static_cast<long long>(j) * ldx;
     const float* yr = y + static_cast<long long>(j) * ldy;
-    float dx = 0.f, dy = 0.f;
-    for (int d = lane; d < D; d += 32) { dx = fmaf(xr[d], sumhx[d], dx); dy = fmaf(yr[d], sumhy[d], dy); }
+    // four independent partial sums per dot product keep 16 loads in flight per lane (the loop is latency-bound otherwise)
+    float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f, dx3 = 0.f, dy0 = 0.f, dy1 = 0.f, dy2 = 0.f, dy3 = 0.f;
+    int d = lane;
+    for (; d + 96 < D; d += 128) {
+        dx0 = fmaf(xr[d], sumhx[d], dx0); dx1 = fmaf(xr[d + 32], sumhx[d + 32], dx1);
+        dx2 = fmaf(xr[d + 64], sumhx[d + 64], dx2); dx3 = fmaf(xr[d + 96], sumhx[d + 96], dx3);
+        dy0 = fmaf(yr[d], sumhy[d], dy0); dy1 = fmaf(yr[d + 32], sumhy[d + 32], dy1);
+        dy2 = fmaf(yr[d + 64], sumhy[d + 64], dy2); dy3 = fmaf(yr[d + 96], sumhy[d + 96], dy3);
+    }
+    for (; d < D; d += 32) { dx0 = fmaf(xr[d], sumhx[d], dx0); dy0 = fmaf(yr[d], sumhy[d], dy0); }
+    float dx = (dx0 + dx1) + (dx2 + dx3), dy = (dy0 + dy1) + (dy2 + dy3);
     dx = warp_sum(dx) * invx[j];
     dy = warp_sum(dy) * invy[j];
     if (lane == 0) {
