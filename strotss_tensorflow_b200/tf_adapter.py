@@ -164,3 +164,52 @@ class StyleLoss:                         # pragma: no cover  (run_strotss.py:27-
         l_remd = relaxed_emd(self.target, prediction)
         l_palette = relaxed_emd(convert_rgb_to_yuv(self.target), convert_rgb_to_yuv(prediction), distance="both")
         return l_m + l_remd + (self.inv_alpha * l_palette)
+
+
+class StrotssLoss:                       # pragma: no cover
+    """Fused evaluation for the reference's train_step (run_strotss.py:136-140): one strotss_eval call per iteration
+    instead of four ops, with the style-side statistics cached per scale (strotss_set_style_target).
+
+        loss_fn = StrotssLoss(sampling(style_feat), alpha)        # replaces StyleLoss(...) at run_strotss.py:128
+        loss, loss_c, loss_s = loss_fn(c_feat, p_feat)            # replaces :138-140
+
+    Masked mode (:97-125): build one StrotssLoss per region exactly as the reference builds one StyleLoss per region, or
+    bind strotss_set_style_targets_grouped / strotss_eval_grouped the same way (see modules.MaskedStrotssLoss)."""
+
+    def __init__(self, target, alpha: float, device_index: int = 0):
+        _require_tf()
+        self.alpha = float(alpha)
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        _lib.check(self.lib, self.h, self.lib.strotss_create(device_index, C.byref(self.h)), "strotss_create")
+        t = _reshape_2d(target)
+        m, d = int(t.shape[0]), int(t.shape[1])
+        p, keep = _dev_ptr(t)
+        tf.test.experimental.sync_devices()
+        _lib.check(self.lib, self.h, self.lib.strotss_set_style_target(self.h, p, m, d, d, None), "strotss_set_style_target")
+        tf.test.experimental.sync_devices()
+
+    def _call(self, content, pred):
+        n, d = int(pred.shape[0]), int(pred.shape[1])
+        scalars = tf.zeros([_lib.NUM_SCALARS], tf.float32)
+        grad = tf.zeros_like(pred)
+        (pp, k1), (pc, k2), (ps, k3), (pg, k4) = _dev_ptr(pred), _dev_ptr(content), _dev_ptr(scalars), _dev_ptr(grad)
+        tf.test.experimental.sync_devices()
+        _lib.check(self.lib, self.h, self.lib.strotss_eval(self.h, pp, d, pc, d, n, self.alpha, ps, pg, d, None, None, None),
+                   "strotss_eval")
+        tf.test.experimental.sync_devices()
+        return scalars[_lib.S_TOTAL], scalars[_lib.S_LOSS_C], scalars[_lib.S_LOSS_S], grad
+
+    def __call__(self, content, prediction):
+        @tf.custom_gradient
+        def op(c2, p2):
+            loss, loss_c, loss_s, grad = tf.py_function(self._call, [c2, p2], [tf.float32] * 4)
+            for t in (loss, loss_c, loss_s):
+                t.set_shape([])
+            grad.set_shape(p2.shape)
+
+            def bwd(g_loss, g_c, g_s):          # only `loss` is differentiated by the driver (run_strotss.py:141)
+                return None, g_loss * grad
+            return (loss, tf.stop_gradient(loss_c), tf.stop_gradient(loss_s)), bwd
+
+        return op(_reshape_2d(content), _reshape_2d(prediction))
