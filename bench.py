@@ -205,7 +205,7 @@ def run_masked(args, dev, S, _lib):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
@@ -393,19 +393,21 @@ def main():
     if rowshard or N <= 2048:
         visited = 1.0
     elif os.environ.get("STROTSS_NO_TRAP"):
-        visited = sum(N - p * 2048 for p in range(-(-own_rows // 2048))) * 2048.0 / (float(N) * N)
+        ph = int(os.environ.get("STROTSS_PANEL", "4096"))
+        visited = sum(min(ph, N - p * ph) * (N - p * ph) for p in range(-(-own_rows // ph))) / (float(N) * N)
     else:
         visited = nt * (nt + 1) / 2.0 / (nt * nt)
     ach = alg_flops_step / (ss1_ms / args.steps * 1e-3) / 1e12 if ss1_n else None
     roof = {"bound": "tensor", "kernel": "ss1_pair_kernel (self-similarity stage 1, cta_group::2; all launches of a step)",
             "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
-            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 8 launches of one step of this workload
-            # (profiles/r01_v14_ss1_trap_ncu_summary.txt; rectangular panels, STROTSS_NO_TRAP=1: r01_v7_ss1_pair_ncu_raw.csv);
-            # algorithmic: operands 220 + 990 MB, P panels 272 MB (302 MB rectangular)
-            "traffic": (1.7148e9 if os.environ.get("STROTSS_NO_TRAP") else 2.183e9) if (world == 1 and N == 16384) else None,
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one step of the DEFAULT build at this
+            # workload (4096-row panels, triangle walk: profiles/r01_v15_ss1_ncu_summary.txt); other switch settings: not captured
+            "traffic": 1.808e9 if (world == 1 and N == 16384 and not os.environ.get("STROTSS_NO_TRAP")
+                                   and not os.environ.get("STROTSS_PANEL")) else None,
             "traffic_unit": "bytes per step (all launches of the kernel)",
-            "algorithmic_bytes": 1.512e9 if os.environ.get("STROTSS_NO_TRAP") else 1.482e9,
+            # operands: A 4 panels x 3 x 4096 x 2240 bf16 = 220 MB, B 550 MB; P panels 2080 tiles x 128 KB = 272 MB
+            "algorithmic_bytes": 1.042e9 if (world == 1 and N == 16384) else None,
             "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
             "launches_per_step": ss1_n / args.steps if ss1_n else None,
             "achieved_executed": (ach * 1.5 * visited) if ach else None,

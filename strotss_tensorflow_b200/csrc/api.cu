@@ -753,9 +753,13 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     RET(ensure(h, "ss.rowloss", (size_t)N, &rowloss));
     RET(ensure(h, "ss.coef", (size_t)N, &out.coef));
     const int np = x.np;
-    // row panel of P (bf16), sized to stay L2-resident between its producer and consumer GEMMs
-    static const int panel_rows = getenv("STROTSS_PANEL") ? atoi(getenv("STROTSS_PANEL")) : 2048;
-    int panel = panel_rows;
+    // Row panel of P (bf16) between its producer (stage 1) and consumer (stage 2) GEMMs: 4096 rows x N columns = 128 MB at
+    // N = 16384, about the size of the 126 MB L2.  Measured at N = 16384 (evals/s): 2048 rows 208, 4096 rows 224, 8192 rows 229,
+    // all 16384 rows (the whole matrix, 512 MB) 231 -- fewer, larger launches win (fewer partially filled tile rounds, stage-2
+    // launches of two full rounds instead of one) and the part of the panel that spills to HBM costs little; 4096 keeps the
+    // staging buffer cache-sized instead of turning it into a stored N x N matrix.
+    static const int panel_rows = getenv("STROTSS_PANEL") ? atoi(getenv("STROTSS_PANEL")) : 4096;
+    int panel = round_up(panel_rows < 256 ? 256 : panel_rows, 256);          // panel starts stay tile-aligned
     if (panel > round_up(sh.n() > 0 ? sh.n() : 1, BM)) panel = round_up(sh.n() > 0 ? sh.n() : 1, BM);
     // Symmetric mode (this rank owns every row): Xd and Yd are symmetric, so a panel only computes the
     // column tiles at or right of its own rows; tiles strictly right of the panel also account for their
