@@ -124,6 +124,68 @@ def test_relaxed_emd_three_channel(handle, cuda_device, dist):
     _gcheck(grad, g64, cos_min=0.999)
 
 
+def _palette_case(name, rng):
+    """Colour sets that stress the candidate search of the palette term (pal_min2_kernel): ties, clamps, clipping."""
+    M, N = 2300, 2600
+    a = rng.uniform(0.02, 1.0, (M, 3)); b = rng.uniform(0.02, 1.0, (N, 3))
+    if name == "uniform":
+        pass
+    elif name == "duplicates":             # 60 % of the targets share one colour (flat background)
+        a[: int(0.6 * M)] = a[0]
+    elif name == "clustered":              # tight cluster plus a few outliers that stretch the bounding box
+        a = 0.5 + 0.002 * rng.standard_normal((M, 3)); a[:5] = rng.uniform(0, 1, (5, 3))
+        b = 0.5 + 0.01 * rng.standard_normal((N, 3))
+    elif name == "disjoint":               # predictions far outside the targets' bounding box
+        b = rng.uniform(1.5, 3.0, (N, 3)); b[:100] = rng.uniform(-2.0, -1.0, (100, 3))
+    elif name == "scaled":                 # 0..255 colours, negative values
+        a = a * 255.0 - 40.0; b = b * 255.0 - 40.0
+    elif name == "flat_axis":              # grey images: U = V = 0 for every colour
+        a = np.repeat(rng.uniform(0.02, 1.0, (M, 1)), 3, axis=1); b = np.repeat(rng.uniform(0.02, 1.0, (N, 1)), 3, axis=1)
+    elif name == "quantised":              # 8-bit style colours: many exact ties
+        a = np.round(a * 15) / 15; b = np.round(b * 15) / 15
+    return a, b
+
+
+@pytest.mark.parametrize("dist", ["both", "l2"])
+@pytest.mark.parametrize("case", ["uniform", "duplicates", "clustered", "disjoint", "scaled", "flat_axis", "quantised"])
+def test_palette_search_is_exact(handle, cuda_device, case, dist):
+    """The one-pass search (sqrt.approx, pre-scaled records, redux.sync column minima) must return the minimum cost of
+    every row / column (fp64 oracle) and the oracle's argmin wherever it is unique by a clear margin; on exact ties the
+    LOWEST index."""
+    rng = np.random.default_rng(11)
+    a, b = _palette_case(case, rng)
+    if dist == "both" or case != "scaled":
+        a = O.convert_rgb_to_yuv(a, np.float32)
+        b = O.convert_rgb_to_yuv(b, np.float32)
+    a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
+    out, grad, ra, ca = handle.relaxed_emd(_t(a, cuda_device), _t(b, cuda_device), dist, True, True)
+    l64, g64, info = O.relaxed_emd(a, b, dist, np.float64, True)
+    out = out.cpu().numpy()
+    # |a - b|^2 by expansion (nn/losses.py:19-22, the reference's own formula) cancels in fp32 when colours nearly coincide:
+    # the tight cluster is held to the north-star's 1e-3, everything else to 1e-4
+    tol = LOSS_RTOL if case == "clustered" else 1e-4
+    assert abs(out[0] - l64) / l64 <= tol
+    assert abs(out[1] - info["R_X"]) <= tol * info["R_X"] + 1e-7 and abs(out[2] - info["R_Y"]) <= tol * info["R_Y"] + 1e-7
+    C = O._dist_fwd(a, b, dist, np.float64)[0]
+    ra, ca = ra.cpu().numpy(), ca.cpu().numpy()
+    scale = max(1.0, float(np.abs(C).max()))
+    # the chosen candidates attain the minimum to the fp32 accuracy of the cost: ~ulp(|a|^2) / (2 sqrt(m)), i.e. up to ~1e-4
+    # next to the clamp floor sqrt(1e-6 / 3) where near-identical colours sit (their computed costs tie exactly)
+    att = 2e-4 if case in ("clustered", "flat_axis") else 2e-5
+    assert np.all(C[np.arange(C.shape[0]), ra] - C.min(axis=1) <= att * scale)
+    assert np.all(C[ca, np.arange(C.shape[1])] - C.min(axis=0) <= att * scale)
+    # ... and are the oracle's own choice wherever that is unique by a clear margin
+    clear_r = info["row_gap"] > 10 * att * scale
+    clear_c = info["col_gap"] > 10 * att * scale
+    assert np.array_equal(ra[clear_r], info["row_argmin"][clear_r])
+    assert np.array_equal(ca[clear_c], info["col_argmin"][clear_c])
+    if case == "quantised":
+        # exact duplicates of a colour: the lowest index wins, as in the exhaustive kernel
+        _, first = np.unique(a, axis=0, return_index=True)
+        firsts = set(first.tolist())
+        assert all(int(i) in firsts for i in ca)
+
+
 def test_palette_identical_inputs_hit_clamp_floor(handle, cuda_device):
     rng = np.random.default_rng(4)
     a = rng.uniform(0.1, 1.0, (300, 3)).astype(np.float32)
