@@ -521,7 +521,7 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
             q.epi.rowbest = rs.rowbest; q.epi.colbest = rs.colbest; q.epi.M = M; q.epi.N = sh.r1;
             RET((launch_gemm<128, 1, 6>(h, q, st)));
         } else {
-            RET((launch_gemm256<1>(h, p, st)));
+            RET((launch_gemm256<1, 8>(h, p, st)));
         }
     }
     PhaseTimer _pm(h, PH_REMD_MISC, st);
