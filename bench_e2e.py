@@ -123,15 +123,7 @@ def main():
     def run(max_iter):
         return _run(args, content, style, sampling, feats, vgg, max_iter)
 
-    run(3)                                       # warm-up: cuDNN autotune, workspace growth, module load
-    if not args.eager:
-        # the warm-up pass's last graph is torn down lazily at the next capture in the pool (hundreds of ms of cudaFree);
-        # pay that here, not inside the timed image
-        g = torch.cuda.CUDAGraph()
-        t = torch.zeros(8, device=dev)
-        with torch.cuda.graph(g, pool=_graph_pool()):
-            t.add_(1.0)
-        del g
+    run(3)                                       # warm-up: module load, workspace growth, per-scale graph capture
     torch.cuda.synchronize()
     t_all = time.perf_counter()
     per_scale = run(args.max_iter)
@@ -144,30 +136,80 @@ def main():
                    "vgg": "torch/cuDNN conv stack, fp32 tensors, channels_last (stand-in for the reference's TF/cuDNN path)",
                    "loss_path": "strotss_tensorflow_b200 (fused sampler + loss/grad kernels)",
                    "launch": "eager (op by op)" if args.eager else
-                             "one CUDA graph per scale: fold + VGG fwd + sampler + loss/grad + VGG bwd + RMSprop captured once "
-                             "(capture inside the timed region), replayed every iteration; sample indices drawn on the host and "
-                             "copied into the graph's index buffer each iteration; the loss scalar is read back every iteration",
+                             "one CUDA graph per scale: fold + VGG fwd + sampler + loss/grad + VGG bwd + RMSprop, captured once per "
+                             "process (in the warm-up pass) and reused for every image: a new image only copies its content "
+                             "features / initial pyramid into the graph's buffers and re-prepares the style target; sample indices "
+                             "are drawn on the host and copied into the graph's index buffer each iteration; the loss scalar is "
+                             "read back every iteration",
                    "pixel_side": "torch ops" if args.eager else "strotss_pyramid_fold / _fold_backward / strotss_rmsprop_step (this repo)",
-                   "warmup": "one untimed pass of 3 iterations per scale"},
+                   "warmup": "one untimed pass of 3 iterations per scale (it also captures the per-scale graphs: steady-state "
+                             "per-image time, as for the 2nd..64th image of BASELINE configs[4])"},
         "per_scale": per_scale}))
 
 
-_POOL = None
-_POOL_KEEPER = None
+class ScaleGraph:
+    """Everything one scale of the driver loop needs, with static buffers and ONE captured CUDA graph of an iteration
+    (run_strotss.py:131-148): fold -> VGG forward -> sampler -> loss + gradient -> VGG backward -> RMSprop."""
+
+    def __init__(self, sampling, vgg_feats, content_feat, style_samples, stylized_nhwc, alpha, lr):
+        self.sampling = sampling
+        self.content_feat = [t.clone() for t in content_feat]
+        self.variables = [v.clone().requires_grad_(True) for v in S.make_laplacian_pyramid(stylized_nhwc, 5)]
+        self.opt = S.RMSprop(rho=0.99, epsilon=1e-8, learning_rate=lr)            # run_strotss.py:63
+        self.opt.build(self.variables)
+        self.loss_fn = S.StrotssLoss(style_samples, alpha)
+        self.static_idx = sampling._make_indices(self.content_feat[0], True)
+        self.base_cpu = torch.empty(self.content_feat[0].shape)                   # shape carrier: indices are drawn on the host
+
+        def feats(img):                      # img: (1, h, w, 3); its NCHW view is channels_last already
+            return [img] + [nhwc(f) for f in vgg_feats(img.permute(0, 3, 1, 2))]
+
+        def iteration(update):
+            img = S.fold_laplacian_pyramid(self.variables)
+            pred = feats(img)
+            c_feat = sampling._sample(self.content_feat, self.static_idx, True)
+            p_feat = sampling._sample(pred, self.static_idx, True)
+            loss = self.loss_fn(c_feat, p_feat)
+            grads = torch.autograd.grad(loss, self.variables)
+            if update:
+                self.opt.apply_gradients(zip(grads, self.variables))
+            return loss
+
+        # one eager forward + backward without an update, so that cuDNN plans/workspaces and the library workspace exist
+        # before capture (no device allocation is allowed inside a capture)
+        iteration(False)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = iteration(True)
+
+    def load(self, content_feat, style_samples, stylized_nhwc):
+        """A new image at this scale: refill the graph's buffers (same shapes), reset the optimizer slots."""
+        with torch.no_grad():
+            for d, src in zip(self.content_feat, content_feat):
+                d.copy_(src)
+            for v, src in zip(self.variables, S.make_laplacian_pyramid(stylized_nhwc, 5)):
+                v.copy_(src)
+            for slot in self.opt._slots.values():
+                slot.zero_()
+        self.loss_fn.handle.set_style_target(style_samples)
+
+    def run(self, max_iter):
+        nxt, last = None, None
+        for it in range(max_iter):
+            if nxt is not None:
+                self.static_idx.copy_(nxt, non_blocking=True)
+            self.graph.replay()
+            nxt = self.sampling._make_indices(self.base_cpu, True).pin_memory()   # next iteration's draw, under the GPU work
+            last = float(self.static_loss.item())   # the reference formats three scalars per iteration (run_strotss.py:150-152)
+        return last
+
+    def image(self):
+        with torch.no_grad():
+            return S.fold_laplacian_pyramid([v.detach() for v in self.variables])
 
 
-def _graph_pool():
-    """One memory pool shared by the per-scale graphs, so a later image (or the timed pass after the warm-up pass) reuses the
-    activations' memory instead of cudaMalloc-ing it again.  A trivial graph that lives for the whole process keeps the pool
-    alive while the per-scale graphs come and go."""
-    global _POOL, _POOL_KEEPER
-    if _POOL is None:
-        _POOL = torch.cuda.graph_pool_handle()
-        keep = torch.zeros(8, device="cuda")
-        _POOL_KEEPER = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(_POOL_KEEPER, pool=_POOL):
-            keep.add_(1.0)
-    return _POOL
+_SCALE_GRAPHS = {}
 
 
 def _run(args, content, style, sampling, feats_nchw, vgg_feats, max_iter):
@@ -188,12 +230,14 @@ def _run(args, content, style, sampling, feats_nchw, vgg_feats, max_iter):
         else:
             stylized = F.interpolate(stylized, size=sc.shape[-2:], mode="bilinear", align_corners=False)
             lr = args.lr / 2
-        variables = [torch.nn.Parameter(v.clone()) for v in make_pyramid(stylized)]
         feats, fold_pyramid = feats_nchw, fold_pyramid_torch
         with torch.no_grad():
             content_feat = feats(sc)
-            style_feat = feats(ss)
-            loss_fn = S.StrotssLoss(sampling(style_feat), alpha)
+            style_samples = sampling(feats(ss))
+        captured = False
+        if args.eager:
+            variables = [torch.nn.Parameter(v.clone()) for v in make_pyramid(stylized)]
+            loss_fn = S.StrotssLoss(style_samples, alpha)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         t_vgg = t_loss = 0.0
         last = None
@@ -217,64 +261,30 @@ def _run(args, content, style, sampling, feats_nchw, vgg_feats, max_iter):
                 t_vgg += ev[0].elapsed_time(ev[1])
                 t_loss += ev[1].elapsed_time(ev[2])
         else:
-            # pixel side on the library kernels: NHWC variables, fused fold (+ backward), one-launch RMSprop(0.99, 1e-8)
-            # (run_strotss.py:63,89,134,148); the update is part of the captured graph
-            variables = [v.clone().requires_grad_(True) for v in S.make_laplacian_pyramid(nhwc(stylized), 5)]
-            opt = S.RMSprop(rho=0.99, epsilon=1e-8, learning_rate=lr)
-            opt.build(variables)
-            idx = sampling._make_indices(content_feat[0], True)
-            static_idx = idx.clone()
-
-            def fold_pyramid(vs):
-                return S.fold_laplacian_pyramid(vs)
-
-            def feats(img):                      # img: (1, h, w, 3); its NCHW view is channels_last already
-                return [img] + [nhwc(f) for f in vgg_feats(img.permute(0, 3, 1, 2))]
-
-            def iteration():
-                img = fold_pyramid(variables)
-                pred = feats(img)
-                c_feat = sampling._sample(content_feat, static_idx, True)
-                p_feat = sampling._sample(pred, static_idx, True)
-                loss = loss_fn(c_feat, p_feat)
-                grads = torch.autograd.grad(loss, variables)
-                opt.apply_gradients(zip(grads, variables))
-                return loss
-
-            torch.cuda.synchronize()
+            key = (i, tuple(sc.shape), args.sample)
             t0 = time.perf_counter()
-            # one eager forward + backward without an update, so that cuDNN plans/workspaces and the library workspace
-            # exist before capture (no device allocation is allowed inside a capture)
-            img = fold_pyramid(variables)
-            pred = feats(img)
-            l0 = loss_fn(sampling._sample(content_feat, static_idx, True), sampling._sample(pred, static_idx, True))
-            torch.autograd.grad(l0, variables)
-            del img, pred, l0
+            runner = _SCALE_GRAPHS.get(key)
+            if runner is None:
+                runner = ScaleGraph(sampling, vgg_feats, content_feat, style_samples, nhwc(stylized), alpha, lr)
+                _SCALE_GRAPHS[key] = runner
+                captured = True
+            else:
+                runner.load(content_feat, style_samples, nhwc(stylized))
             torch.cuda.synchronize()
-            t_warm = time.perf_counter() - t0
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, pool=_graph_pool()):
-                static_loss = iteration()
-            torch.cuda.synchronize()
-            t_capture = time.perf_counter() - t0
-            base_cpu = torch.empty(content_feat[0].shape)          # shape carrier: indices are drawn on the host
-            nxt = None
-            for it in range(max_iter):
-                if nxt is not None:
-                    static_idx.copy_(nxt, non_blocking=True)
-                graph.replay()
-                nxt = sampling._make_indices(base_cpu, True).pin_memory()      # next iteration's draw, under the GPU work
-                last = float(static_loss.item())
+            t_warm, t_capture = 0.0, time.perf_counter() - t0
+            last = runner.run(max_iter)
+            variables = None
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         with torch.no_grad():
-            stylized = fold_pyramid(variables).detach()
-            if not args.eager:
-                stylized = stylized.permute(0, 3, 1, 2)
+            if args.eager:
+                stylized = fold_pyramid(variables).detach()
+            else:
+                stylized = runner.image().permute(0, 3, 1, 2)
         per_scale.append({"scale": scl, "content_hw": list(sc.shape[-2:]), "style_hw": list(ss.shape[-2:]), "alpha": alpha,
                           "seconds": dt, "ms_per_iter": dt / max_iter * 1e3, "setup_seconds": t0 - t_setup,
-                          "capture_seconds": (t_capture - t_warm if not args.eager else 0.0),
-                          "eager_first_iteration_seconds": (t_warm if not args.eager else 0.0),
+                          "graph_setup_seconds": (t_capture if not args.eager else 0.0),
+                          "graph_captured_in_this_pass": (captured if not args.eager else False),
                           "fold_vgg_fwd_ms_per_iter": t_vgg / max_iter,
                           "sample_loss_fwd_ms_per_iter": t_loss / max_iter, "last_loss": last})
         alpha /= 2.0
