@@ -319,6 +319,14 @@ int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     return 0;
 }
 
+// 16-wide MMA steps that carry data in the last 64-wide K block of a K extent of `k` real columns (0 = all four)
+int tail_steps(int k) {
+    static const bool off = (getenv("STROTSS_NO_KTAIL") != nullptr);
+    if (off) return 0;
+    const int rem = k % BK;
+    return rem == 0 ? 0 : ((rem + 15) / 16 == BK / 16 ? 0 : (rem + 15) / 16);
+}
+
 // rows per block of the column-partial kernels: at most `cap` (32), fewer when that leaves SMs without a block
 int rows_per_block(const strotss_ctx* h, int n, int cap, int mult) {
     int r = (n + 2 * h->num_sms - 1) / (2 * h->num_sms);
@@ -495,7 +503,7 @@ struct RemdState {
 
 // zeroed: rs.rowbest / rs.colbest were assigned and cleared by the caller (one memset for the whole evaluation)
 int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int N, Shard sh, int Dp, RemdState& rs,
-               float* ry_partial, cudaStream_t st, bool zeroed = false) {
+               float* ry_partial, cudaStream_t st, bool zeroed = false, int D_real = 0) {
     if (!zeroed) {
         RET(ensure(h, "remd.colbest", (size_t)N, &rs.colbest));
         CK(cudaMemsetAsync(rs.rowbest, 0, sizeof(unsigned long long) * M, st));
@@ -509,6 +517,7 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
         p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (sh.n() + 255) / 256;
         p.a_row0 = 0; p.b_row0 = sh.r0;
         p.epi.rowbest = rs.rowbest; p.epi.colbest = rs.colbest; p.epi.M = M; p.epi.N = sh.r1;
+        p.k_tail_steps = D_real > 0 ? tail_steps(D_real) : 0;
         PhaseTimer _pt(h, PH_REMD_GEMM, st);
         if (M <= 2048 && sh.n() <= 2048) {
             // few 256-wide tiles: 128 x 128 single-CTA tiles fill four times as many SMs
@@ -676,6 +685,7 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
             q.nseg = 1; q.seg_kblocks[0] = Dp / BK; q.seg_acc[0] = 0;
             q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (sh.n() + 255) / 256;
             q.a_row0 = 0; q.b_row0 = sh.r0;
+            q.k_tail_steps = tail_steps(D);
             q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = sh.r1; q.epi.alpha = 1.f; q.epi.col_off = sh.r0;
             RET((launch_gemm256<1>(h, q, st)));
         } else {
@@ -827,6 +837,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             sp.tmA[1] = p.tmA[0]; sp.tmB[1] = p.tmB[0];       // delta . x^T   -> acc0
             sp.tmA[2] = p.tmA[1]; sp.tmB[2] = p.tmB[1];       // y^ . delta^T  -> acc0
             sp.kblocks = Dp / BK;
+            sp.k_tail_steps = tail_steps(D);
             sp.tiles_m = p.tiles_m; sp.tiles_n = p.tiles_n; sp.a_row0 = p.a_row0; sp.b_row0 = p.b_row0;
             sp.epi = p.epi;
             {
@@ -1206,7 +1217,7 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaStreamWaitEvent(s_aux, h->ev_fork2, 0));
         CK(cudaStreamWaitEvent(s_mom, h->ev_fork2, 0));
     }
-    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, s_aux, true));
+    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, s_aux, true, D));
     if (par)
         RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, s_aux));
@@ -1503,7 +1514,7 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
     RET(prep_features(h, "fn.x", fx, x, ldx, M, D, Dp, w, nullptr, 0, st));
     RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, w, nullptr, 0, st));
     RemdState rs; rs.rowbest = best;
-    RET(remd_local(h, fx, M, fy, N, sh, Dp, rs, partials + PS_REMD_RY, st));
+    RET(remd_local(h, fx, M, fy, N, sh, Dp, rs, partials + PS_REMD_RY, st, false, D));
     RET(remd_finish(h, fx, M, N, sh, D, rs, partials + PS_REMD_RY, sc, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad,
                     row_argmin, col_argmin, st));
     if (want_grad) {

@@ -133,10 +133,12 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
                         const uint64_t bdesc = bmn ? make_mnmajor_sw128_desc(a_addr + Cfg::A_BYTES, Cfg::B_BYTES / 2)
                                                    : make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+                        const int ksteps = (p.k_tail_steps && kb == p.seg_kblocks[s] - 1) ? p.k_tail_steps : BK / 16;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,
-                                           ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
+                            if (k < ksteps)
+                                umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,
+                                               ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
                         touched |= (1u << acc);
                         umma_commit_2cta(&empty[stage], 3);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -49,6 +49,9 @@ struct GemmParams {
     int kb_lo_mul[kMaxSeg], kb_hi_mul[kMaxSeg];
     // B_MODE == 2 of the pair kernel: segment s reads its B operand MN-major (transposed) iff seg_bmn[s]
     int seg_bmn[kMaxSeg];
+    // CTA-pair kernel: number of 16-wide MMA steps that carry data in the LAST K block of a segment (0 = all four).  K is
+    // zero-padded to a multiple of 64 (D = 2179 -> 2240): the last block holds 3 real columns, so 3 of its 4 steps multiply zeros.
+    int k_tail_steps;
     typename Epi::Params epi;
 };
 

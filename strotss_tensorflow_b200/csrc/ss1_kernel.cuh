@@ -30,6 +30,7 @@ struct Ss1Params {
     CUtensorMap tmA[3];
     CUtensorMap tmB[3];          // segment 0: (y^, y^) -> acc1 ; 1: (delta, x^) -> acc0 ; 2: (y^, delta) -> acc0
     int kblocks;                 // K blocks per segment
+    int k_tail_steps;            // 16-wide MMA steps that carry data in the last K block (0 = all four; see GemmParams)
     int tiles_m, tiles_n, group_n;
     int tri;                     // always 0 here (decode_tile's triangular walk is used by the covariance kernel)
     int a_row0, b_row0;
@@ -152,8 +153,10 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
                         const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
                         const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + A_BYTES);
+                        const int ksteps = (p.k_tail_steps && kb == p.kblocks - 1) ? p.k_tail_steps : BK / 16;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
+                            if (k >= ksteps) break;
                             const uint32_t accum = ((s == 2) || kb > 0 || k > 0) ? 1u : 0u;
                             if constexpr (PAIR) umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
                             else umma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
