@@ -393,7 +393,7 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
     RET(ensure(h, "pred.mean", (size_t)D, &fx.mean));
     RET(ensure(h, "pred.sumhat", (size_t)D, &fx.sumhat));
     RET(ensure(h, "content.sumhat", (size_t)D, &fy.sumhat));
-    const int rpb = rows_per_block(h, n, kPrRowsPerBlock, kPrGroup);
+    const int rpb = rows_per_block(h, n, kPrRowsPerBlock, kPrGroup);      // 16 / 8 rows per block at N = 16384: 3 % / 8 % slower
     const int nblk = (n + rpb - 1) / rpb;
     float* part;
     RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
@@ -595,7 +595,10 @@ int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int
         // one pass: queries = all target rows (row minima), keys = this rank's prediction rows (column minima)
         const int nq = M, nk = sh.n();
         const int qblocks = (nq + kPalThreads * kPalQT - 1) / (kPalThreads * kPalQT);
-        int ks = (4 * h->num_sms + qblocks - 1) / qblocks;
+        // blocks per SM the key range is split for: 16 x 4 warps fill the SM (ncu: 4 per SM leave 19.5 % of the warp slots
+        // active and the dependent FMA / redux chains exposed); measured 0.326 -> 0.268 ms
+        static const int pal_bps = getenv("STROTSS_PAL_BPS") ? atoi(getenv("STROTSS_PAL_BPS")) : 16;
+        int ks = (pal_bps * h->num_sms + qblocks - 1) / qblocks;
         const int maxks = (nk + kPalKeyTile - 1) / kPalKeyTile;
         if (ks > maxks) ks = maxks;
         if (ks < 1) ks = 1;
