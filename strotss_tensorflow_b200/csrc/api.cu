@@ -329,7 +329,7 @@ int tail_steps(int k) {
 
 // rows per block of the column-partial kernels: at most `cap` (32), fewer when that leaves SMs without a block
 int rows_per_block(const strotss_ctx* h, int n, int cap, int mult) {
-    int r = (n + 2 * h->num_sms - 1) / (2 * h->num_sms);
+    int r = (n + 2 * h->num_sms - 1) / (2 * h->num_sms);      // 4 blocks per SM: row pass -5 %, column-sum pass +10 % (a wash)
     r = (r + mult - 1) / mult * mult;
     if (r < mult) r = mult;
     if (r > cap) r = cap;
@@ -985,7 +985,9 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
 int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) {
     if (nrows <= 0) return 0;
     PhaseTimer _pt(h, PH_FINALIZE, st);
-    finalize_grad_kernel<<<nrows, 256, sizeof(float) * a.D, st>>>(a);
+    static const bool generic = (getenv("STROTSS_FINALIZE_GENERIC") != nullptr);
+    if (a.D <= kFinU * 256 && !generic) finalize_grad_1b_kernel<<<nrows, 256, 0, st>>>(a);
+    else finalize_grad_kernel<<<nrows, 256, sizeof(float) * a.D, st>>>(a);
     CKL();
     return 0;
 }

@@ -840,6 +840,81 @@ struct FinalizeArgs {
 // with one load group per loop iteration the kernel is latency-bound (ncu: 80 % long-scoreboard stalls).
 constexpr int kFinU = 9;                    // 9 x 256 = 2304 >= 2179: one batch per row at the reference's width
 
+// Single-batch variant (D <= kFinU * 256, i.e. every width up to 2304 incl. the reference's 2179): each thread keeps its nine
+// elements of the row in registers across the block reduction and fetches the moment-matching row Q together with the other
+// operands, so a block pays one global-memory latency instead of two.
+__global__ void __launch_bounds__(256) finalize_grad_1b_kernel(const FinalizeArgs a) {
+    __shared__ float sh[8];
+    __shared__ float sh2[8];
+    __shared__ float s_dot;
+    const int li = blockIdx.x;
+    const int i = a.r0 + li;
+    const float* xr = a.x + static_cast<long long>(i) * a.ldx;
+    const float iv = a.inv[i];
+    const float invN = 1.f / static_cast<float>(a.N);
+    const float ci = a.ss2 ? a.coef[i] : 0.f;
+    const bool remd_gather = a.gremd && a.scalars[a.slot_branch] == 0.f;
+    const float* g2 = nullptr; float g2s = 0.f;
+    if (a.gremd) {
+        if (remd_gather) {
+            const int it = static_cast<int>(best_idx(a.remd_colbest[i]));
+            g2 = a.remd_xs + static_cast<long long>(it) * a.remd_ldxs;
+            g2s = -a.remd_inv_s[it] * invN * a.w_remd;
+        } else {
+            g2 = a.gremd + static_cast<long long>(li) * a.ld_gremd;
+            g2s = a.w_remd;
+        }
+    }
+    const float* s2 = a.ss2 ? a.ss2 + static_cast<long long>(li) * a.ld_ss2 : nullptr;
+    const float* qr = a.Q ? a.Q + static_cast<long long>(li) * a.ldq : nullptr;
+    const float wss = a.w_ss;
+    float v_x[kFinU], v_g[kFinU], v_q[kFinU];
+    {
+        float v_s2[kFinU], v_g2[kFinU];
+#pragma unroll
+        for (int k = 0; k < kFinU; ++k) {
+            const int d = threadIdx.x + 256 * k;
+            const bool ok = d < a.D;
+            v_x[k] = ok ? xr[d] : 0.f;
+            v_s2[k] = (ok && s2) ? s2[d] : 0.f;
+            v_g2[k] = (ok && g2) ? g2[d] : 0.f;
+            v_q[k] = (ok && qr) ? qr[d] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kFinU; ++k) {
+            const int d = threadIdx.x + 256 * k;
+            const bool ok = d < a.D;
+            const float vv = (ok && s2) ? a.v[d] : 0.f;
+            const float vs = (ok && s2) ? a.sumhat[d] : 0.f;
+            v_g[k] = ok ? wss * (-v_s2[k] * invN + vv + ci * vs) + g2s * v_g2[k] : 0.f;
+        }
+    }
+    float dot = 0.f, ssq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFinU; ++k) { dot = fmaf(v_g[k], v_x[k], dot); ssq = fmaf(v_x[k], v_x[k], ssq); }
+    dot = warp_sum(dot); ssq = warp_sum(ssq);
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = dot; sh2[threadIdx.x >> 5] = ssq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f, q = 0.f;
+        for (int k = 0; k < 8; ++k) { t += sh[k]; q += sh2[k]; }
+        s_dot = (q >= kL2NEps) ? t * iv * iv * iv : 0.f;
+    }
+    __syncthreads();
+    const float pd = s_dot;
+    float* gr = a.grad + static_cast<long long>(i) * a.ldg;
+#pragma unroll
+    for (int k = 0; k < kFinU; ++k) {
+        const int d = threadIdx.x + 256 * k;
+        if (d < a.D) {
+            float o = v_g[k] * iv - v_x[k] * pd;
+            if (qr) o += a.w_mom * (a.q_scale * v_q[k] + a.gmu[d] * invN);
+            if (a.gpal && d < 3) o += a.w_pal * a.gpal[static_cast<long long>(li) * 4 + d];
+            gr[d] = o;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a) {
     extern __shared__ float sg[];       // D floats: g^
     __shared__ float sh[8];
