@@ -28,6 +28,14 @@ def _check_features(name: str, t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """Row-major (n, C) view the C ABI can read in place: unit column stride, any row stride >= C (a column slice of a wider
+    matrix is passed with its own `ld` instead of being copied)."""
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t.contiguous()
+
+
 def reshape_2d(x: torch.Tensor, channel_axis: int = -1) -> torch.Tensor:
     """nn/losses.py:31-36: squeeze, then reshape to (-1, C).  (The rank test at :32 never fires.)"""
     x = torch.squeeze(x)
@@ -103,22 +111,22 @@ class Handle:
 
     # ---- fused path -----------------------------------------------------------------
     def set_style_target(self, style: torch.Tensor):
-        style = _check_features("style target", reshape_2d(style)).contiguous()
+        style = _rows(_check_features("style target", reshape_2d(style)))
         M, D = style.shape
         self._ck(self.lib.strotss_set_style_target(self._h, _ptr(style), M, D, style.stride(0), _stream(style.device)),
                  "strotss_set_style_target")
         self.style_shape = (M, D)
 
     def eval(self, pred: torch.Tensor, content: torch.Tensor, alpha: float, want_grad: bool = True, want_argmin: bool = False):
-        pred = _check_features("prediction", reshape_2d(pred)).contiguous()
-        content = _check_features("content", reshape_2d(content)).contiguous()
+        pred = _rows(_check_features("prediction", reshape_2d(pred)))
+        content = _rows(_check_features("content", reshape_2d(content)))
         if pred.shape != content.shape:
             raise ValueError(f"prediction {tuple(pred.shape)} and content {tuple(content.shape)} must have the same shape")
         N, D = pred.shape
         if self.style_shape is None or self.style_shape[1] != D:
             raise ValueError("style target not set or feature width differs from the prediction's")
         scalars = torch.empty(_lib.NUM_SCALARS, device=pred.device, dtype=torch.float32)
-        grad = torch.empty_like(pred) if want_grad else None
+        grad = torch.empty(N, D, device=pred.device, dtype=torch.float32) if want_grad else None
         ra = torch.empty(self.style_shape[0], device=pred.device, dtype=torch.int32) if want_argmin else None
         ca = torch.empty(N, device=pred.device, dtype=torch.int32) if want_argmin else None
         self._ck(self.lib.strotss_eval(self._h, _ptr(pred), pred.stride(0), _ptr(content), content.stride(0), N, float(alpha),

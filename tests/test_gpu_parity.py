@@ -308,6 +308,25 @@ def test_modules_match_reference_wrappers(S, cuda_device, alpha):
     _gcheck(p2.grad, gref, cos_min=0.99)
 
 
+def test_row_strides_are_honoured(S, cuda_device):
+    """Inputs may be column slices of wider matrices (row stride > D): the C ABI takes `ld` and must give bit-identical
+    results to the packed copies."""
+    st, co, pr = O.synth_problem(333, 200, 67, eps=0.1, seed=77)
+    def wide(a, pad):
+        buf = torch.full((a.shape[0], a.shape[1] + pad), 7.5, device=cuda_device, dtype=torch.float32)
+        buf[:, :a.shape[1]] = _t(a, cuda_device)
+        return buf[:, :a.shape[1]]
+    h1, h2 = S.Handle(cuda_device), S.Handle(cuda_device)
+    h1.set_style_target(_t(st, cuda_device))
+    sw = wide(st, 5)
+    assert not sw.is_contiguous()
+    h2.set_style_target(sw)
+    s1, g1, ra1, ca1 = h1.eval(_t(pr, cuda_device), _t(co, cuda_device), 4.0, True, True)
+    s2, g2, ra2, ca2 = h2.eval(wide(pr, 13), wide(co, 3), 4.0, True, True)
+    assert torch.equal(s1[:12], s2[:12]) and torch.equal(ra1, ra2) and torch.equal(ca1, ca2)
+    assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-10)          # the scatter branch of the relaxed EMD uses float atomics
+
+
 def test_wide_features_take_the_general_preparation_path(S, cuda_device):
     """D > 2560 exceeds the fused row pass (10 columns per thread) and must fall back, not fail."""
     st, co, pr = O.synth_problem(200, 180, 2700, eps=0.1, seed=51)
