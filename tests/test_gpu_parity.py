@@ -327,6 +327,31 @@ def test_row_strides_are_honoured(S, cuda_device):
     assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-10)          # the scatter branch of the relaxed EMD uses float atomics
 
 
+def test_evaluation_is_cuda_graph_capturable(S, cuda_device):
+    """After one warm-up call at a given size no entry point allocates or synchronises, and the branch streams fork from /
+    join to the caller's stream: an evaluation can be captured into the caller's CUDA graph and replayed on new data."""
+    st, co, pr = O.synth_problem(384, 300, 2179, eps=0.1, seed=91)
+    h = S.Handle(cuda_device)
+    h.set_style_target(_t(st, cuda_device))
+    pred, content = _t(pr, cuda_device), _t(co, cuda_device)
+    want, gwant, _, _ = h.eval(pred, content, 8.0, True)                   # warm-up: workspace growth
+    want, gwant = want.clone(), gwant.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        sc, grad, _, _ = h.eval(pred, content, 8.0, True)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(sc[:12], want[:12])
+    assert torch.allclose(grad, gwant, rtol=1e-5, atol=1e-10)
+    # new data in the captured buffers
+    _, co2, pr2 = O.synth_problem(384, 300, 2179, eps=0.3, seed=92)
+    pred.copy_(_t(pr2, cuda_device)); content.copy_(_t(co2, cuda_device))
+    graph.replay()
+    torch.cuda.synchronize()
+    ref = O.total_loss(st, co2, pr2, 8.0, np.float64)
+    assert abs(sc[0].item() - ref) / ref <= LOSS_RTOL
+
+
 def test_wide_features_take_the_general_preparation_path(S, cuda_device):
     """D > 2560 exceeds the fused row pass (10 columns per thread) and must fall back, not fail."""
     st, co, pr = O.synth_problem(200, 180, 2700, eps=0.1, seed=51)
