@@ -393,21 +393,37 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
     RET(ensure(h, "pred.mean", (size_t)D, &fx.mean));
     RET(ensure(h, "pred.sumhat", (size_t)D, &fx.sumhat));
     RET(ensure(h, "content.sumhat", (size_t)D, &fy.sumhat));
-    const int rpb = rows_per_block(h, n, kPrRowsPerBlock, kPrGroup);      // 16 / 8 rows per block at N = 16384: 3 % / 8 % slower
-    const int nblk = (n + rpb - 1) / rpb;
-    float* part;
-    RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
-    const int smem = 2 * kPrGroup * Dp * (int)sizeof(float);
+    static const bool prep_v1 = (getenv("STROTSS_PREP_V1") != nullptr);
     static bool configured = false;
     if (!configured) {
         CK(cudaFuncSetAttribute(prep_pair_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPrGroup * 2560 * (int)sizeof(float)));
         CK(cudaFuncSetAttribute(prep_pair_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(prep_pair_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPrGroup * 2560 * (int)sizeof(float)));
+        CK(cudaFuncSetAttribute(prep_pair_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    prep_pair_rows_kernel<<<nblk, 256, smem, st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh, fy.xh, fx.dlt, part, rpb);
-    CKL();
-    colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
-    CKL();
+    float* part;
+    if (prep_v1) {
+        const int rpb = rows_per_block(h, n, kPrRowsPerBlock, kPrGroup);      // 16 / 8 rows per block at N = 16384: 3 % / 8 % slower
+        const int nblk = (n + rpb - 1) / rpb;
+        RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
+        prep_pair_rows_kernel<<<nblk, 256, 2 * kPrGroup * Dp * (int)sizeof(float), st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh,
+                                                                                       fy.xh, fx.dlt, part, rpb);
+        CKL();
+        colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+        CKL();
+    } else {
+        // double-buffered row pass: 72 KB of staging per block, three blocks per SM, one wave of blocks
+        int rpb = round_up((n + 3 * h->num_sms - 1) / (3 * h->num_sms), kPrGroup);
+        if (rpb < kPrGroup) rpb = kPrGroup;
+        const int nblk = (n + rpb - 1) / rpb;
+        RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
+        prep_pair_rows2_kernel<<<nblk, 256, 4 * kPrGroup * Dp * (int)sizeof(float), st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh,
+                                                                                        fy.xh, fx.dlt, part, rpb);
+        CKL();
+        colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+        CKL();
+    }
     EmitArgs a{};
     a.x = x; a.ldx = ldx; a.n = n; a.D = D; a.Dp = Dp; a.np = fx.np; a.inv = fx.inv; a.mean = fx.mean;
     if (want_grad) {

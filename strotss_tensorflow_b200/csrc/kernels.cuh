@@ -278,6 +278,116 @@ __global__ void __launch_bounds__(256, 4) prep_pair_rows_kernel(const float* __r
     }
 }
 
+// Double-buffered variant: the next group's rows are fetched with cp.async (4-byte LDGSTS, the rows are only 4-byte aligned)
+// while the current group is normalised, emitted and column-summed, so every block always has a 36 KB load in flight and the
+// three barriers per group no longer serialise memory latency with arithmetic.  Same outputs, same summation order.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 3) prep_pair_rows2_kernel(const float* __restrict__ x, long long ldx,
+                                                                 const float* __restrict__ y, long long ldy, int n, int D, int Dp,
+                                                                 float* __restrict__ inv_x, float* __restrict__ inv_y,
+                                                                 __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ yh,
+                                                                 __nv_bfloat16* __restrict__ dlt, float* __restrict__ part,
+                                                                 int rows_per_block) {
+    extern __shared__ float sm[];          // [2 buffers][x | y][kPrGroup][Dp]
+    __shared__ float s_inv[2][kPrGroup];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row_base = blockIdx.x * rows_per_block;
+    const int buf_floats = 2 * kPrGroup * Dp;
+    constexpr int kMaxCols = 10;
+    float ax[kMaxCols], ahx[kMaxCols], ahy[kMaxCols];
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c) { ax[c] = 0.f; ahx[c] = 0.f; ahy[c] = 0.f; }
+    // K padding columns stay zero in both buffers for the whole kernel
+    for (int e = threadIdx.x; e < 2 * 2 * kPrGroup * (Dp - D); e += 256) {
+        const int vec = e / (Dp - D), d = D + e % (Dp - D);
+        sm[vec * Dp + d] = 0.f;
+    }
+    auto fetch = [&](int g, int b) {
+        float* sx = sm + b * buf_floats;
+        float* sy = sx + kPrGroup * Dp;
+#pragma unroll
+        for (int rr = 0; rr < kPrGroup; ++rr) {
+            const int r = row_base + g + rr;
+            if (r < n) {
+                const float* xr = x + static_cast<long long>(r) * ldx;
+                const float* yr = y + static_cast<long long>(r) * ldy;
+#pragma unroll 3
+                for (int d = threadIdx.x; d < D; d += 256) {
+                    cp_async4(sx + rr * Dp + d, xr + d);
+                    cp_async4(sy + rr * Dp + d, yr + d);
+                }
+            } else {
+                for (int d = threadIdx.x; d < D; d += 256) { sx[rr * Dp + d] = 0.f; sy[rr * Dp + d] = 0.f; }
+            }
+        }
+        cp_async_commit();
+    };
+    fetch(0, 0);
+    int b = 0;
+    for (int g = 0; g < rows_per_block; g += kPrGroup, b ^= 1) {
+        if (g + kPrGroup < rows_per_block) { fetch(g + kPrGroup, b ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();                    // group g landed (and the padding zeros of the first iteration)
+        const float* sx = sm + b * buf_floats;
+        const float* sy = sx + kPrGroup * Dp;
+        if (warp < 2 * kPrGroup) {
+            const float* src = (warp < kPrGroup) ? sx + warp * Dp : sy + (warp - kPrGroup) * Dp;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int d = lane;
+            for (; d + 96 < Dp; d += 128) {
+                const float v0 = src[d], v1 = src[d + 32], v2 = src[d + 64], v3 = src[d + 96];
+                s0 = fmaf(v0, v0, s0); s1 = fmaf(v1, v1, s1); s2 = fmaf(v2, v2, s2); s3 = fmaf(v3, v3, s3);
+            }
+            for (; d < Dp; d += 32) { const float v = src[d]; s0 = fmaf(v, v, s0); }
+            const float ss = warp_sum((s0 + s1) + (s2 + s3));
+            if (lane == 0) s_inv[warp / kPrGroup][warp % kPrGroup] = rsqrtf(fmaxf(ss, kL2NEps));
+        }
+        __syncthreads();
+        {
+            constexpr int kWarpsPerRow = 8 / kPrGroup;
+            const int rr = warp / kWarpsPerRow, sub = warp % kWarpsPerRow;
+            const int r = row_base + g + rr;
+            if (r < n) {
+                const float ix = s_inv[0][rr], iy = s_inv[1][rr];
+                if (lane == 0 && sub == 0) { inv_x[r] = ix; inv_y[r] = iy; }
+                const long long off = static_cast<long long>(r) * Dp;
+                for (int d = sub * 64 + 2 * lane; d < Dp; d += 64 * kWarpsPerRow) {
+                    const float x0 = sx[rr * Dp + d] * ix, x1 = sx[rr * Dp + d + 1] * ix;
+                    const float y0 = sy[rr * Dp + d] * iy, y1 = sy[rr * Dp + d + 1] * iy;
+                    *reinterpret_cast<uint32_t*>(xh + off + d) = pack_bf16x2(x0, x1);
+                    *reinterpret_cast<uint32_t*>(yh + off + d) = pack_bf16x2(y0, y1);
+                    *reinterpret_cast<uint32_t*>(dlt + off + d) = pack_bf16x2(x0 - y0, x1 - y1);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+            const int d = threadIdx.x + c * 256;
+            if (d < D) {
+#pragma unroll
+                for (int rr = 0; rr < kPrGroup; ++rr) {
+                    const float xv = sx[rr * Dp + d], yv = sy[rr * Dp + d];
+                    ax[c] += xv;
+                    ahx[c] = fmaf(xv, s_inv[0][rr], ahx[c]);
+                    ahy[c] = fmaf(yv, s_inv[1][rr], ahy[c]);
+                }
+            }
+        }
+        __syncthreads();                    // buffer b is free for the fetch issued in the next iteration
+    }
+    float* pb = part + static_cast<long long>(blockIdx.x) * 3 * D;
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c) {
+        const int d = threadIdx.x + c * 256;
+        if (d < D) { pb[d] = ax[c]; pb[D + d] = ahx[c]; pb[2 * D + d] = ahy[c]; }
+    }
+}
+
 // out[q][d] = scale_q * sum_b part[b][q][d] for the three sums of prep_pair_rows_kernel (fixed order)
 __global__ void __launch_bounds__(256) colsum3_finish_kernel(const float* __restrict__ part, int nblocks, int D,
                                                              float scale0, float* __restrict__ out0,
