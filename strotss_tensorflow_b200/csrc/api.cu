@@ -431,7 +431,13 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
         RET(ensure(h, "pred.xhT", (size_t)D * fx.np, &fx.xhT)); a.xhT = fx.xhT;
     }
     RET(ensure(h, "pred.cenT", (size_t)D * fx.np, &fx.cenT)); a.cenT = fx.cenT;
-    emit_operands_kernel<<<dim3(Dp / 64, fx.np / 64), 256, 0, st>>>(a);
+    if (prep_v1) {
+        emit_operands_kernel<<<dim3(Dp / 64, fx.np / 64), 256, 0, st>>>(a);
+    } else {
+        const int tx = Dp / 64, ty = fx.np / 64;
+        const int grid = tx * ty < 5 * h->num_sms ? tx * ty : 5 * h->num_sms;
+        emit_operands2_kernel<<<grid, 256, 0, st>>>(a, tx, ty);
+    }
     CKL();
     return 0;
 }

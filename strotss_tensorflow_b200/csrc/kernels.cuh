@@ -117,6 +117,81 @@ struct EmitArgs {
     __nv_bfloat16* xhT; __nv_bfloat16* cenT;
 };
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Persistent, double-buffered variant for the calls without a delta operand (the fused evaluation): every block walks the
+// 64 x 64 tiles with stride gridDim.x and fetches its next tile with cp.async while it converts and stores the current one.
+__global__ void __launch_bounds__(256) emit_operands2_kernel(const EmitArgs a, int tiles_x, int tiles_y) {
+    __shared__ float sx[2][64][65];
+    __shared__ float s_inv[2][64], s_mean[2][64];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int ntiles = tiles_x * tiles_y;
+    auto fetch = [&](int t, int b) {
+        const int col0 = (t % tiles_x) * 64, row0 = (t / tiles_x) * 64;
+        if (threadIdx.x < 64) {
+            const int r = row0 + threadIdx.x;
+            s_inv[b][threadIdx.x] = (r < a.n) ? a.inv[r] : 0.f;
+            const int c = col0 + threadIdx.x;
+            s_mean[b][threadIdx.x] = (a.mean && c < a.D) ? a.mean[c] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = grp * 8 + i, r = row0 + rr;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = lane + 32 * h, c = col0 + cc;
+                if (r < a.n && c < a.D) cp_async4(&sx[b][rr][cc], a.x + static_cast<long long>(r) * a.ldx + c);
+                else sx[b][rr][cc] = 0.f;
+            }
+        }
+        cp_async_commit();
+    };
+    int t = blockIdx.x, b = 0;
+    if (t < ntiles) fetch(t, 0);
+    for (; t < ntiles; t += gridDim.x, b ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) { fetch(tn, b ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const int col0 = (t % tiles_x) * 64, row0 = (t / tiles_x) * 64;
+        for (int rr = grp * 8; rr < grp * 8 + 8; ++rr) {
+            const int r = row0 + rr;
+            if (r >= a.n) continue;
+            const int cc = 2 * lane, c = col0 + cc;
+            const float x0 = sx[b][rr][cc], x1 = sx[b][rr][cc + 1];
+            const float iv = s_inv[b][rr];
+            const long long off = static_cast<long long>(r) * a.Dp + c;
+            if (a.xh) *reinterpret_cast<uint32_t*>(a.xh + off) = pack_bf16x2(x0 * iv, x1 * iv);
+            if (a.cen) {
+                const float c0 = (c < a.D) ? x0 - s_mean[b][cc] : 0.f;
+                const float c1 = (c + 1 < a.D) ? x1 - s_mean[b][cc + 1] : 0.f;
+                *reinterpret_cast<uint32_t*>(a.cen + off) = pack_bf16x2(c0, c1);
+            }
+        }
+        if (a.xhT || a.cenT) {
+            for (int cc = grp * 8; cc < grp * 8 + 8; ++cc) {
+                const int c = col0 + cc;
+                if (c >= a.D) continue;
+                const int rr = 2 * lane, r = row0 + rr;
+                if (r >= a.np) continue;
+                const long long off = static_cast<long long>(c) * a.np + r;
+                if (a.xhT)
+                    *reinterpret_cast<uint32_t*>(a.xhT + off) = pack_bf16x2(sx[b][rr][cc] * s_inv[b][rr], sx[b][rr + 1][cc] * s_inv[b][rr + 1]);
+                if (a.cenT) {
+                    const float m = s_mean[b][cc];
+                    const float c0 = (r < a.n) ? sx[b][rr][cc] - m : 0.f;
+                    const float c1 = (r + 1 < a.n) ? sx[b][rr + 1][cc] - m : 0.f;
+                    *reinterpret_cast<uint32_t*>(a.cenT + off) = pack_bf16x2(c0, c1);
+                }
+            }
+        }
+        __syncthreads();                    // buffer b may be refilled by the fetch of the next iteration
+    }
+}
+
 __global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
     __shared__ float sx[64][65];
     __shared__ float sy[64][65];
@@ -281,11 +356,6 @@ __global__ void __launch_bounds__(256, 4) prep_pair_rows_kernel(const float* __r
 // Double-buffered variant: the next group's rows are fetched with cp.async (4-byte LDGSTS, the rows are only 4-byte aligned)
 // while the current group is normalised, emitted and column-summed, so every block always has a 36 KB load in flight and the
 // three barriers per group no longer serialise memory latency with arithmetic.  Same outputs, same summation order.
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(256, 3) prep_pair_rows2_kernel(const float* __restrict__ x, long long ldx,
                                                                  const float* __restrict__ y, long long ldy, int n, int D, int Dp,
