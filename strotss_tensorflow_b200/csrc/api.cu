@@ -555,9 +555,11 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
             RET((launch_gemm256<1, 8>(h, p, st)));
         }
     }
-    PhaseTimer _pm(h, PH_REMD_MISC, st);
-    best_partial_kernel<<<1, 1024, 0, st>>>(rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
-    CKL();
+    if (ry_partial) {                     // null on a single GPU: remd_finish sums the column minima itself
+        PhaseTimer _pm(h, PH_REMD_MISC, st);
+        best_partial_kernel<<<1, 1024, 0, st>>>(rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
+        CKL();
+    }
     return 0;
 }
 
@@ -636,8 +638,10 @@ int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int
             pal_min2_kernel<0><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
         CKL();
     }
-    best_partial_kernel<<<1, 1024, 0, st>>>(ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
-    CKL();
+    if (ry_partial) {
+        best_partial_kernel<<<1, 1024, 0, st>>>(ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
+        CKL();
+    }
     return 0;
 }
 
@@ -1212,14 +1216,18 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     // regions) are latency-bound chains of short kernels: there the independent terms run as parallel branches.
     const bool exch = sharded && h->world > 1 && h->nccl_comm;
     const bool par = h->opt_branches != 0 && !exch && N <= h->branch_max_n && M <= h->branch_max_n && st != h->side && st != h->aux;
+    // only a communicator needs the column sums as separate partials (they are summed over ranks); otherwise the finish
+    // kernels reduce the column minima themselves
+    float* ry_remd = exch ? partials + PS_REMD_RY : nullptr;
+    float* ry_pal = exch ? partials + PS_PAL_RY : nullptr;
     cudaStream_t s_pal = par ? h->side : st, s_aux = par ? h->aux : st, s_mom = par ? h->aux2 : st;
     if (par) {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(s_pal, h->ev_fork, 0));
     }
-    RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, partials + PS_PAL_RY, s_pal, true));
+    RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, ry_pal, s_pal, true));
     if (par) {
-        RET(pal_finish(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
+        RET(pal_finish(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, 1, ps, ry_pal, scalars, S_LPAL, S_PAL_RX,
                        S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, s_pal, pal_g));
         CK(cudaEventRecord(h->ev_join, s_pal));
     }
@@ -1244,9 +1252,9 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaStreamWaitEvent(s_aux, h->ev_fork2, 0));
         CK(cudaStreamWaitEvent(s_mom, h->ev_fork2, 0));
     }
-    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, partials + PS_REMD_RY, s_aux, true, D));
+    RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, ry_remd, s_aux, true, D));
     if (par)
-        RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
+        RET(remd_finish(h, h->style, M, N, sh, D, rs, ry_remd, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, s_aux));
     if (par) CK(cudaEventRecord(h->ev_join2, s_aux));
     RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_mom, mom_part));
@@ -1259,9 +1267,9 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaStreamWaitEvent(st, h->ev_join3, 0));
     } else {
         if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
-        RET(remd_finish(h, h->style, M, N, sh, D, rs, partials + PS_REMD_RY, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
+        RET(remd_finish(h, h->style, M, N, sh, D, rs, ry_remd, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, st));
-        RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, partials + PS_PAL_RY, scalars, S_LPAL, S_PAL_RX,
+        RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, ry_pal, scalars, S_LPAL, S_PAL_RX,
                        S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st, pal_g));
     }
     combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom,
@@ -1521,8 +1529,8 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
         RET(prep_features(h, "fn.x", fx, x, ldx, M, D, round_up(D, BK), w, nullptr, 0, st));
         RET(prep_features(h, "fn.y", fy, y, ldy, N, D, round_up(D, BK), w, nullptr, 0, st));
         PalState ps; ps.rowbest = best;
-        RET(pal_local(h, fx.srec, M, fy.srec, N, sh, distance, ps, partials + PS_PAL_RY, st));
-        RET(pal_finish(h, fx.rec, M, fy.rec, N, sh, distance, 0, ps, partials + PS_PAL_RY, sc, S_LPAL, S_PAL_RX, S_PAL_RY,
+        RET(pal_local(h, fx.srec, M, fy.srec, N, sh, distance, ps, nullptr, st));
+        RET(pal_finish(h, fx.rec, M, fy.rec, N, sh, distance, 0, ps, nullptr, sc, S_LPAL, S_PAL_RX, S_PAL_RY,
                        S_PAL_BRANCH, want_grad, row_argmin, col_argmin, st));
         if (want_grad) {
             CK(cudaMemcpy2DAsync(grad_y, sizeof(float) * ld_grad, ps.g, sizeof(float) * 4, sizeof(float) * 3, N,
@@ -1541,8 +1549,8 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
     RET(prep_features(h, "fn.x", fx, x, ldx, M, D, Dp, w, nullptr, 0, st));
     RET(prep_features(h, "fn.y", fy, y, ldy, N, D, Dp, w, nullptr, 0, st));
     RemdState rs; rs.rowbest = best;
-    RET(remd_local(h, fx, M, fy, N, sh, Dp, rs, partials + PS_REMD_RY, st, false, D));
-    RET(remd_finish(h, fx, M, N, sh, D, rs, partials + PS_REMD_RY, sc, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad,
+    RET(remd_local(h, fx, M, fy, N, sh, Dp, rs, nullptr, st, false, D));
+    RET(remd_finish(h, fx, M, N, sh, D, rs, nullptr, sc, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH, want_grad,
                     row_argmin, col_argmin, st));
     if (want_grad) {
         FinalizeArgs a{};

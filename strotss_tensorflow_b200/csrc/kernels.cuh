@@ -601,22 +601,27 @@ __global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long l
                                                            int* __restrict__ row_arg,
                                                            const unsigned long long* __restrict__ colbest, int r0, int r1,
                                                            int* __restrict__ col_arg) {
-    __shared__ float sh[32];
-    float a = 0.f;
+    // ry_sum == nullptr (single GPU): the column sum is taken here as well, over colbest[r0, r1) == all N columns
+    __shared__ float sh[32], shb[32];
+    float a = 0.f, b = 0.f;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         const unsigned long long k = rowbest[i];
         a += offset - best_val(k);
         if (row_arg) row_arg[i] = static_cast<int>(best_idx(k));
     }
-    if (col_arg)
-        for (int j = r0 + threadIdx.x; j < r1; j += blockDim.x) col_arg[j] = static_cast<int>(best_idx(colbest[j]));
-    a = warp_sum(a);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    if (col_arg || !ry_sum)
+        for (int j = r0 + threadIdx.x; j < r1; j += blockDim.x) {
+            const unsigned long long k = colbest[j];
+            if (!ry_sum) b += offset - best_val(k);
+            if (col_arg) col_arg[j] = static_cast<int>(best_idx(k));
+        }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = a; shb[threadIdx.x >> 5] = b; }
     __syncthreads();
     if (threadIdx.x < 32) {
-        float aa = warp_sum(sh[threadIdx.x]);
+        const float aa = warp_sum(sh[threadIdx.x]), bb = warp_sum(shb[threadIdx.x]);
         if (threadIdx.x == 0) {
-            const float rx = aa / static_cast<float>(M), ry = *ry_sum / static_cast<float>(N);
+            const float rx = aa / static_cast<float>(M), ry = (ry_sum ? *ry_sum : bb) / static_cast<float>(N);
             scalars[slot_rx] = rx; scalars[slot_ry] = ry;
             scalars[slot_loss] = fmaxf(rx, ry);
             scalars[slot_branch] = (rx >= ry) ? 1.f : 0.f;
