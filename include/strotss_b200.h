@@ -114,8 +114,9 @@ int strotss_eval(strotss_handle h, const float* pred, long long ld_pred, const f
  * scalars: device float[STROTSS_NUM_SCALARS], every slot the mean over regions (TOTAL, LOSS_C, LOSS_S are the three
  * values train_step returns, :123-125).  region_scalars: optional device float[R][STROTSS_NUM_SCALARS].
  * grad_pred: device (sum_r N_r) x D or NULL; rows of region r receive d loss / d pred_r (including the 1/R).
- * The regions are enqueued one after the other on `stream` (each one as a branch-parallel launch sequence); every
- * region has its own workspace, so N_r may change freely between calls.  Single GPU only. */
+ * Region 0 is enqueued on `stream` by the calling thread, regions 1..R-1 by library-owned launching threads on per-region
+ * streams forked from / joined to `stream` (the first call after new targets, and any call during stream capture, stay on the
+ * calling thread); every region has its own workspace, so N_r may change freely between calls.  Single GPU only. */
 int strotss_set_style_targets_grouped(strotss_handle h, const float* style, long long ld, const int* offsets_M, int R, int D,
                                       void* stream);
 int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred, const float* content, long long ld_content,

@@ -8,6 +8,10 @@
 #include <vector>
 #include <map>
 #include <dlfcn.h>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 
 #include "../../include/strotss_b200.h"
 #include "gemm_core.cuh"
@@ -83,6 +87,42 @@ struct Feat {
     float* srec = nullptr;      // palette records for the candidate search
 };
 
+// One launching thread per extra region of a grouped (masked) evaluation: a small evaluation is bound by the host thread
+// that enqueues its ~30 launches, so R regions are enqueued by R threads in parallel (each on its region's own stream).
+struct RegionWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool pending = false, stop = false;
+    RegionWorker() : th([this] { loop(); }) {}
+    ~RegionWorker() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        th.join();
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [this] { return pending || stop; });
+            if (stop) return;
+            lk.unlock();
+            job();
+            lk.lock();
+            pending = false;
+            cv.notify_all();
+        }
+    }
+    void post(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(m); job = std::move(f); pending = true; }
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return !pending; });
+    }
+};
+
 struct strotss_ctx {
     int device = 0;
     int num_sms = 148;
@@ -131,8 +171,11 @@ struct strotss_ctx {
     // masked (region-guided) transfer: one child context per region (own workspace, own style target, own stream)
     std::vector<strotss_ctx*> regions;
     float* region_scalars = nullptr;      // [R][STROTSS_NUM_SCALARS] device block owned by the parent
+    std::vector<RegionWorker*> workers;   // launching threads for regions 1..R-1
+    bool group_warm = false;              // the first grouped evaluation after new targets runs on the calling thread
 
     ~strotss_ctx() {
+        for (auto* w : workers) delete w;
         for (auto* c : regions) delete c;
         for (int i = 0; i < 2; ++i) {
             if (pipe_in[i]) cudaEventDestroy(pipe_in[i]);
@@ -1336,6 +1379,7 @@ int strotss_set_style_targets_grouped(strotss_handle h, const float* style, long
         if (rc != 0) { h->err = "region context: " + c->err; return rc; }
     }
     RET(ensure(h, "grouped.scalars", (size_t)R * STROTSS_NUM_SCALARS, &h->region_scalars));
+    h->group_warm = false;
     // the preparation of each target runs on the caller's stream (once per scale; not worth a fork)
     for (int r = 0; r < R; ++r) {
         strotss_ctx* c = h->regions[r];
@@ -1368,27 +1412,49 @@ int strotss_eval_grouped(strotss_handle h, const float* pred, long long ld_pred,
         }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
-    // The regions are evaluated one after the other on the caller's stream, each as a branch-parallel launch sequence
-    // (palette / relaxed EMD / moments / self-similarity on the region context's own forked streams).  Measured on B200
-    // (R = 3, N_r <= 1024): 0.54 ms; additionally forking the regions onto concurrent streams was slower (0.63-0.94 ms,
-    // the evaluation is bound by the launching thread, not by the GPU).  Then the scalars are averaged (run_strotss.py:118-124).
-    static const bool fork_regions = (getenv("STROTSS_GROUP_FORK") != nullptr);
-    if (fork_regions) CK(cudaEventRecord(h->ev_fork, st));
-    for (int r = 0; r < R; ++r) {
+    // A region's evaluation is ~30 short launches: bound by the host thread that enqueues them, not by the GPU.  After a
+    // first (warm-up) evaluation on the calling thread, regions 1..R-1 are therefore enqueued by their own launching threads
+    // on their own streams (forked from / joined to the caller's stream) while the caller enqueues region 0; measured on
+    // B200 (R = 3, N_r <= 1024): 0.54-0.60 ms on one thread (forking the streams from ONE thread was slower still: 0.63-0.94 ms).
+    // During stream capture everything stays on the calling thread and the caller's stream.
+    static const bool threads_on = !(getenv("STROTSS_GROUP_THREADS") && atoi(getenv("STROTSS_GROUP_THREADS")) == 0);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(st, &cap));
+    const bool threaded = threads_on && R > 1 && h->group_warm && cap == cudaStreamCaptureStatusNone;
+    auto run_region = [&](int r, cudaStream_t sr) -> int {
         strotss_ctx* c = h->regions[r];
         c->profiling = h->profiling;
         const int n = offsets_N[r + 1] - offsets_N[r];
         const long long ro = offsets_N[r];
-        cudaStream_t sr = fork_regions ? c->own : st;
-        if (fork_regions) CK(cudaStreamWaitEvent(sr, h->ev_fork, 0));
-        const int rc = eval_impl(c, pred + ro * ld_pred, ld_pred, content + ro * ld_content, ld_content, n, alpha,
-                                 h->region_scalars + (size_t)r * STROTSS_NUM_SCALARS, grad_pred ? grad_pred + ro * ld_grad : nullptr,
-                                 ld_grad, nullptr, nullptr, true, false, sr, 1.f / R);
-        if (rc != 0) { h->err = "region " + std::to_string(r) + ": " + c->err; return rc; }
-        if (fork_regions) {
-            CK(cudaEventRecord(c->ev_join2, sr));
-            CK(cudaStreamWaitEvent(st, c->ev_join2, 0));
+        return eval_impl(c, pred + ro * ld_pred, ld_pred, content + ro * ld_content, ld_content, n, alpha,
+                         h->region_scalars + (size_t)r * STROTSS_NUM_SCALARS, grad_pred ? grad_pred + ro * ld_grad : nullptr,
+                         ld_grad, nullptr, nullptr, true, false, sr, 1.f / R);
+    };
+    if (!threaded) {
+        for (int r = 0; r < R; ++r) {
+            const int rc = run_region(r, st);
+            if (rc != 0) { h->err = "region " + std::to_string(r) + ": " + h->regions[r]->err; return rc; }
         }
+        h->group_warm = true;
+    } else {
+        while (static_cast<int>(h->workers.size()) < R - 1) h->workers.push_back(new RegionWorker());
+        CK(cudaEventRecord(h->ev_fork, st));
+        std::vector<int> rcs(R, 0);
+        for (int r = 1; r < R; ++r) {
+            h->workers[r - 1]->post([&, r] {
+                strotss_ctx* c = h->regions[r];
+                cudaError_t e = cudaSetDevice(h->device);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(c->own, h->ev_fork, 0);
+                if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rcs[r] = STROTSS_ERR_CUDA; return; }
+                rcs[r] = run_region(r, c->own);
+                if (rcs[r] == 0 && cudaEventRecord(c->ev_join2, c->own) != cudaSuccess) { c->err = "cudaEventRecord"; rcs[r] = STROTSS_ERR_CUDA; }
+            });
+        }
+        rcs[0] = run_region(0, st);
+        for (int r = 1; r < R; ++r) h->workers[r - 1]->wait();
+        for (int r = 0; r < R; ++r)
+            if (rcs[r] != 0) { h->err = "region " + std::to_string(r) + ": " + h->regions[r]->err; return rcs[r]; }
+        for (int r = 1; r < R; ++r) CK(cudaStreamWaitEvent(st, h->regions[r]->ev_join2, 0));
     }
     mean_scalars_kernel<<<1, 32, 0, st>>>(h->region_scalars, R, STROTSS_NUM_SCALARS, scalars, region_scalars);
     CKL();
