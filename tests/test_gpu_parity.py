@@ -435,6 +435,30 @@ def test_grouped_masked_evaluation(S, cuda_device):
     assert abs(l2.item() - ref2) / ref2 <= LOSS_RTOL
 
 
+def test_grouped_evaluation_threads_and_capture(S, cuda_device):
+    """Repeated grouped calls (launching threads after the warm-up call) and a captured grouped call (everything on the
+    capturing thread) return what the first, single-threaded call returned."""
+    alpha = 4.0
+    probs = [O.synth_problem(N, M, 259, eps=0.1, seed=120 + r) for r, (N, M) in enumerate([(300, 200), (129, 64), (40, 70)])]
+    h = S.Handle(cuda_device)
+    h.set_style_targets_grouped([_t(p[0], cuda_device) for p in probs])
+    preds = [_t(p[2], cuda_device) for p in probs]; contents = [_t(p[1], cuda_device) for p in probs]
+    s0, r0, g0 = h.eval_grouped(preds, contents, alpha, True)                # warm-up: calling thread only
+    for _ in range(5):
+        s1, r1, g1 = h.eval_grouped(preds, contents, alpha, True)            # regions 1.. on launching threads
+        assert torch.equal(s0[:6], s1[:6]) and torch.equal(r0[:, :6], r1[:, :6])
+        assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-10) for a, b in zip(g0, g1))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        s2, r2, g2 = h.eval_grouped(preds, contents, alpha, True)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(s0[:6], s2[:6])
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-10) for a, b in zip(g0, g2))
+    ref = O.masked_total_loss([p[0] for p in probs], [p[1] for p in probs], [p[2] for p in probs], alpha, np.float64)
+    assert abs(s2[0].item() - ref) / ref <= LOSS_RTOL
+
+
 def test_grouped_argument_errors(S, cuda_device):
     st, co, pr = O.synth_problem(64, 48, 67, eps=0.1, seed=1)
     mod = S.MaskedStrotssLoss([_t(st, cuda_device), _t(st[:20], cuda_device)], 4.0)
