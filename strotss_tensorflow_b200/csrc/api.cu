@@ -12,6 +12,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <functional>
+#include <unordered_map>
 
 #include "../../include/strotss_b200.h"
 #include "gemm_core.cuh"
@@ -129,6 +130,20 @@ struct strotss_ctx {
     std::string err;
     PFN_tmapEncodeTiled encode = nullptr;
     std::map<std::string, std::pair<void*, size_t>> bufs;
+    // encoded tensor maps by (pointer, extents, stride, box, layout): an evaluation re-encodes the same ~20 maps every call
+    struct TmKey {
+        const void* p; int a, b; long long ld; int box, mn;
+        bool operator==(const TmKey& o) const { return p == o.p && a == o.a && b == o.b && ld == o.ld && box == o.box && mn == o.mn; }
+    };
+    struct TmHash {
+        size_t operator()(const TmKey& k) const {
+            size_t h = reinterpret_cast<size_t>(k.p) * 0x9E3779B97F4A7C15ull;
+            h ^= (static_cast<size_t>(k.a) << 1) ^ (static_cast<size_t>(k.b) << 21) ^ (static_cast<size_t>(k.ld) << 33) ^
+                 (static_cast<size_t>(k.box) << 7) ^ static_cast<size_t>(k.mn);
+            return h;
+        }
+    };
+    std::unordered_map<TmKey, CUtensorMap, TmHash> tmaps;
     size_t ws_bytes = 0;
     long long launches = 0;
     // style target
@@ -256,6 +271,9 @@ int ensure(strotss_ctx* h, const char* name, size_t count, T** out, bool zero_on
 }
 
 int make_tmap(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int rows, int kcols, long long ld_elems, int box_rows) {
+    const strotss_ctx::TmKey key{ptr, rows, kcols, ld_elems, box_rows, 0};
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) { *tm = it->second; return 0; }
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(kcols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * sizeof(bf16)};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
@@ -268,11 +286,16 @@ int make_tmap(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int rows, int kc
                  std::to_string(rows) + " k=" + std::to_string(kcols) + " ld=" + std::to_string(ld_elems) + ")";
         return STROTSS_ERR_CUDA;
     }
+    if (h->tmaps.size() > 512) h->tmaps.clear();
+    h->tmaps.emplace(key, *tm);
     return 0;
 }
 
 // Tensor map for an MN-major A operand: the matrix is stored k_rows x m_extent (m contiguous).
 int make_tmap_mn(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int m_extent, int k_rows, long long ld_elems) {
+    const strotss_ctx::TmKey key{ptr, m_extent, k_rows, ld_elems, 64, 1};
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) { *tm = it->second; return 0; }
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(m_extent), static_cast<cuuint64_t>(k_rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * sizeof(bf16)};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BK)};
@@ -284,6 +307,8 @@ int make_tmap_mn(strotss_ctx* h, CUtensorMap* tm, const bf16* ptr, int m_extent,
         h->err = "cuTensorMapEncodeTiled (MN-major) failed with code " + std::to_string(static_cast<int>(r));
         return STROTSS_ERR_CUDA;
     }
+    if (h->tmaps.size() > 512) h->tmaps.clear();
+    h->tmaps.emplace(key, *tm);
     return 0;
 }
 
