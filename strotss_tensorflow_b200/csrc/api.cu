@@ -404,6 +404,44 @@ int rows_per_block(const strotss_ctx* h, int n, int cap, int mult) {
     return r;
 }
 
+// Wide CTA-pair tiles (256 x 512, gemm2w_kernel): p.tiles_m counts 128-row blocks, p.tiles_n 512-column tiles.
+bool wide_enabled() {
+    static const bool on = pair_enabled() && !(getenv("STROTSS_WIDE") && atoi(getenv("STROTSS_WIDE")) == 0);
+    return on;
+}
+
+template <int B_MODE = 0, class Epi>
+int launch_gemm256w(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
+    constexpr int STAGES = 4, EPI_WARPS = 8;
+    constexpr int stage_bytes = 3 * 128 * BK * 2;
+    constexpr int smem = STAGES * stage_bytes + Epi::SMEM_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
+    auto kern = gemm2w_kernel<STAGES, EPI_WARPS, Epi, B_MODE>;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    GemmParams<Epi> q = p;
+    q.tiles_m = (p.tiles_m + 1) / 2;
+    q.tri = 0;
+    const int tiles = q.tiles_m * q.tiles_n;
+    if (tiles <= 0) return 0;
+    {
+        long long kbytes = 0;
+        for (int s = 0; s < p.nseg; ++s) kbytes += static_cast<long long>(p.seg_kblocks[s]) * BK * 2;
+        long long g = (32ll << 20) / (kbytes * 512);
+        if (g < 2) g = 2;
+        if (g > q.tiles_n) g = q.tiles_n;
+        q.group_n = static_cast<int>(g);
+    }
+    const int max_pairs = h->num_sms / 2;
+    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    CKL();
+    return 0;
+}
+
 // ---- operand preparation --------------------------------------------------------------
 struct PrepWant { bool mean, sumhat, xh, cen, dlt, xhT, cenT, rec; };
 
@@ -997,7 +1035,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     RET(make_tmap_mn(h, &q.tmB[1], P + r0, rows, rows, np));
                     q.nseg = 2; q.seg_kblocks[1] = (rows + BK - 1) / BK; q.seg_acc[1] = 0;
                     q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
-                    RET((launch_gemm256<1, 8, 2>(h, q, st2)));
+                    if (wide_enabled()) {
+                        q.tiles_n = (rows + 511) / 512;
+                        RET((launch_gemm256w<2>(h, q, st2)));
+                    } else {
+                        RET((launch_gemm256<1, 8, 2>(h, q, st2)));
+                    }
                 } else {
                     RET((launch_gemm256<1, 8>(h, q, st2)));
                 }
@@ -1012,7 +1055,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
                     t.epi.C = out.ss2 + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = mext;
                     t.epi.alpha = 1.f; t.epi.col_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
-                    RET((launch_gemm256<1, 8, 1>(h, t, st2)));
+                    if (wide_enabled()) {
+                        t.tiles_n = (mext + 511) / 512;
+                        RET((launch_gemm256w<1>(h, t, st2)));
+                    } else {
+                        RET((launch_gemm256<1, 8, 1>(h, t, st2)));
+                    }
                 }
             } else {
                 // single-CTA kernels: ss2[panel rows] (+)= P[panel, c0:] . x^[c0:]

@@ -185,4 +185,171 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     if (warp == 2) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
 }
 
+// ---- wide variant: one CTA pair owns a 256 x 512 tile (two 256-wide B sub-tiles per K block, one shared A tile) -------------
+// Why: every pair kernel delivers ~11-11.5 TB/s from L2 to shared memory (32 KB per CTA and K block) whatever its epilogue -- the
+// L2 -> SM throughput cap (~6300 B/clk chip-wide), not the tensor pipe, sets the 0.43 us per K block they all show.  Bytes per
+// FLOP scale with 1/BM + 1/BN: a 256 x 512 tile needs 48 KB per CTA and K block for twice the MMAs (-25 %).  The price: its two
+// accumulator halves fill TMEM, so the epilogue of a tile is not hidden behind the next tile's MMAs -- worth it where K is long
+// (stage 2 of the self-similarity: 32..256 K blocks per tile).  Sub-tile `sub` covers B rows tn*512 + sub*256 ..; the optional
+// tile-dependent K ranges of GemmParams apply per 256-row sub-tile index 2*tn + sub (an MMA is skipped outside its range).
+template <int STAGES, int EPI_WARPS, class Epi, int B_MODE = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
+gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
+    static_assert(EPI_WARPS == 8, "8 epilogue warps");
+    constexpr int BNW = 512;
+    constexpr int A_BYTES = 128 * BK * 2, B_BYTES = 128 * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;           // per CTA
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::SMEM_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) { tma_prefetch_desc(&p.tmA[s]); tma_prefetch_desc(&p.tmB[s]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tempty[0], 2 * EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int num_tiles = num_tiles_of(p);
+
+    // K-block range of segment s for the whole tile (union over the two sub-tiles) and per sub-tile
+    auto lo_of = [&](int s, int t256) { return p.kb_lo_mul[s] * t256; };
+    auto hi_of = [&](int s, int t256) { return p.kb_hi_mul[s] ? min(p.seg_kblocks[s], p.kb_hi_mul[s] * t256) : p.seg_kblocks[s]; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                int tm, tn;
+                decode_tile(p, t, tm, tn);
+                const int arow = p.a_row0 + tm * BM2 + static_cast<int>(rank) * 128;
+                const int brow = p.b_row0 + tn * BNW + static_cast<int>(rank) * 128;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int kb0 = min(lo_of(s, 2 * tn), lo_of(s, 2 * tn + 1));
+                    const int kb1 = max(hi_of(s, 2 * tn), hi_of(s, 2 * tn + 1));
+                    const bool bmn = (B_MODE == 1) || (B_MODE == 2 && p.seg_bmn[s]);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * STAGE_BYTES;
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            uint8_t* sB = sA + A_BYTES + sub * B_BYTES;
+                            if (bmn) {
+                                tma_load_2d_2cta(sB, &p.tmB[s], lead_full, brow + sub * 256, kb * BK);
+                                tma_load_2d_2cta(sB + B_BYTES / 2, &p.tmB[s], lead_full, brow + sub * 256 + 64, kb * BK);
+                            } else {
+                                tma_load_2d_2cta(sB, &p.tmB[s], lead_full, kb * BK, brow + sub * 256);
+                            }
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc_k = make_idesc_bf16(BM2, 256, false, false);
+            constexpr uint32_t idesc_mn = make_idesc_bf16(BM2, 256, false, true);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t aphase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                int tm_, tn_;
+                decode_tile(p, t, tm_, tn_);
+                mbar_wait(&tempty[0], aphase ^ 1);
+                tc_fence_after();
+                uint32_t touched = 0;                          // bit sub: accumulator half already written in this tile
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int lo0 = lo_of(s, 2 * tn_), lo1 = lo_of(s, 2 * tn_ + 1);
+                    const int hi0 = hi_of(s, 2 * tn_), hi1 = hi_of(s, 2 * tn_ + 1);
+                    const int kb0 = min(lo0, lo1), kb1 = max(hi0, hi1);
+                    const bool bmn = (B_MODE == 1) || (B_MODE == 2 && p.seg_bmn[s]);
+                    const uint32_t idesc = bmn ? idesc_mn : idesc_k;
+                    const uint32_t b_step = bmn ? (16 * 128) >> 4 : 2;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const int ksteps = (p.k_tail_steps && kb == p.seg_kblocks[s] - 1) ? p.k_tail_steps : BK / 16;
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const bool active = sub == 0 ? (kb >= lo0 && kb < hi0) : (kb >= lo1 && kb < hi1);
+                            if (!active) continue;
+                            const uint32_t b_addr = a_addr + A_BYTES + sub * B_BYTES;
+                            const uint64_t bdesc = bmn ? make_mnmajor_sw128_desc(b_addr, B_BYTES / 2) : make_kmajor_sw128_desc(b_addr);
+                            const uint32_t d_addr = tmem_base + sub * 256;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                if (k < ksteps)
+                                    umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,
+                                                   ((touched >> sub) & 1u) | (k > 0 ? 1u : 0u));
+                            touched |= (1u << sub);
+                        }
+                        umma_commit_2cta(&empty[stage], 3);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit_2cta(&tfull[0], 3);
+                aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        uint32_t aphase = 0;
+        int seq = 0;
+        typename Epi::State st;
+        Epi::init(st, p.epi, q, lane);
+        constexpr int kSplit = EPI_WARPS / 4;
+        constexpr int kChunks = BNW / 32 / kSplit;
+        for (int t = pair; t < num_tiles; t += npairs, ++seq) {
+            TileInfo ti;
+            int tm2;
+            decode_tile(p, t, tm2, ti.tn);
+            ti.tm = tm2 * 2 + static_cast<int>(rank);
+            ti.row0 = p.a_row0 + tm2 * BM2 + static_cast<int>(rank) * 128;
+            ti.col0 = p.b_row0 + ti.tn * BNW;
+            ti.q = q; ti.lane = lane; ti.tile_seq = seq;
+            ti.w = warp - 4; ti.nw = EPI_WARPS; ti.csplit = (warp - 4) >> 2; ti.nsplit = kSplit;
+            ti.c0 = ti.csplit * kChunks; ti.c1 = ti.c0 + kChunks;
+            ti.tid = threadIdx.x - kNonEpiThreads;
+            ti.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+            Epi::prologue(st, p.epi, ti, epi_smem);
+            mbar_wait(&tfull[0], aphase);
+            tc_fence_after();
+            Epi::run(st, p.epi, ti, epi_smem);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[0]), 0));
+            aphase ^= 1;
+        }
+        Epi::finish(st, p.epi, q, lane);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
 }  // namespace sb
