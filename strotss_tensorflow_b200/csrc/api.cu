@@ -658,6 +658,8 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
             q.epi.rowbest = rs.rowbest; q.epi.colbest = rs.colbest; q.epi.M = M; q.epi.N = sh.r1;
             RET((launch_gemm<128, 1, 6>(h, q, st)));
         } else {
+            // (256 x 512 tiles were measured here as well: 0.92 -> 1.03 ms -- with only 35 K blocks per tile the epilogue that
+            // the full-TMEM accumulator leaves exposed costs more than the saved L2 traffic)
             RET((launch_gemm256<1, 8>(h, p, st)));
         }
     }

@@ -557,7 +557,8 @@ print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.no
                                  {"STROTSS_NO_PAIR": "1", "STROTSS_SS1_GENERIC": "1"},
                                  {"STROTSS_BRANCHES": "0"}, {"STROTSS_PAL_TWO_PASS": "1"},
                                  {"STROTSS_BRANCHES": "0", "STROTSS_OVERLAP": "1", "STROTSS_PANEL": "1024"}, {"STROTSS_NO_TRAP": "1", "STROTSS_PANEL": "2048"},
-                                 {"STROTSS_PANEL": "1024"}, {"STROTSS_FINALIZE_GENERIC": "1", "STROTSS_NO_KTAIL": "1", "STROTSS_PREP_V1": "1"}])
+                                 {"STROTSS_PANEL": "1024"}, {"STROTSS_FINALIZE_GENERIC": "1", "STROTSS_NO_KTAIL": "1", "STROTSS_PREP_V1": "1"},
+                                 {"STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_PANEL": "1024"}])
 def test_alternative_kernel_paths(cuda_device, env):
     """The single-CTA GEMM kernels (STROTSS_NO_PAIR), the generic stage-1 epilogue (STROTSS_SS1_GENERIC), the
     single-stream launch order (STROTSS_BRANCHES=0), the two-pass palette search and the two-stream stage-1/stage-2
