@@ -1043,6 +1043,9 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     } else {
                         RET((launch_gemm256<1, 8, 2>(h, q, st2)));
                     }
+                } else if (wide_enabled()) {
+                    q.tiles_n = (rows + 511) / 512;
+                    RET((launch_gemm256w<0>(h, q, st2)));
                 } else {
                     RET((launch_gemm256<1, 8>(h, q, st2)));
                 }
