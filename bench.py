@@ -398,7 +398,7 @@ def main():
     else:
         visited = nt * (nt + 1) / 2.0 / (nt * nt)
     ach = alg_flops_step / (ss1_ms / args.steps * 1e-3) / 1e12 if ss1_n else None
-    roof = {"bound": "tensor", "kernel": "ss1_pair_kernel (self-similarity stage 1, cta_group::2; all launches of a step)",
+    roof = {"bound": "tensor", "kernel": "ss1_pair_merged_kernel (self-similarity stage 1, cta_group::2; all launches of a step)",
             "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
             # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one step of the DEFAULT build at this

@@ -387,6 +387,46 @@ int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     return 0;
 }
 
+// K blocks by which the halves of a tile couple are skewed (gemm2s_kernel); STROTSS_REMD_SKEW=-1 selects the plain pair kernel
+int couple_skew() {
+    static const int skew = getenv("STROTSS_REMD_SKEW") ? atoi(getenv("STROTSS_REMD_SKEW")) : 16;
+    return skew;
+}
+
+// Skewed couples of 256 x 256 tiles sharing their A tile (gemm2s_kernel): p.tiles_m counts 128-row blocks, p.tiles_n 256-column
+// tiles (as for launch_gemm256); one segment, K-major operands.
+template <int EPI_WARPS = 8, class Epi>
+int launch_gemm256s(strotss_ctx* h, const GemmParams<Epi>& p, int skew, cudaStream_t st) {
+    constexpr int STAGES = 4;
+    constexpr int stage_bytes = 3 * 128 * BK * 2;
+    constexpr int smem = STAGES * stage_bytes + Epi::SMEM_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
+    auto kern = gemm2s_kernel<STAGES, EPI_WARPS, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    if (p.nseg != 1 || p.tri) { h->err = "internal: the skewed-couple kernel takes one segment on a rectangular tile grid"; return STROTSS_ERR_STATE; }
+    GemmParams<Epi> q = p;
+    q.tiles_m = (p.tiles_m + 1) / 2;
+    q.tiles_n = (p.tiles_n + 1) / 2;
+    q.skew = skew;
+    const int tiles = q.tiles_m * q.tiles_n;
+    if (tiles <= 0) return 0;
+    {
+        long long g = (32ll << 20) / (static_cast<long long>(p.seg_kblocks[0]) * BK * 2 * 512);
+        if (g < 2) g = 2;
+        if (g > q.tiles_n) g = q.tiles_n;
+        q.group_n = static_cast<int>(g);
+    }
+    const int max_pairs = h->num_sms / 2;
+    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    CKL();
+    return 0;
+}
+
 // 16-wide MMA steps that carry data in the last 64-wide K block of a K extent of `k` real columns (0 = all four)
 int tail_steps(int k) {
     static const bool off = (getenv("STROTSS_NO_KTAIL") != nullptr);
@@ -660,7 +700,10 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
         } else {
             // (256 x 512 tiles were measured here as well: 0.92 -> 1.03 ms -- with only 35 K blocks per tile the epilogue that
             // the full-TMEM accumulator leaves exposed costs more than the saved L2 traffic)
-            RET((launch_gemm256<1, 8>(h, p, st)));
+            // skewed couples (two tiles share their A tile, epilogues stay hidden; see gemm2s_kernel): 0.94 -> 0.79 ms at
+            // N = M = 16384 (skew 8 / 12 / 16 / 20: 0.835 / 0.803 / 0.789 / 0.805 ms)
+            if (couple_skew() >= 0 && pair_enabled() && p.tiles_n >= 4) RET((launch_gemm256s<8>(h, p, couple_skew(), st)));
+            else RET((launch_gemm256<1, 8>(h, p, st)));
         }
     }
     if (ry_partial) {                     // null on a single GPU: remd_finish sums the column minima itself
@@ -824,7 +867,8 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
             q.a_row0 = 0; q.b_row0 = sh.r0;
             q.k_tail_steps = tail_steps(D);
             q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = sh.r1; q.epi.alpha = 1.f; q.epi.col_off = sh.r0;
-            RET((launch_gemm256<1>(h, q, st)));
+            if (couple_skew() >= 0 && q.tiles_n >= 8) RET((launch_gemm256s<8>(h, q, couple_skew(), st)));
+            else RET((launch_gemm256<1>(h, q, st)));
         } else {
             GemmParams<EpiStoreT<256>> q{};
             RET(make_tmap(h, &q.tmA[0], pred.cen, N, Dp, Dp, BM));
@@ -987,6 +1031,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             if (!configured) {
                 CK(cudaFuncSetAttribute(ss1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1SmemBytes));
                 CK(cudaFuncSetAttribute(ss1_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1PairSmemBytes));
+                CK(cudaFuncSetAttribute(ss1_pair_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1MergedSmemBytes));
                 configured = true;
             }
             if (pair_enabled()) {
@@ -997,7 +1042,14 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                 const int max_pairs = h->num_sms / 2;
                 if (tiles > 0) {
                     PhaseTimer _pt(h, PH_SS1, st);
-                    ss1_pair_kernel<<<2 * (tiles < max_pairs ? tiles : max_pairs), kSs1Threads, kSs1PairSmemBytes, st>>>(sp);
+                    // merged K loop (one shared y^ tile, two B tiles, two accumulators per stage): see ss1_kernel.cuh
+                    // measured at N = 16384: 1.52 -> 1.36 ms per evaluation (tail 4 / 8 / 12: 1.355 / 1.372 / 1.372 ms)
+                    static const bool merged = !(getenv("STROTSS_SS1_MERGED") && atoi(getenv("STROTSS_SS1_MERGED")) == 0);
+                    static const int tail_blocks = getenv("STROTSS_SS1_TAIL") ? atoi(getenv("STROTSS_SS1_TAIL")) : 4;
+                    sp.tail_blocks = tail_blocks < 0 ? 0 : tail_blocks;
+                    const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+                    if (merged) ss1_pair_merged_kernel<<<grid, kSs1Threads, kSs1MergedSmemBytes, st>>>(sp);
+                    else ss1_pair_kernel<<<grid, kSs1Threads, kSs1PairSmemBytes, st>>>(sp);
                     CKL();
                 }
             } else {

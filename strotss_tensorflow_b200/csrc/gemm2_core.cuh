@@ -352,4 +352,164 @@ gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
     if (warp == 2) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
 }
 
+// ---- skewed couple: one CTA pair owns TWO neighbouring 256 x 256 tiles that share their A tile ---------------------------------
+// The wide kernel above saves a quarter of the L2 -> shared-memory traffic but leaves its epilogue exposed (both accumulator
+// halves complete together and fill TMEM) -- too expensive where K is short (relaxed EMD: 35 K blocks per tile).  Here the two
+// halves are skewed by `skew` K blocks so that each half's epilogue hides behind MMAs that do not need its TMEM columns:
+//
+//   MMA warp, per couple:  wait half 0 free -> K blocks [0, skew) of half 0 alone          (A + B0: 32 KB stages)
+//                          wait half 1 free -> K blocks [skew, K) of BOTH halves           (A + B0 + B1: 48 KB, two MMAs per stage)
+//                          commit tfull[0]  -> K blocks [0, skew) of half 1 alone          (A + B1)   -> commit tfull[1]
+//   epilogue, per couple:  wait tfull[0] -> half 0 (while half 1 finishes)   -> release half 0
+//                          wait tfull[1] -> half 1 (while the next couple's half 0 starts) -> release half 1
+//
+// Per couple and CTA 2*skew*32 + (K - skew)*48 KB instead of 2*K*32 KB (K = 35, skew = 12: -17 %).  The epilogue policy sees two
+// ordinary 256-wide tiles (tn = 2 * couple + half).  One segment, K-major B, no tile-dependent K ranges.  p.tiles_n counts couples;
+// a ragged last couple computes a phantom half (TMA zero fill or columns the policy masks).
+template <int STAGES, int EPI_WARPS, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
+gemm2s_kernel(const __grid_constant__ GemmParams<Epi> p) {
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
+    constexpr int BN = 256;
+    constexpr int A_BYTES = 128 * BK * 2, B_BYTES = 128 * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;           // per CTA
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Epi::SMEM_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;      // [half]
+    uint64_t* tempty = tfull + 2;             // [half]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = (rank == 0);
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int num_tiles = num_tiles_of(p);
+    const int K = p.seg_kblocks[0];
+    const int skew = p.skew < K ? (p.skew > 0 ? p.skew : 0) : K;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                int tm, tn;
+                decode_tile(p, t, tm, tn);
+                const int arow = p.a_row0 + tm * BM2 + static_cast<int>(rank) * 128;
+                const int brow = p.b_row0 + tn * 2 * BN + static_cast<int>(rank) * 128;
+                for (int part = 0; part < 3; ++part) {
+                    const int kb0 = (part == 1) ? skew : 0;
+                    const int kb1 = (part == 1) ? K : skew;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sA = smem + stage * STAGE_BYTES;
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + (part == 1 ? 2 : 1) * B_BYTES));
+                        tma_load_2d_2cta(sA, &p.tmA[0], lead_full, kb * BK, arow);
+                        // a lone half always sits in the first B slot
+                        tma_load_2d_2cta(sA + A_BYTES, &p.tmB[0], lead_full, kb * BK, brow + (part == 2 ? BN : 0));
+                        if (part == 1) tma_load_2d_2cta(sA + A_BYTES + B_BYTES, &p.tmB[0], lead_full, kb * BK, brow + BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM2, BN, false, false);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t tph = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                uint32_t touched = 0;                            // bit h: half h already written in this couple
+                for (int part = 0; part < 3; ++part) {
+                    const int kb0 = (part == 1) ? skew : 0;
+                    const int kb1 = (part == 1) ? K : skew;
+                    if (part < 2) {                              // half 0 before part 0, half 1 before part 1
+                        mbar_wait(&tempty[part], tph ^ 1);
+                        tc_fence_after();
+                    }
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const int ksteps = (p.k_tail_steps && kb == K - 1) ? p.k_tail_steps : BK / 16;
+#pragma unroll
+                        for (int slot = 0; slot < 2; ++slot) {
+                            if (slot == 1 && part != 1) continue;
+                            const int half = (part == 2) ? 1 : slot;
+                            const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + A_BYTES + slot * B_BYTES);
+                            const uint32_t d_addr = tmem_base + half * BN;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                if (k < ksteps)
+                                    umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, ((touched >> half) & 1u) | (k > 0 ? 1u : 0u));
+                            touched |= (1u << half);
+                        }
+                        umma_commit_2cta(&empty[stage], 3);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (part == 1) umma_commit_2cta(&tfull[0], 3);
+                }
+                umma_commit_2cta(&tfull[1], 3);
+                tph ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        uint32_t tph = 0;
+        int seq = 0;
+        typename Epi::State st;
+        Epi::init(st, p.epi, q, lane);
+        constexpr int kSplit = EPI_WARPS / 4;
+        constexpr int kChunks = BN / 32 / kSplit;
+        for (int t = pair; t < num_tiles; t += npairs, ++seq) {
+            int tm2, tnc;
+            decode_tile(p, t, tm2, tnc);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                TileInfo ti;
+                ti.tn = 2 * tnc + half;
+                ti.tm = tm2 * 2 + static_cast<int>(rank);            // row block in units of 128 rows
+                ti.row0 = p.a_row0 + tm2 * BM2 + static_cast<int>(rank) * 128;
+                ti.col0 = p.b_row0 + ti.tn * BN;
+                ti.q = q; ti.lane = lane; ti.tile_seq = 2 * seq + half;
+                ti.w = warp - 4; ti.nw = EPI_WARPS; ti.csplit = (warp - 4) >> 2; ti.nsplit = kSplit;
+                ti.c0 = ti.csplit * kChunks; ti.c1 = ti.c0 + kChunks;
+                ti.tid = threadIdx.x - kNonEpiThreads;
+                ti.taddr = tmem_base + half * BN + (static_cast<uint32_t>(q * 32) << 16);
+                Epi::prologue(st, p.epi, ti, epi_smem);
+                mbar_wait(&tfull[half], tph);
+                tc_fence_after();
+                Epi::run(st, p.epi, ti, epi_smem);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[half]), 0));
+            }
+            tph ^= 1;
+        }
+        Epi::finish(st, p.epi, q, lane);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
 }  // namespace sb

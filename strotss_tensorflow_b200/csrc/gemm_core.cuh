@@ -52,6 +52,8 @@ struct GemmParams {
     // CTA-pair kernel: number of 16-wide MMA steps that carry data in the LAST K block of a segment (0 = all four).  K is
     // zero-padded to a multiple of 64 (D = 2179 -> 2240): the last block holds 3 real columns, so 3 of its 4 steps multiply zeros.
     int k_tail_steps;
+    // gemm2s_kernel: K blocks by which the two 256-wide halves of a tile couple are skewed against each other
+    int skew;
     typename Epi::Params epi;
 };
 

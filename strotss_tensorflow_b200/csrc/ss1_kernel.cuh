@@ -15,6 +15,17 @@
 //
 // PAIR = true runs the same protocol on a CTA pair (cta_group::2, see gemm2_core.cuh): 256 x 256 tiles,
 // each CTA stages 128 rows of A and 128 rows of B, barriers full/tempty live in the leader CTA.
+//
+// MERGED = true (CTA pair only): segments 0 and 2 share their A operand (y^ rows of the tile), so they run as ONE K loop whose
+// stages hold A = y^_I and two B tiles (delta_J -> accumulator "D", y^_J -> accumulator "Y"): 48 KB per CTA and K block for two
+// MMAs instead of 2 x 32 KB -- the pair kernels sit at the L2 -> shared-memory throughput cap, and this removes a sixth of the
+// stage-1 operand traffic (35 x (32 + 48) KB instead of 105 x 32 KB per tile and CTA).  Both accumulators are then busy until the
+// merged loop ends, so to keep the epilogue hidden
+//   * the delta.x^T segment is split around the merged loop: its first kblocks - tail_blocks K blocks run BEFORE it (they need only
+//     the D columns), its last tail_blocks after it (while they run the epilogue stashes Y and releases those columns), and
+//   * the two 256-column TMEM regions swap roles every tile: the region whose Y was stashed is free almost at once and takes the
+//     next tile's D, whose leading delta.x^T blocks cover the epilogue streaming the previous D out of the other region.
+//   tempty[] is indexed by REGION (each region is released once per tile), tfull[] by role (0 = D, 1 = Y).
 #pragma once
 #include "gemm2_core.cuh"
 
@@ -38,6 +49,7 @@ struct Ss1Params {
     // trapezoid of a row panel of a symmetric matrix -- and every tile right of its own diagonal tile accounts for its
     // mirror image.  Same L2 raster as decode_tile: groups of group_n column tiles, row tiles swept inside a group.
     int trap;
+    int tail_blocks;             // MERGED kernel: K blocks of the delta.x^T segment issued after the merged loop
     Ss1Epi::Params epi;
 };
 
@@ -63,16 +75,20 @@ __device__ __forceinline__ void ss1_decode(const Ss1Params& p, int t, int& tm, i
 }
 
 constexpr int kSs1PairStages = 6;
+constexpr int kSs1MergedStages = 4;                       // 48 KB stages
 constexpr int kSs1SmemBytes = kSs1Stages * TileCfg<kSs1BN, 2>::STAGE_BYTES + Ss1Epi::SMEM_BYTES + (2 * kSs1Stages + 4) * 8 + 16 + 1024;
 constexpr int kSs1PairSmemBytes = kSs1PairStages * PairCfg<2>::STAGE_BYTES + Ss1Epi::SMEM_BYTES + (2 * kSs1PairStages + 4) * 8 + 16 + 1024;
+constexpr int kSs1MergedSmemBytes = kSs1MergedStages * 3 * 128 * BK * 2 + Ss1Epi::SMEM_BYTES + (2 * kSs1MergedStages + 4) * 8 + 16 + 1024;
+static_assert(kSs1MergedSmemBytes <= 232448, "shared memory budget exceeded");
 
-template <bool PAIR>
+template <bool PAIR, bool MERGED = false>
 __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
+    static_assert(PAIR || !MERGED, "the merged K loop exists for the CTA-pair kernel only");
     constexpr int BN = kSs1BN;
-    constexpr int STAGES = PAIR ? kSs1PairStages : kSs1Stages;
+    constexpr int STAGES = MERGED ? kSs1MergedStages : (PAIR ? kSs1PairStages : kSs1Stages);
     constexpr int A_BYTES = 128 * BK * 2;
     constexpr int B_BYTES = (PAIR ? 128 : BN) * BK * 2;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + (MERGED ? 2 : 1) * B_BYTES;
     constexpr int TILE_M = PAIR ? BM2 : BM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,6 +124,8 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int num_tiles = ss1_num_tiles(p);
+    const int ksplit = (p.kblocks > p.tail_blocks) ? p.kblocks - p.tail_blocks : 0;      // MERGED only
+    (void)ksplit;
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -117,6 +135,31 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
                 int tm, tn;
                 ss1_decode(p, t, tm, tn);
                 const int arow = p.a_row0 + tm * TILE_M + rank * 128, brow = p.b_row0 + tn * BN + rank * 128;
+                if constexpr (MERGED) {
+                    // part 0: delta.x^T blocks [0, ksplit) ; part 1: merged y^.(delta | y^)^T blocks ; part 2: delta.x^T blocks [ksplit, kblocks)
+                    for (int part = 0; part < 3; ++part) {
+                        const bool merged = (part == 1);
+                        const int kb0 = (part == 2) ? ksplit : 0;
+                        const int kb1 = (part == 0) ? ksplit : p.kblocks;
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            uint8_t* sA = smem + stage * STAGE_BYTES;
+                            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                            if (merged) {
+                                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + 2 * B_BYTES));
+                                tma_load_2d_2cta(sA, &p.tmA[2], lead_full, kb * BK, arow);
+                                tma_load_2d_2cta(sA + A_BYTES, &p.tmB[2], lead_full, kb * BK, brow);
+                                tma_load_2d_2cta(sA + A_BYTES + B_BYTES, &p.tmB[0], lead_full, kb * BK, brow);
+                            } else {
+                                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
+                                tma_load_2d_2cta(sA, &p.tmA[1], lead_full, kb * BK, arow);
+                                tma_load_2d_2cta(sA + A_BYTES, &p.tmB[1], lead_full, kb * BK, brow);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 for (int s = 0; s < 3; ++s) {
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -139,7 +182,50 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
             int stage = 0; uint32_t phase = 0;
             uint32_t tph = 0;
-            for (int t = first; t < num_tiles; t += stride) {
+            int seq = 0;
+            for (int t = first; t < num_tiles; t += stride, ++seq) {
+                if constexpr (MERGED) {
+                    const int dreg = seq & 1, yreg = dreg ^ 1;       // TMEM region of the D / Y accumulator of this tile
+                    const uint32_t d_addr = tmem_base + dreg * BN, y_addr = tmem_base + yreg * BN;
+                    uint32_t dacc = 0;                               // D already written in this tile
+                    for (int part = 0; part < 3; ++part) {
+                        const bool merged = (part == 1);
+                        const int kb0 = (part == 2) ? ksplit : 0;
+                        const int kb1 = (part == 0) ? ksplit : p.kblocks;
+                        if (part < 2) {                              // D region before part 0, Y region before the merged loop
+                            mbar_wait(&tempty[part == 0 ? dreg : yreg], tph ^ 1);
+                            tc_fence_after();
+                        }
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                            const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                            const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + A_BYTES);
+                            const int ksteps = (p.k_tail_steps && kb == p.kblocks - 1) ? p.k_tail_steps : BK / 16;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (k >= ksteps) break;
+                                umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, dacc | (k > 0 ? 1u : 0u));
+                            }
+                            dacc = 1u;
+                            if (merged) {
+                                const uint64_t ydesc = make_kmajor_sw128_desc(a_addr + A_BYTES + B_BYTES);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    if (k >= ksteps) break;
+                                    umma_bf16_2cta(y_addr, adesc + 2 * k, ydesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                                }
+                            }
+                            umma_commit_2cta(&empty[stage], 3);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        if (merged) umma_commit_2cta(&tfull[1], 3);
+                    }
+                    umma_commit_2cta(&tfull[0], 3);
+                    tph ^= 1;
+                    continue;
+                }
                 for (int s = 0; s < 3; ++s) {
                     const int acc = (s == 0) ? 1 : 0;
                     if (s < 2) {                       // first segment of each accumulator: wait until it is free
@@ -199,6 +285,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             const float ui = rvalid ? P.u[row] : 0.f;
             const float wi = rvalid ? P.w[row] : 0.f;
             const bool both = P.sym && (p.trap ? (tn > tm) : (col0 >= P.panel_end));
+            const int dreg = MERGED ? (seq & 1) : 0, yreg = dreg ^ 1;     // TMEM regions (MERGED: roles swap every tile)
 
             // ---- accumulator 1 (y^.y^T): stash Yd = 1 - acc1, then hand the columns back to the MMA warp
             float yd[kChunks * 32];
@@ -207,7 +294,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 uint32_t a1[32];
-                tmem_ld32(lane_addr + BN + (csplit * kChunks + c) * 32, a1);
+                tmem_ld32(lane_addr + yreg * BN + (csplit * kChunks + c) * 32, a1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 32; ++e) yd[c * 32 + e] = 1.f - __uint_as_float(a1[e]);
@@ -215,7 +302,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[1]), 0)); else mbar_arrive(&tempty[1]);
+                if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[yreg]), 0)); else mbar_arrive(&tempty[1]);
             }
 
             // ---- accumulator 0 (delta form of Xd - Yd), 32 columns at a time
@@ -227,7 +314,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             for (int c = 0; c < kChunks; ++c) {
                 const int cc = csplit * kChunks + c;
                 uint32_t a0[32];
-                tmem_ld32(lane_addr + cc * 32, a0);
+                tmem_ld32(lane_addr + dreg * BN + cc * 32, a0);
                 tmem_ld_wait();
                 const int colbase = col0 + cc * 32;
                 const bool pwrite = P.write_p && rvalid && colbase < P.ldp;
@@ -282,7 +369,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[0]), 0)); else mbar_arrive(&tempty[0]);
+                if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[dreg]), 0)); else mbar_arrive(&tempty[0]);
             }
             if (rvalid) {
                 const long long slot = static_cast<long long>(col0 / BN) * 2 + csplit;
@@ -306,5 +393,8 @@ __global__ void __launch_bounds__(kSs1Threads, 1) ss1_kernel(const __grid_consta
 // tiles_m of Ss1Params counts 256-row tiles for the pair kernel
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSs1Threads, 1)
 ss1_pair_kernel(const __grid_constant__ Ss1Params p) { ss1_body<true>(p); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSs1Threads, 1)
+ss1_pair_merged_kernel(const __grid_constant__ Ss1Params p) { ss1_body<true, true>(p); }
 
 }  // namespace sb

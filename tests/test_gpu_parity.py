@@ -73,7 +73,8 @@ def test_tcgen05_gemm_transposed_a(handle, cuda_device, m, n, k):
 
 
 # ------------------------------------------------------------------------------ relaxed EMD
-@pytest.mark.parametrize("N,M,seed", [(700, 517, 0), (333, 1024, 1), (128, 256, 2), (1, 300, 3), (130, 1, 4)])
+@pytest.mark.parametrize("N,M,seed", [(700, 517, 0), (333, 1024, 1), (128, 256, 2), (1, 300, 3), (130, 1, 4),
+                                      (2300, 300, 5), (2561, 2100, 6)])       # > 2048: CTA-pair kernels, ragged tile couples
 def test_relaxed_emd_cosine(handle, cuda_device, N, M, seed):
     st, co, pr = O.synth_problem(N, M, 2179, eps=1.0, seed=seed)
     out, grad, ra, ca = handle.relaxed_emd(_t(st, cuda_device), _t(pr, cuda_device), "cosine", True, True)
@@ -558,7 +559,9 @@ print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.no
                                  {"STROTSS_BRANCHES": "0"}, {"STROTSS_PAL_TWO_PASS": "1"},
                                  {"STROTSS_BRANCHES": "0", "STROTSS_OVERLAP": "1", "STROTSS_PANEL": "1024"}, {"STROTSS_NO_TRAP": "1", "STROTSS_PANEL": "2048"},
                                  {"STROTSS_PANEL": "1024"}, {"STROTSS_FINALIZE_GENERIC": "1", "STROTSS_NO_KTAIL": "1", "STROTSS_PREP_V1": "1"},
-                                 {"STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_PANEL": "1024"}])
+                                 {"STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_PANEL": "1024"},
+                                 {"STROTSS_SS1_MERGED": "0", "STROTSS_REMD_SKEW": "-1"}, {"STROTSS_SS1_TAIL": "0", "STROTSS_REMD_SKEW": "0"},
+                                 {"STROTSS_SS1_TAIL": "40", "STROTSS_REMD_SKEW": "40"}])
 def test_alternative_kernel_paths(cuda_device, env):
     """The single-CTA GEMM kernels (STROTSS_NO_PAIR), the generic stage-1 epilogue (STROTSS_SS1_GENERIC), the
     single-stream launch order (STROTSS_BRANCHES=0), the two-pass palette search and the two-stream stage-1/stage-2
