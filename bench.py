@@ -402,9 +402,10 @@ def main():
             "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
             # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one step of the DEFAULT build at this
-            # workload (4096-row panels, triangle walk: profiles/r01_v15_ss1_ncu_summary.txt); other switch settings: not captured
-            "traffic": 1.808e9 if (world == 1 and N == 16384 and not os.environ.get("STROTSS_NO_TRAP")
-                                   and not os.environ.get("STROTSS_PANEL")) else None,
+            # workload (4096-row panels, triangle walk, merged K loop: profiles/r01_v21_ss1_merged_remd_skew_ncu_summary.txt;
+            # the kernel with three separate K loops moved 1.808e9); other switch settings: not captured
+            "traffic": 1.628e9 if (world == 1 and N == 16384 and not os.environ.get("STROTSS_NO_TRAP")
+                                   and not os.environ.get("STROTSS_PANEL") and not os.environ.get("STROTSS_SS1_MERGED")) else None,
             "traffic_unit": "bytes per step (all launches of the kernel)",
             # operands: A 4 panels x 3 x 4096 x 2240 bf16 = 220 MB, B 550 MB; P panels 2080 tiles x 128 KB = 272 MB
             "algorithmic_bytes": 1.042e9 if (world == 1 and N == 16384) else None,
