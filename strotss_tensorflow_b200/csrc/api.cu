@@ -393,6 +393,20 @@ int couple_skew() {
     return skew;
 }
 
+// Couples pay when they save rounds: a couple costs (2*skew*32 + (K - skew)*48) / (K*32) plain tiles (1.73 at K = 35, skew = 16),
+// and a launch lasts as many rounds as its tiles / couples need on the chip's CTA pairs.  p.tiles_m counts 128-row blocks.
+template <class Epi>
+bool couples_pay(const strotss_ctx* h, const GemmParams<Epi>& p) {
+    const int skew = couple_skew(), K = p.seg_kblocks[0];
+    if (skew < 0 || !pair_enabled() || p.nseg != 1 || p.tri || K <= 0) return false;
+    const int s = skew < K ? skew : K;
+    const double couple_cost = (2.0 * s * 32 + (K - s) * 48.0) / (K * 32.0);
+    const long long tm = (p.tiles_m + 1) / 2, pairs = h->num_sms / 2 > 0 ? h->num_sms / 2 : 1;
+    const long long plain_rounds = (tm * p.tiles_n + pairs - 1) / pairs;
+    const long long couple_rounds = (tm * ((p.tiles_n + 1) / 2) + pairs - 1) / pairs;
+    return couple_rounds * couple_cost < static_cast<double>(plain_rounds);
+}
+
 // Skewed couples of 256 x 256 tiles sharing their A tile (gemm2s_kernel): p.tiles_m counts 128-row blocks, p.tiles_n 256-column
 // tiles (as for launch_gemm256); one segment, K-major operands.
 template <int EPI_WARPS = 8, class Epi>
@@ -702,7 +716,7 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
             // the full-TMEM accumulator leaves exposed costs more than the saved L2 traffic)
             // skewed couples (two tiles share their A tile, epilogues stay hidden; see gemm2s_kernel): 0.94 -> 0.79 ms at
             // N = M = 16384 (skew 8 / 12 / 16 / 20: 0.835 / 0.803 / 0.789 / 0.805 ms)
-            if (couple_skew() >= 0 && pair_enabled() && p.tiles_n >= 4) RET((launch_gemm256s<8>(h, p, couple_skew(), st)));
+            if (couples_pay(h, p)) RET((launch_gemm256s<8>(h, p, couple_skew(), st)));
             else RET((launch_gemm256<1, 8>(h, p, st)));
         }
     }
@@ -867,7 +881,7 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
             q.a_row0 = 0; q.b_row0 = sh.r0;
             q.k_tail_steps = tail_steps(D);
             q.epi.C = out.Q; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = sh.r1; q.epi.alpha = 1.f; q.epi.col_off = sh.r0;
-            if (couple_skew() >= 0 && q.tiles_n >= 8) RET((launch_gemm256s<8>(h, q, couple_skew(), st)));
+            if (couples_pay(h, q)) RET((launch_gemm256s<8>(h, q, couple_skew(), st)));
             else RET((launch_gemm256<1>(h, q, st)));
         } else {
             GemmParams<EpiStoreT<256>> q{};

@@ -544,7 +544,7 @@ sys.path.insert(0, %r)
 from oracle import strotss_oracle as O
 import strotss_tensorflow_b200 as S
 dev = torch.device('cuda', 0)
-st, co, pr = O.synth_problem(2300, 700, 2179, eps=0.1, seed=41)
+st, co, pr = O.synth_problem(2300, 2100, 2179, eps=0.1, seed=41)   # sizes at which tile couples pay (two rounds of plain tiles)
 mod = S.StrotssLoss(torch.tensor(st, device=dev), 16.0)
 sc, grad, _, _ = mod.handle.eval(torch.tensor(pr, device=dev), torch.tensor(co, device=dev), 16.0, True)
 ref, gref, info = O.total_loss(st, co, pr, 16.0, np.float64, True)
