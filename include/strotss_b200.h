@@ -209,6 +209,15 @@ int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, 
 int strotss_debug_gemm_ta(strotss_handle h, const float* At, int m, const float* B, int n, int k, float alpha,
                           float* C, int accumulate, void* stream);
 
+/* Test hooks without GPU work (CPU tests of the host logic).  strotss_debug_tile_walk replays the tile order of the
+ * persistent kernels -- walk 0: rectangular raster in groups of group_n column tiles; 1: upper block triangle
+ * (covariance); 2: block trapezoid tn >= tm of a symmetric row panel (self-similarity stage 1) -- returns the tile count
+ * and writes up to `capacity` (tm, tn) pairs in visiting order.  strotss_debug_couples_pay returns 1 where the host
+ * sends a GEMM of tiles_m128 x tiles_n256 tiles and `kblocks` K blocks to skewed tile couples.  Not part of the
+ * reference interface. */
+int strotss_debug_tile_walk(int walk, int tiles_m, int tiles_n, int group_n, int* tm_out, int* tn_out, int capacity);
+int strotss_debug_couples_pay(int num_sms, int tiles_m128, int tiles_n256, int kblocks, int skew);
+
 #ifdef __cplusplus
 }
 #endif

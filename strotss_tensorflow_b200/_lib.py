@@ -53,6 +53,8 @@ SIGNATURES = {
     "strotss_rmsprop_step": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _f, _f, _f, _vp]),
     "strotss_debug_gemm": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
     "strotss_debug_gemm_ta": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
+    "strotss_debug_tile_walk": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i]),
+    "strotss_debug_couples_pay": (_i, [_i, _i, _i, _i, _i]),
 }
 
 _lib = None

@@ -395,16 +395,19 @@ int couple_skew() {
 
 // Couples pay when they save rounds: a couple costs (2*skew*32 + (K - skew)*48) / (K*32) plain tiles (1.73 at K = 35, skew = 16),
 // and a launch lasts as many rounds as its tiles / couples need on the chip's CTA pairs.  p.tiles_m counts 128-row blocks.
-template <class Epi>
-bool couples_pay(const strotss_ctx* h, const GemmParams<Epi>& p) {
-    const int skew = couple_skew(), K = p.seg_kblocks[0];
-    if (skew < 0 || !pair_enabled() || p.nseg != 1 || p.tri || K <= 0) return false;
+bool couples_pay_rule(int num_sms, int tiles_m128, int tiles_n256, int K, int skew) {
+    if (skew < 0 || K <= 0 || tiles_m128 <= 0 || tiles_n256 <= 0) return false;
     const int s = skew < K ? skew : K;
     const double couple_cost = (2.0 * s * 32 + (K - s) * 48.0) / (K * 32.0);
-    const long long tm = (p.tiles_m + 1) / 2, pairs = h->num_sms / 2 > 0 ? h->num_sms / 2 : 1;
-    const long long plain_rounds = (tm * p.tiles_n + pairs - 1) / pairs;
-    const long long couple_rounds = (tm * ((p.tiles_n + 1) / 2) + pairs - 1) / pairs;
+    const long long tm = (tiles_m128 + 1) / 2, pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
+    const long long plain_rounds = (tm * tiles_n256 + pairs - 1) / pairs;
+    const long long couple_rounds = (tm * ((tiles_n256 + 1) / 2) + pairs - 1) / pairs;
     return couple_rounds * couple_cost < static_cast<double>(plain_rounds);
+}
+template <class Epi>
+bool couples_pay(const strotss_ctx* h, const GemmParams<Epi>& p) {
+    if (!pair_enabled() || p.nseg != 1 || p.tri) return false;
+    return couples_pay_rule(h->num_sms, p.tiles_m, p.tiles_n, p.seg_kblocks[0], couple_skew());
 }
 
 // Skewed couples of 256 x 256 tiles sharing their A tile (gemm2s_kernel): p.tiles_m counts 128-row blocks, p.tiles_n 256-column
@@ -2057,6 +2060,34 @@ int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, 
     p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + 127) / 128;
     p.epi.C = C; p.epi.ldc = n; p.epi.rows = m; p.epi.cols = n; p.epi.alpha = alpha; p.epi.row_off = 0;
     return launch_gemm<128, 1, 6>(h, p, st);
+}
+
+// Host-side replay of the persistent kernels' tile walks (the very functions the kernels call, compiled for the host):
+// walk 0 = decode_tile raster (groups of group_n column tiles, row tiles swept inside a group), 1 = decode_tile triangle
+// (tiles_m == tiles_n, tn >= tm), 2 = ss1_decode trapezoid (tn >= tm, raster of groups).  Returns the number of tiles and
+// writes min(count, capacity) (tm, tn) pairs in visiting order.  No GPU work.
+int strotss_debug_tile_walk(int walk, int tiles_m, int tiles_n, int group_n, int* tm_out, int* tn_out, int capacity) {
+    if (walk < 0 || walk > 2 || tiles_m <= 0 || tiles_n <= 0 || group_n <= 0 || (capacity > 0 && (!tm_out || !tn_out))) return STROTSS_ERR_ARG;
+    if (walk == 1 && tiles_m != tiles_n) return STROTSS_ERR_ARG;
+    int count = 0;
+    if (walk == 2) {
+        Ss1Params p{};
+        p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.group_n = group_n; p.trap = 1;
+        count = ss1_num_tiles(p);
+        for (int t = 0; t < count && t < capacity; ++t) ss1_decode(p, t, tm_out[t], tn_out[t]);
+    } else {
+        GemmParams<EpiStore> p{};
+        p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.group_n = group_n; p.tri = walk;
+        count = num_tiles_of(p);
+        for (int t = 0; t < count && t < capacity; ++t) decode_tile(p, t, tm_out[t], tn_out[t]);
+    }
+    return count;
+}
+
+// The host rule that sends a one-segment GEMM to skewed tile couples (gemm2s_kernel) instead of plain pair tiles:
+// 1 if couples need less time on num_sms / 2 CTA pairs.  tiles_m128 counts 128-row blocks, tiles_n256 256-column tiles.
+int strotss_debug_couples_pay(int num_sms, int tiles_m128, int tiles_n256, int kblocks, int skew) {
+    return couples_pay_rule(num_sms, tiles_m128, tiles_n256, kblocks, skew) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -73,12 +73,12 @@ struct TileInfo {
 // CTAs that run concurrently then share a few A row blocks and one group of B column blocks, so
 // both stay L2-resident instead of B being re-streamed from HBM for every row block.
 template <class P>
-__device__ __forceinline__ int num_tiles_of(const P& p) {
+__host__ __device__ __forceinline__ int num_tiles_of(const P& p) {
     return p.tri ? p.tiles_n * (p.tiles_n + 1) / 2 : p.tiles_m * p.tiles_n;
 }
 
 template <class P>
-__device__ __forceinline__ void decode_tile(const P& p, int t, int& tm, int& tn) {
+__host__ __device__ __forceinline__ void decode_tile(const P& p, int t, int& tm, int& tn) {
     if (p.tri) {                 // row-major walk over the upper triangle (tiles_m == tiles_n)
         int row = 0, len = p.tiles_n;
         while (t >= len) { t -= len; ++row; --len; }

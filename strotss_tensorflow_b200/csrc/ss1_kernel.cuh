@@ -53,13 +53,13 @@ struct Ss1Params {
     Ss1Epi::Params epi;
 };
 
-__device__ __forceinline__ int ss1_num_tiles(const Ss1Params& p) {
+__host__ __device__ __forceinline__ int ss1_num_tiles(const Ss1Params& p) {
     if (!p.trap) return num_tiles_of(p);
     const int tmx = min(p.tiles_m, p.tiles_n);
     return tmx * p.tiles_n - tmx * (tmx - 1) / 2;
 }
 
-__device__ __forceinline__ void ss1_decode(const Ss1Params& p, int t, int& tm, int& tn) {
+__host__ __device__ __forceinline__ void ss1_decode(const Ss1Params& p, int t, int& tm, int& tn) {
     if (!p.trap) { decode_tile(p, t, tm, tn); return; }
     for (int c_lo = 0; c_lo < p.tiles_n; c_lo += p.group_n) {
         const int c_hi = min(p.tiles_n, c_lo + p.group_n);
