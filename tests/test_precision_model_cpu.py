@@ -1,0 +1,58 @@
+"""CPU model of the tensor-core arithmetic of the self-similarity term (DESIGN "Precision design"): operands
+rounded to bf16, exact products, wide accumulation -- what tcgen05 kind::f16 computes up to fp32 accumulation order.
+
+It pins the two claims the kernel design rests on, without a GPU:
+  * one bf16 pass over each Gram matrix (x^x^T and y^y^T separately) breaks the loss when pred ~ content: the difference
+    Xd/s - Yd/t is then of the size of the bf16 rounding of x^ and y^ themselves;
+  * the delta form  x^x^T - y^y^T = delta.x^T + y^.delta^T  with delta = x^ - y^ formed in fp32 and only then rounded keeps
+    every rounding error relative to |delta|: <= 2e-4 on the loss at every eps, well inside the 1e-3 tolerance.
+The GPU parity tests measure the same figures on the device (<= 6e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import strotss_oracle as O
+
+
+def _bf16(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).bfloat16().double().numpy()
+
+
+def _unit_rows(a):
+    a = a.astype(np.float32)
+    n2 = np.maximum((a.astype(np.float64) ** 2).sum(1, keepdims=True), 1e-12)      # epsilon inside the sqrt (nn/losses.py:13-14)
+    return (a / np.sqrt(n2)).astype(np.float32)
+
+
+def _model(N, eps, seed=3):
+    _, content, pred = O.synth_problem(N, 8, 2179, eps=eps, seed=seed)
+    ref = O.self_similarity(pred, content, np.float64)
+    xh, yh = _unit_rows(pred), _unit_rows(content)
+    # column sums from the O(ND) identity s_j = N - x^_j . sum_i x^_i, as the kernels form them (ss_vectors_kernel)
+    s = np.maximum(N - xh.astype(np.float64) @ xh.astype(np.float64).sum(0), 1e-12)
+    t = np.maximum(N - yh.astype(np.float64) @ yh.astype(np.float64).sum(0), 1e-12)
+    u, w = 1.0 / s, 1.0 / s - 1.0 / t
+    off = ~np.eye(N, dtype=bool)                                                   # the epilogue masks the diagonal
+    # (a) one bf16 pass per Gram matrix
+    Xd = 1.0 - _bf16(xh) @ _bf16(xh).T
+    Yd = 1.0 - _bf16(yh) @ _bf16(yh).T
+    naive = np.abs((Xd / s[None, :] - Yd / t[None, :]) * off).sum() / N
+    # (b) delta form: acc0 = delta.x^T + y^.delta^T = -(Xd - Yd), acc1 = y^.y^T = 1 - Yd  (three bf16 K passes)
+    d = _bf16(xh - yh)
+    acc0 = d @ _bf16(xh).T + _bf16(yh) @ d.T
+    acc1 = _bf16(yh) @ _bf16(yh).T
+    term = -acc0 * u[None, :] + (1.0 - acc1) * w[None, :]
+    delta = np.abs(term * off).sum() / N
+    return ref, naive, delta
+
+
+@pytest.mark.parametrize("eps", [1.0, 0.1, 0.01])
+def test_delta_form_keeps_the_loss_within_tolerance(eps):
+    ref, _, delta = _model(512, eps)
+    assert abs(delta - ref) / ref <= 2e-4           # tolerance on losses: 1e-3 (BASELINE north_star)
+
+
+def test_single_bf16_pass_per_gram_matrix_fails_near_content():
+    ref, naive, delta = _model(384, 0.01)
+    assert abs(naive - ref) / ref > 0.2             # tens of per cent: why the kernel does not use it
+    assert abs(delta - ref) / ref < 1e-3 * abs(naive - ref) / ref
