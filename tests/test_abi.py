@@ -101,3 +101,31 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_tf_adapter_calls_match_the_abi_signatures():
+    """tf_adapter.py cannot be executed here (no TensorFlow); at least every C-ABI call it makes must exist in the
+    header and pass as many arguments as the entry point takes."""
+    import ast
+    from strotss_tensorflow_b200 import _lib
+    src = open(os.path.join(ROOT, "strotss_tensorflow_b200", "tf_adapter.py")).read()
+    calls = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute)
+             and n.func.attr.startswith("strotss_")]
+    assert len(calls) >= 6
+    for c in calls:
+        name = c.func.attr
+        assert name in _lib.SIGNATURES, f"{name} is not declared in include/strotss_b200.h"
+        assert not c.keywords and len(c.args) == len(_lib.SIGNATURES[name][1]), \
+            f"{name}: {len(c.args)} arguments passed, the entry point takes {len(_lib.SIGNATURES[name][1])}"
+
+
+def test_ctypes_signatures_have_the_arity_of_the_header_prototypes():
+    from strotss_tensorflow_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "strotss_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(strotss_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes binding {len(_lib.SIGNATURES[name][1])}"
