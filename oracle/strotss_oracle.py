@@ -1,9 +1,16 @@
 """CPU oracle for the STROTSS per-iteration loss hot path.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (interaction-lab-uh/STROTSS-tensorflow) ships no tests, golden
-vectors or fixtures for this path, and TensorFlow cannot be imported in this environment, so
-this restatement cannot be checked against reference outputs.  It is pinned only by the
-analytic known-answer cases, invariances and fp64 finite-difference checks in tests/.
+PARITY STATUS: pinned to the reference's own Python code, NOT to TensorFlow.  The reference
+(interaction-lab-uh/STROTSS-tensorflow) ships no tests, golden vectors or fixtures for this path, and
+TensorFlow cannot be imported in this environment.  tests/golden/make_reference_golden.py therefore
+executes the reference's source text unmodified (nn/losses.py imported; ContentLoss, StyleLoss,
+convert_rgb_to_yuv exec'd from run_strotss.py / nn/strotss_utils.py) over a stand-in for the dozen
+TensorFlow ops the path calls, and commits the results as tests/golden/ref_*.npz: this restatement
+reproduces them to <= 5e-14 (losses, every term, the gradient; tests/test_reference_golden.py), ties
+included.  That pins op order, argument order, axes, broadcasting and weights to the reference's
+code.  UNPINNED remains that those dozen ops behave as TensorFlow's do (stated from TensorFlow's
+documentation, listed below); beyond that the oracle is held by analytic known-answer cases,
+invariances and fp64 finite-difference checks in tests/.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module, and only as the checker.  The product path (strotss_tensorflow_b200) never

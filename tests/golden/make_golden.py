@@ -1,6 +1,8 @@
-"""Generate tests/golden/*.npz from the oracle (fp64).  PARITY UNPINNED: the reference has no golden
-vectors and cannot run here (no TensorFlow), so these fixtures pin the ORACLE's outputs on seeded
-synthetic inputs; they guard against regressions of the oracle and give the GPU tests fixed targets.
+"""Generate tests/golden/*.npz from the oracle (fp64).  The reference has no golden vectors and cannot run
+here (no TensorFlow), so these fixtures pin the ORACLE's outputs on seeded synthetic inputs; they guard
+against regressions of the oracle and give the GPU tests fixed targets (incl. argmin rows and gaps).
+The companion make_reference_golden.py produces ref_*.npz for the same problems from the reference's own
+loss code run over a stand-in for its TensorFlow ops; tests/test_reference_golden.py holds the two together.
 
     python tests/golden/make_golden.py
 """

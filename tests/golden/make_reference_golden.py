@@ -1,0 +1,240 @@
+"""Golden vectors produced by the REFERENCE'S OWN loss code (test infrastructure; runs only where /root/reference exists).
+
+The reference (interaction-lab-uh/STROTSS-tensorflow) cannot run here because TensorFlow is not installed.  Its loss path,
+however, is plain Python over a dozen TensorFlow ops.  This script executes the reference's source text unmodified --
+
+    nn/losses.py                      imported as a module (mae, cosine_distance, l2_distance, dist_metrics, reshape_2d,
+                                      moment_matching, self_similarity, relaxed_emd)
+    nn/strotss_utils.py:166-167       convert_rgb_to_yuv      (function source extracted with ast, exec'd)
+    run_strotss.py:21-40              ContentLoss, StyleLoss  (class sources extracted with ast, exec'd)
+
+-- against a small stand-in for the `tensorflow` module (`TFShim` below) that implements exactly the ops this path calls,
+on torch fp64 tensors, with TensorFlow's documented semantics (l2_normalize's epsilon inside the
+square root, reduce_min gradient split among ties, maximum's gradient to the first argument on ties, the rgb_to_yuv
+kernel).  The two lines that combine the losses (run_strotss.py:92,140) live inside a nested function of the driver and
+are restated here.  Gradients come from torch autograd THROUGH the reference's op sequence.
+
+What this pins: the oracle follows the reference's code -- op order, argument order, axes, broadcasting (e.g. the
+column-sum division of self_similarity), weights.  What stays unpinned: that the shim's dozen ops equal TensorFlow's
+(stated from TensorFlow's documentation, not executed).
+
+    python tests/golden/make_reference_golden.py            # writes tests/golden/ref_*.npz
+
+No reference source is copied into this repository; the script reads it from /root/reference when it runs.
+"""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+REFERENCE = os.environ.get("STROTSS_REFERENCE", "/root/reference")
+
+# the same cases as make_golden.py (inputs are regenerated from the seed by oracle.synth_problem)
+CASES = {
+    "small_d67": (48, 40, 67, 0.1, 11, 16.0),
+    "ragged_d2179": (333, 517, 2179, 0.1, 5, 16.0),
+    "default_d2179_eps1": (256, 256, 2179, 1.0, 0, 8.0),
+    "near_d2179_eps001": (256, 200, 2179, 0.01, 7, 2.0),
+}
+
+
+# --------------------------------------------------------------------------------------------------- the stand-in
+class _Shape(tuple):
+    @property
+    def dims(self):                       # tf.TensorShape.dims is a list (nn/losses.py:32 compares it with an int)
+        return list(self)
+
+
+class T:
+    """Stand-in for tf.Tensor: a torch tensor plus the few attributes / operators the reference's loss code touches."""
+
+    def __init__(self, t):
+        self.t = t
+
+    @property
+    def shape(self):
+        return _Shape(self.t.shape)
+
+    @property
+    def dtype(self):
+        return self.t.dtype
+
+    def __getitem__(self, idx):
+        return T(self.t[idx])
+
+    def __neg__(self):
+        return T(-self.t)
+
+    def __pow__(self, p):
+        return T(self.t ** p)
+
+
+def _raw(v):
+    return v.t if isinstance(v, T) else v
+
+
+def _binary(name, op):
+    def fwd(a, b):
+        return T(op(_raw(a), _raw(b)))
+
+    def rev(a, b):
+        return T(op(_raw(b), _raw(a)))
+    setattr(T, f"__{name}__", fwd)
+    setattr(T, f"__r{name}__", rev)
+
+
+_binary("add", lambda a, b: a + b)
+_binary("sub", lambda a, b: a - b)
+_binary("mul", lambda a, b: a * b)
+_binary("truediv", lambda a, b: a / b)
+_binary("matmul", lambda a, b: a @ b)
+
+_YUV_KERNEL = [[0.299, -0.14714119, 0.61497538],      # tf.image.rgb_to_yuv: images (tensordot) kernel, rows = R, G, B
+               [0.587, -0.28886916, -0.51496512],
+               [0.114, 0.43601035, -0.10001026]]
+
+
+def make_tf_shim() -> types.ModuleType:
+    tf = types.ModuleType("tensorflow")
+    tf.Tensor = T
+    tf.float32, tf.float64 = torch.float32, torch.float64
+
+    def reduce(fn):
+        def op(x, axis=None, keepdims=False):
+            x = _raw(x)
+            return T(fn(x) if axis is None else fn(x, dim=axis, keepdim=keepdims))
+        return op
+
+    tf.reduce_mean = reduce(torch.mean)
+    tf.reduce_sum = reduce(torch.sum)
+    tf.reduce_min = reduce(torch.amin)            # amin splits the gradient equally among tied minima, as TensorFlow does
+    tf.square = lambda x: T(_raw(x) ** 2)
+    tf.abs = lambda x: T(torch.abs(_raw(x)))      # gradient sign(x), 0 at 0
+    tf.sqrt = lambda x: T(torch.sqrt(_raw(x)))
+    tf.squeeze = lambda x: T(torch.squeeze(_raw(x)))
+    tf.reshape = lambda x, shape: T(torch.reshape(_raw(x), tuple(int(_raw(s)) for s in shape)))
+    tf.shape = lambda x: [int(s) for s in _raw(x).shape]
+
+    def cast(x, dtype):
+        x = _raw(x)
+        return T(x.to(dtype) if torch.is_tensor(x) else torch.tensor(x, dtype=dtype))
+    tf.cast = cast
+
+    def maximum(a, b):
+        a, b = _raw(a), _raw(b)
+        a = a if torch.is_tensor(a) else torch.tensor(a, dtype=b.dtype)
+        b = b if torch.is_tensor(b) else torch.tensor(b, dtype=a.dtype)
+        return T(torch.where(a >= b, a, b))       # TensorFlow's gradient mask is a >= b: ties go to the first argument
+    tf.maximum = maximum
+
+    def matmul(a, b, transpose_a=False, transpose_b=False):
+        a, b = _raw(a), _raw(b)
+        return T((a.T if transpose_a else a) @ (b.T if transpose_b else b))
+    tf.matmul = matmul
+
+    tf.nn = types.SimpleNamespace()
+
+    def l2_normalize(x, axis=None, epsilon=1e-12):
+        x = _raw(x)
+        sq = torch.sum(x * x, dim=axis, keepdim=True)
+        return T(x * torch.rsqrt(torch.clamp_min(sq, epsilon)))      # x * rsqrt(max(sum(x^2), epsilon))
+    tf.nn.l2_normalize = l2_normalize
+
+    tf.image = types.SimpleNamespace()
+    tf.image.rgb_to_yuv = lambda x: T(_raw(x) @ torch.tensor(_YUV_KERNEL, dtype=_raw(x).dtype))
+
+    class Module:
+        def __init__(self, **kwargs):
+            pass
+
+        @staticmethod
+        def with_name_scope(fn):
+            return fn
+    tf.Module = Module
+    return tf
+
+
+# --------------------------------------------------------------------------------------- running the reference's text
+def _source_of(path, name):
+    text = open(path).read()
+    for node in ast.parse(text).body:
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name == name:
+            return ast.get_source_segment(text, node)
+    raise KeyError(f"{name} not found in {path}")
+
+
+def load_reference(tf=None):
+    """Returns a namespace with the reference's own relaxed_emd, moment_matching, self_similarity, convert_rgb_to_yuv,
+    ContentLoss and StyleLoss, bound to the stand-in tensorflow module."""
+    tf = tf or make_tf_shim()
+    saved = sys.modules.get("tensorflow")
+    sys.modules["tensorflow"] = tf
+    try:
+        spec = importlib.util.spec_from_file_location("_strotss_reference_losses", os.path.join(REFERENCE, "nn", "losses.py"))
+        losses = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(losses)
+    finally:
+        if saved is None:
+            del sys.modules["tensorflow"]
+        else:
+            sys.modules["tensorflow"] = saved
+    utils_ns = {"tf": tf}
+    exec(_source_of(os.path.join(REFERENCE, "nn", "strotss_utils.py"), "convert_rgb_to_yuv"), utils_ns)
+    ns = {"tf": tf, "moment_matching": losses.moment_matching, "relaxed_emd": losses.relaxed_emd,
+          "self_similarity": losses.self_similarity, "strotss": types.SimpleNamespace(convert_rgb_to_yuv=utils_ns["convert_rgb_to_yuv"])}
+    for cls in ("ContentLoss", "StyleLoss"):
+        exec(_source_of(os.path.join(REFERENCE, "run_strotss.py"), cls), ns)
+    return types.SimpleNamespace(tf=tf, losses=losses, convert_rgb_to_yuv=utils_ns["convert_rgb_to_yuv"],
+                                 ContentLoss=ns["ContentLoss"], StyleLoss=ns["StyleLoss"])
+
+
+def evaluate(ref, style, content, pred, alpha, dtype=torch.float64):
+    """The loss lines of train_step (run_strotss.py:136-141) on given sampled features."""
+    st = T(torch.tensor(style, dtype=dtype))
+    co = T(torch.tensor(content, dtype=dtype))
+    pr_t = torch.tensor(pred, dtype=dtype, requires_grad=True)
+    pr = T(pr_t)
+    loss_content = ref.ContentLoss()
+    loss_style = ref.StyleLoss(st, alpha=alpha)
+    loss_denom = (2. + alpha + 1. / max(alpha, 1.))             # run_strotss.py:92
+    loss_c = loss_content(co, pr)
+    loss_s = loss_style(pr)
+    loss = (alpha * loss_c + loss_s) / loss_denom               # run_strotss.py:140
+    loss.t.backward()
+    with torch.no_grad():
+        l_m = ref.losses.moment_matching(st, T(pr_t)).t.item()
+        l_remd = ref.losses.relaxed_emd(st, T(pr_t)).t.item()
+        l_pal = ref.losses.relaxed_emd(ref.convert_rgb_to_yuv(st), ref.convert_rgb_to_yuv(T(pr_t)), distance="both").t.item()
+        l_pal_l2 = ref.losses.relaxed_emd(ref.convert_rgb_to_yuv(st), ref.convert_rgb_to_yuv(T(pr_t)), distance="l2").t.item()
+    return dict(total=loss.t.item(), loss_c=loss_c.t.item(), loss_s=loss_s.t.item(), l_m=l_m, l_remd=l_remd,
+                l_palette=l_pal, l_palette_l2=l_pal_l2, grad=pr_t.grad.numpy().copy())
+
+
+def main():
+    from oracle import strotss_oracle as O
+    ref = load_reference()
+    for name, (N, M, D, eps, seed, alpha) in CASES.items():
+        st, co, pr = O.synth_problem(N, M, D, eps=eps, seed=seed)
+        r = evaluate(ref, st, co, pr, alpha)
+        g = r.pop("grad")
+        out = dict(N=N, M=M, D=D, eps=eps, seed=seed, alpha=alpha, **r, grad_norm=np.linalg.norm(g), grad_rowsum=g.sum(axis=1),
+                   grad_colsum=g.sum(axis=0), grad_head=g[:8, :16].copy(),
+                   input_checksum=np.array([st.astype(np.float64).sum(), co.astype(np.float64).sum(), pr.astype(np.float64).sum()]))
+        if D <= 128:
+            out["grad"] = g
+        np.savez_compressed(os.path.join(HERE, "ref_" + name + ".npz"), **out)
+        print(name, "total", out["total"], "grad_norm", out["grad_norm"])
+
+
+if __name__ == "__main__":
+    main()

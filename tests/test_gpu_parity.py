@@ -281,6 +281,28 @@ def test_total_against_golden(S, cuda_device, name):
         assert float((g * ref).sum() / (np.linalg.norm(g) * np.linalg.norm(ref))) >= 0.99
 
 
+@pytest.mark.parametrize("name", ["small_d67", "ragged_d2179", "default_d2179_eps1", "near_d2179_eps001"])
+def test_total_against_reference_code_golden(S, cuda_device, name):
+    """The same four problems against tests/golden/ref_*.npz: numbers produced by the REFERENCE'S OWN loss code
+    (nn/losses.py, StyleLoss / ContentLoss of run_strotss.py executed over a stand-in for the TensorFlow ops they call;
+    tests/golden/make_reference_golden.py), gradient by autograd through the reference's op sequence."""
+    from strotss_tensorflow_b200 import _lib
+    z = np.load(os.path.join(GOLDEN, "ref_" + name + ".npz"))
+    N, M, D, alpha = int(z["N"]), int(z["M"]), int(z["D"]), float(z["alpha"])
+    st, co, pr = O.synth_problem(N, M, D, eps=float(z["eps"]), seed=int(z["seed"]))
+    mod = S.StrotssLoss(_t(st, cuda_device), alpha)
+    sc, grad, _, _ = mod.handle.eval(_t(pr, cuda_device), _t(co, cuda_device), alpha, True, True)
+    s = sc.cpu().numpy()
+    for slot, key in [(_lib.S_TOTAL, "total"), (_lib.S_LOSS_C, "loss_c"), (_lib.S_LOSS_S, "loss_s"), (_lib.S_L_M, "l_m"),
+                      (_lib.S_L_REMD, "l_remd"), (_lib.S_L_PALETTE, "l_palette")]:
+        assert abs(s[slot] - float(z[key])) / abs(float(z[key])) <= LOSS_RTOL, key
+    g = grad.double().cpu().numpy()
+    assert abs(np.linalg.norm(g) - float(z["grad_norm"])) / float(z["grad_norm"]) <= GRADNORM_RTOL
+    if "grad" in z.files:
+        ref = z["grad"]
+        assert float((g * ref).sum() / (np.linalg.norm(g) * np.linalg.norm(ref))) >= 0.99
+
+
 @pytest.mark.parametrize("alpha", [16.0, 0.5])
 def test_modules_match_reference_wrappers(S, cuda_device, alpha):
     """ContentLoss / StyleLoss keep run_strotss.py:21-40 semantics; autograd delivers d loss / d pred."""
