@@ -7,6 +7,9 @@ however, is plain Python over a dozen TensorFlow ops.  This script executes the 
                                       moment_matching, self_similarity, relaxed_emd)
     nn/strotss_utils.py:166-167       convert_rgb_to_yuv      (function source extracted with ast, exec'd)
     run_strotss.py:21-40              ContentLoss, StyleLoss  (class sources extracted with ast, exec'd)
+    nn/strotss_utils.py:12-81         _clip_and_cast, Sampling._sample                       (fp32, bit-exact)
+    nn/strotss_utils.py:139-163       make_laplacian, make_laplacian_pyramid, fold_laplacian_pyramid       
+    nn/utils.py:14-41                 _validate_and_get_shape, resize, resize_like
 
 -- against a small stand-in for the `tensorflow` module (`TFShim` below) that implements exactly the ops this path calls,
 on torch fp64 tensors, with TensorFlow's documented semantics (l2_normalize's epsilon inside the
@@ -17,6 +20,9 @@ are restated here.  Gradients come from torch autograd THROUGH the reference's o
 What this pins: the oracle follows the reference's code -- op order, argument order, axes, broadcasting (e.g. the
 column-sum division of self_similarity), weights.  What stays unpinned: that the shim's dozen ops equal TensorFlow's
 (stated from TensorFlow's documentation, not executed).
+
+tf.image.resize (bilinear, half-pixel centres, no antialiasing) is stood in for by torch's F.interpolate(mode="bilinear",
+align_corners=False), which uses the same source coordinate (dst + 0.5) * in / out - 0.5 and the same edge clamping.
 
     python tests/golden/make_reference_golden.py            # writes tests/golden/ref_*.npz
 
@@ -52,6 +58,13 @@ CASES = {
 class _Shape(tuple):
     @property
     def dims(self):                       # tf.TensorShape.dims is a list (nn/losses.py:32 compares it with an int)
+        return list(self)
+
+    @property
+    def rank(self):
+        return len(self)
+
+    def as_list(self):
         return list(self)
 
 
@@ -98,6 +111,7 @@ _binary("sub", lambda a, b: a - b)
 _binary("mul", lambda a, b: a * b)
 _binary("truediv", lambda a, b: a / b)
 _binary("matmul", lambda a, b: a @ b)
+_binary("floordiv", lambda a, b: a // b)
 
 _YUV_KERNEL = [[0.299, -0.14714119, 0.61497538],      # tf.image.rgb_to_yuv: images (tensordot) kernel, rows = R, G, B
                [0.587, -0.28886916, -0.51496512],
@@ -123,7 +137,18 @@ def make_tf_shim() -> types.ModuleType:
     tf.sqrt = lambda x: T(torch.sqrt(_raw(x)))
     tf.squeeze = lambda x: T(torch.squeeze(_raw(x)))
     tf.reshape = lambda x, shape: T(torch.reshape(_raw(x), tuple(int(_raw(s)) for s in shape)))
-    tf.shape = lambda x: [int(s) for s in _raw(x).shape]
+    tf.int32 = torch.int32
+    tf.split = lambda x, n, axis=0: [T(p) for p in torch.chunk(_raw(x), n, dim=axis)]
+    tf.math = types.SimpleNamespace(floor=lambda x: T(torch.floor(_raw(x))))
+    tf.clip_by_value = lambda x, lo, hi: T(torch.minimum(torch.maximum(_raw(x), _raw(lo)), _raw(hi)))
+    tf.gather = lambda params, indices, axis=0: T(torch.index_select(_raw(params), axis, _raw(indices).long()))
+    tf.concat = lambda xs, axis: T(torch.cat([_raw(x) for x in xs], dim=axis))
+
+    def gather_nd(params, indices):
+        idx = _raw(indices).long()
+        return T(_raw(params)[tuple(idx[:, k] for k in range(idx.shape[1]))])
+    tf.gather_nd = gather_nd
+    tf.shape = lambda x: T(torch.tensor(list(_raw(x).shape), dtype=torch.int64))      # a 1-D integer tensor, as in TensorFlow
 
     def cast(x, dtype):
         x = _raw(x)
@@ -152,6 +177,14 @@ def make_tf_shim() -> types.ModuleType:
 
     tf.image = types.SimpleNamespace()
     tf.image.rgb_to_yuv = lambda x: T(_raw(x) @ torch.tensor(_YUV_KERNEL, dtype=_raw(x).dtype))
+
+    def resize(images, size, method="bilinear"):
+        assert method == "bilinear"
+        x = _raw(images)                                                     # NHWC
+        size = [int(v) for v in (_raw(size).tolist() if torch.is_tensor(_raw(size)) else size)]
+        y = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=size, mode="bilinear", align_corners=False, antialias=False)
+        return T(y.permute(0, 2, 3, 1))
+    tf.image.resize = resize
 
     class Module:
         def __init__(self, **kwargs):
@@ -198,6 +231,63 @@ def load_reference(tf=None):
                                  ContentLoss=ns["ContentLoss"], StyleLoss=ns["StyleLoss"])
 
 
+def load_reference_widened(tf=None):
+    """The reference's own Sampling (with _clip_and_cast), make_laplacian, make_laplacian_pyramid, fold_laplacian_pyramid
+    (nn/strotss_utils.py) and resize, resize_like (nn/utils.py), exec'd from their source text over the stand-in."""
+    import math
+    from functools import partialmethod
+    from typing import List, Optional, Tuple, Union
+    tf = tf or make_tf_shim()
+    su = os.path.join(REFERENCE, "nn", "strotss_utils.py")
+    ut = os.path.join(REFERENCE, "nn", "utils.py")
+    ns = {"tf": tf, "math": math, "partialmethod": partialmethod, "List": List, "Optional": Optional, "Tuple": Tuple,
+          "Union": Union, "tf_rng": None}
+    for name in ("_clip_and_cast", "Sampling", "make_laplacian", "make_laplacian_pyramid", "fold_laplacian_pyramid"):
+        exec(_source_of(su, name), ns)
+    for name in ("_validate_and_get_shape", "resize", "resize_like"):
+        exec(_source_of(ut, name), ns)
+    return types.SimpleNamespace(**{k: ns[k] for k in ("Sampling", "make_laplacian", "make_laplacian_pyramid",
+                                                        "fold_laplacian_pyramid", "resize", "resize_like")}, tf=tf)
+
+
+SAMPLER_SHAPES = [(42, 64, 3), (42, 64, 8), (42, 64, 8), (21, 32, 16), (21, 32, 16), (10, 16, 32), (10, 16, 32), (10, 16, 32),
+                  (5, 8, 64), (5, 8, 64)]            # the ten maps of the content image at scale 64, fewer channels
+SAMPLER_N = 32
+
+
+def sampler_inputs(seed=0):
+    rng = np.random.default_rng(seed)
+    xs = [rng.standard_normal((1,) + s).astype(np.float32) for s in SAMPLER_SHAPES]
+    idx = np.stack([rng.uniform(0, 42, SAMPLER_N), rng.uniform(0, 64, SAMPLER_N)], axis=1).astype(np.float32)
+    idx[:4] = np.floor(idx[:4])                      # integral positions, the border row and the border column
+    idx[4] = [41.0, 63.0]
+    idx[5] = [41.7, 63.9]
+    return xs, idx
+
+
+def evaluate_sampler(wid, xs, idx, bilinear):
+    s = wid.Sampling(SAMPLER_N)
+    out = s._sample([T(torch.tensor(x)) for x in xs], T(torch.tensor(idx)), bilinear)
+    return out.t.numpy().copy()
+
+
+def pyramid_input(seed=1):
+    return np.random.default_rng(seed).uniform(0, 1, (1, 21, 30, 3))
+
+
+def evaluate_pyramid(wid, img):
+    x = T(torch.tensor(img, dtype=torch.float64))
+    pyr = wid.make_laplacian_pyramid(x, levels=5)
+    fold = wid.fold_laplacian_pyramid(pyr)
+    lap, down = wid.make_laplacian(x, return_downscale=True)
+    small = wid.resize(x, 16)
+    like = wid.resize_like(small, x)
+    out = {f"pyr{k}": p.t.numpy().copy() for k, p in enumerate(pyr)}
+    out.update(fold=fold.t.numpy().copy(), lap=lap.t.numpy().copy(), down=down.t.numpy().copy(), resize16=small.t.numpy().copy(),
+               resize_like=like.t.numpy().copy())
+    return out
+
+
 def evaluate(ref, style, content, pred, alpha, dtype=torch.float64):
     """The loss lines of train_step (run_strotss.py:136-141) on given sampled features."""
     st = T(torch.tensor(style, dtype=dtype))
@@ -234,6 +324,12 @@ def main():
             out["grad"] = g
         np.savez_compressed(os.path.join(HERE, "ref_" + name + ".npz"), **out)
         print(name, "total", out["total"], "grad_norm", out["grad_norm"])
+    wid = load_reference_widened()
+    xs, idx = sampler_inputs()
+    np.savez_compressed(os.path.join(HERE, "ref_sampler.npz"), indices=idx, bilinear=evaluate_sampler(wid, xs, idx, True),
+                        nearest=evaluate_sampler(wid, xs, idx, False), input_checksum=np.array([float(x.astype(np.float64).sum()) for x in xs]))
+    np.savez_compressed(os.path.join(HERE, "ref_pyramid.npz"), **evaluate_pyramid(wid, pyramid_input()))
+    print("sampler, pyramid written")
 
 
 if __name__ == "__main__":

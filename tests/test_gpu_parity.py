@@ -508,6 +508,21 @@ def test_sampler_forward_is_bit_exact(S, cuda_device, bilinear):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_sampler_against_reference_code_golden(S, cuda_device, mode):
+    """tests/golden/ref_sampler.npz: Sampling._sample executed from the reference's own source (fp32) on ten small maps --
+    the kernel must reproduce it bit for bit."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_reference_golden as G
+    z = np.load(os.path.join(GOLDEN, "ref_sampler.npz"))
+    xs, idx = G.sampler_inputs()
+    assert np.array_equal(idx, z["indices"])
+    got = S.Sampling(G.SAMPLER_N)._sample([_t(x, cuda_device) for x in xs], _t(idx, cuda_device), mode == "bilinear").cpu().numpy()
+    assert got.shape == z[mode].shape
+    assert np.array_equal(got, z[mode])
+
+
 def test_sampler_backward_matches_autograd(S, cuda_device):
     rng = np.random.default_rng(6)
     shapes = [(20, 24, 3), (20, 24, 16), (10, 12, 32), (5, 6, 40)]

@@ -67,6 +67,31 @@ def test_laplacian_pyramid_and_fold(S, cuda_device, shape):
     assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
 
 
+def test_pyramid_against_reference_code_golden(S, cuda_device):
+    """tests/golden/ref_pyramid.npz: make_laplacian_pyramid / fold_laplacian_pyramid / make_laplacian / utils.resize /
+    utils.resize_like executed from the reference's own source (fp64) on a 21 x 30 image."""
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    import make_reference_golden as G
+    z = np.load(os.path.join(golden, "ref_pyramid.npz"))
+    img = G.pyramid_input()[0]
+    x = _img(img, cuda_device)
+    xs = S.make_laplacian_pyramid(x, 5)
+    assert len(xs) == 6
+    for k, a in enumerate(xs):
+        assert tuple(a.shape) == z[f"pyr{k}"].shape
+        assert np.abs(a[0].cpu().numpy() - z[f"pyr{k}"][0]).max() <= ATOL
+    assert np.abs(S.fold_laplacian_pyramid(xs)[0].cpu().numpy() - z["fold"][0]).max() <= ATOL
+    lap, down = S.make_laplacian(x, True)
+    assert np.abs(lap[0].cpu().numpy() - z["lap"][0]).max() <= ATOL and np.abs(down[0].cpu().numpy() - z["down"][0]).max() <= ATOL
+    small = S.resize(x, 16)
+    assert tuple(small.shape) == z["resize16"].shape and np.abs(small[0].cpu().numpy() - z["resize16"][0]).max() <= ATOL
+    like = S.resize_like(small, x)
+    assert np.abs(like[0].cpu().numpy() - z["resize_like"][0]).max() <= ATOL
+
+
 @pytest.mark.parametrize("shape", [(42, 64, 3), (341, 512, 3), (33, 7, 3)])
 def test_fold_backward(S, cuda_device, shape):
     rng = np.random.default_rng(8)
