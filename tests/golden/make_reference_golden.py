@@ -83,7 +83,15 @@ class T:
         return self.t.dtype
 
     def __getitem__(self, idx):
-        return T(self.t[idx])
+        if isinstance(idx, slice):                    # tf.range(h)[offset::step] with a scalar-tensor offset
+            idx = slice(*(None if v is None else int(_raw(v)) for v in (idx.start, idx.stop, idx.step)))
+        return T(self.t[_raw(idx)])
+
+    def __lt__(self, other):
+        return T(self.t < _raw(other))
+
+    def __bool__(self):
+        return bool(self.t)
 
     def __neg__(self):
         return T(-self.t)
@@ -143,6 +151,11 @@ def make_tf_shim() -> types.ModuleType:
     tf.clip_by_value = lambda x, lo, hi: T(torch.minimum(torch.maximum(_raw(x), _raw(lo)), _raw(hi)))
     tf.gather = lambda params, indices, axis=0: T(torch.index_select(_raw(params), axis, _raw(indices).long()))
     tf.concat = lambda xs, axis: T(torch.cat([_raw(x) for x in xs], dim=axis))
+    tf.range = lambda n: T(torch.arange(int(_raw(n))))
+    tf.meshgrid = lambda a, b: [T(m) for m in torch.meshgrid(_raw(a), _raw(b), indexing="xy")]      # TensorFlow's default indexing
+    tf.reduce_max = reduce(torch.amax)
+    tf.greater = lambda a, b: T(_raw(a) > _raw(b))
+    tf.random = types.SimpleNamespace(shuffle=lambda x: x)      # index generation: the candidate list is compared as a set
 
     def gather_nd(params, indices):
         idx = _raw(indices).long()
@@ -180,10 +193,12 @@ def make_tf_shim() -> types.ModuleType:
 
     def resize(images, size, method="bilinear"):
         assert method == "bilinear"
-        x = _raw(images)                                                     # NHWC
+        x = _raw(images)                                                     # NHWC or HWC
         size = [int(v) for v in (_raw(size).tolist() if torch.is_tensor(_raw(size)) else size)]
-        y = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=size, mode="bilinear", align_corners=False, antialias=False)
-        return T(y.permute(0, 2, 3, 1))
+        x4 = x if x.dim() == 4 else x[None]
+        y = torch.nn.functional.interpolate(x4.permute(0, 3, 1, 2), size=size, mode="bilinear", align_corners=False, antialias=False)
+        y = y.permute(0, 2, 3, 1)
+        return T(y if x.dim() == 4 else y[0])
     tf.image.resize = resize
 
     class Module:
@@ -247,7 +262,51 @@ def load_reference_widened(tf=None):
     for name in ("_validate_and_get_shape", "resize", "resize_like"):
         exec(_source_of(ut, name), ns)
     return types.SimpleNamespace(**{k: ns[k] for k in ("Sampling", "make_laplacian", "make_laplacian_pyramid",
-                                                        "fold_laplacian_pyramid", "resize", "resize_like")}, tf=tf)
+                                                        "fold_laplacian_pyramid", "resize", "resize_like")}, tf=tf, ns=ns)
+
+
+class _FixedRng:
+    """Stands in for nn/rand.py's tf_rng inside Sampling._make_indices: returns the given offsets in turn."""
+
+    def __init__(self, values):
+        self.values = list(values)
+
+    def uniform(self, shape, minval, maxval, dtype=None):
+        v = self.values.pop(0)
+        assert minval <= v < maxval
+        return T(torch.tensor(v))
+
+
+INDEX_CASES = {
+    # name: (h, w, bilinear, (off_x, off_y), mask kind)
+    "nearest_42x64": (42, 64, False, (0, 0), None),
+    "bilinear_341x512_off12": (341, 512, True, (1, 2), None),
+    "bilinear_341x512_rect": (341, 512, True, (2, 3), "rect"),
+    "bilinear_170x256_empty": (170, 256, True, (0, 1), "empty"),
+    "nearest_42x64_lowres_mask": (42, 64, False, (0, 0), "lowres"),
+}
+
+
+def index_mask(kind, h, w):
+    if kind is None:
+        return None
+    if kind == "rect":
+        m = np.zeros((h, w, 1), np.float32); m[: h // 3, : w // 2] = 1
+    elif kind == "empty":
+        m = np.zeros((h, w, 1), np.float32)
+    else:                                   # a mask at another resolution: resized with tf.image.resize (:105)
+        m = np.zeros((2 * h + 1, 3 * w, 1), np.float32); m[h // 2:, w:] = 1
+    return m
+
+
+def evaluate_indices(wid, h, w, bilinear, offsets, mask):
+    """All candidate (row, col) pairs of Sampling._make_indices (nn/strotss_utils.py:83-121) in the reference's order
+    (tf.random.shuffle stood in for by the identity, sample_size larger than the candidate count)."""
+    wid.ns["tf_rng"] = _FixedRng(offsets)
+    s = wid.Sampling(10 ** 9)
+    base = T(torch.zeros(1, h, w, 3))
+    ret = s._make_indices(base, bilinear, None if mask is None else T(torch.tensor(mask)))
+    return ret.t.numpy().astype(np.int16)
 
 
 SAMPLER_SHAPES = [(42, 64, 3), (42, 64, 8), (42, 64, 8), (21, 32, 16), (21, 32, 16), (10, 16, 32), (10, 16, 32), (10, 16, 32),
@@ -329,7 +388,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_sampler.npz"), indices=idx, bilinear=evaluate_sampler(wid, xs, idx, True),
                         nearest=evaluate_sampler(wid, xs, idx, False), input_checksum=np.array([float(x.astype(np.float64).sum()) for x in xs]))
     np.savez_compressed(os.path.join(HERE, "ref_pyramid.npz"), **evaluate_pyramid(wid, pyramid_input()))
-    print("sampler, pyramid written")
+    np.savez_compressed(os.path.join(HERE, "ref_indices.npz"),
+                        **{name: evaluate_indices(wid, h, w, bil, off, index_mask(kind, h, w))
+                           for name, (h, w, bil, off, kind) in INDEX_CASES.items()})
+    print("sampler, pyramid, indices written")
 
 
 if __name__ == "__main__":
