@@ -10,6 +10,8 @@ however, is plain Python over a dozen TensorFlow ops.  This script executes the 
     nn/strotss_utils.py:12-81         _clip_and_cast, Sampling._sample                       (fp32, bit-exact)
     nn/strotss_utils.py:139-163       make_laplacian, make_laplacian_pyramid, fold_laplacian_pyramid       
     nn/utils.py:14-41                 _validate_and_get_shape, resize, resize_like
+    run_strotss.py:104-125,131-142    the two nested train_step functions (masked / unmasked), exec'd with stand-ins for
+                                      their closure (a toy feature extractor instead of VGG, tf.GradientTape over torch autograd)
 
 -- against a small stand-in for the `tensorflow` module (`TFShim` below) that implements exactly the ops this path calls,
 on torch fp64 tensors, with TensorFlow's documented semantics (l2_normalize's epsilon inside the
@@ -34,6 +36,7 @@ import ast
 import importlib.util
 import os
 import sys
+import textwrap
 import types
 
 import numpy as np
@@ -201,6 +204,20 @@ def make_tf_shim() -> types.ModuleType:
         return T(y if x.dim() == 4 else y[0])
     tf.image.resize = resize
 
+    class GradientTape:                            # tape.gradient(loss, variables) over torch autograd
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        @staticmethod
+        def gradient(loss, variables):
+            gs = torch.autograd.grad(_raw(loss), [_raw(v) for v in variables], retain_graph=True, allow_unused=True)
+            return [None if g is None else T(g) for g in gs]
+    tf.GradientTape = GradientTape
+    tf.function = lambda fn: fn
+
     class Module:
         def __init__(self, **kwargs):
             pass
@@ -347,6 +364,83 @@ def evaluate_pyramid(wid, img):
     return out
 
 
+# ------------------------------------------------------------------------------ the driver's train_step functions
+def _train_step_sources():
+    text = open(os.path.join(REFERENCE, "run_strotss.py")).read()
+    nodes = [n for n in ast.walk(ast.parse(text)) if isinstance(n, ast.FunctionDef) and n.name == "train_step"]
+    nodes.sort(key=lambda n: n.lineno)
+    assert len(nodes) == 2                        # masked (run_strotss.py:104-125) first, unmasked (:131-142) second
+    return [textwrap.dedent(ast.get_source_segment(text, n, padded=True)) for n in nodes]
+
+
+def _toy_vgg(img):
+    """Stands in for VGG (nn/model.py): two deterministic 'feature maps' of an NHWC image, differentiable."""
+    x = _raw(img)
+    m1 = torch.tensor([[0.5, -0.2, 0.1, 0.3], [0.1, 0.4, -0.3, 0.2], [-0.2, 0.1, 0.6, 0.1]], dtype=x.dtype)
+    m2 = torch.tensor(np.random.default_rng(7).standard_normal((3, 6)), dtype=x.dtype)
+    f1 = torch.relu(x @ m1 + 0.1)
+    pooled = torch.nn.functional.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    f2 = torch.relu(pooled @ m2 + 0.2)
+    return [T(f1), T(f2)]
+
+
+def evaluate_train_steps(alpha=16.0, sample_size=40, dtype=torch.float64):
+    """Runs the reference's masked and unmasked train_step on a toy problem and records the per-region sampled features, so
+    that the composition (per-region StyleLoss targets, alpha / loss_denom weighting, mean over regions) can be checked."""
+    ref = load_reference()
+    wid = load_reference_widened(ref.tf)
+    tf = ref.tf
+    rng = np.random.default_rng(11)
+    content = T(torch.tensor(rng.uniform(0, 1, (1, 24, 32, 3)), dtype=dtype))
+    style = T(torch.tensor(rng.uniform(0, 1, (1, 20, 28, 3)), dtype=dtype))
+    start = T(torch.tensor(rng.uniform(0, 1, (1, 24, 32, 3)), dtype=dtype))
+    st_variables = [T(v.t.clone().requires_grad_(True)) for v in wid.make_laplacian_pyramid(start, levels=2)]
+    cm = np.zeros((2, 24, 32, 1), np.float32); cm[0, :, :16] = 1; cm[1, :, 16:] = 1
+    sm = np.zeros((2, 20, 28, 1), np.float32); sm[0, :10] = 1; sm[1, 10:] = 1
+    content_masks = [T(torch.tensor(m)) for m in cm]
+    style_masks = [T(torch.tensor(m)) for m in sm]
+    wid.ns["tf_rng"] = _FixedRng([0] * 64)
+    sampling = wid.Sampling(sample_size)
+    records = []
+    inner = sampling.bilinear
+
+    def recording_bilinear(xs, ys=None, mask=None):
+        c, p = inner(xs, ys, mask=mask)
+        records.append((c, p))
+        return c, p
+    sampling.bilinear = recording_bilinear
+    vgg = _toy_vgg
+    content_feat = [content] + vgg(content)
+    style_feat = [style] + vgg(style)
+    loss_denom = (2. + alpha + 1. / max(alpha, 1.))                               # run_strotss.py:92
+    loss_styles = [ref.StyleLoss(sampling(style_feat, mask=m), alpha=alpha) for m in style_masks]      # :97-101
+    loss_style = ref.StyleLoss(sampling(style_feat), alpha=alpha)                  # :128
+    ns = dict(tf=tf, strotss=types.SimpleNamespace(fold_laplacian_pyramid=wid.fold_laplacian_pyramid), st_variables=st_variables,
+              vgg=vgg, content_masks=content_masks, sampling=sampling, content_feat=content_feat, loss_content=ref.ContentLoss(),
+              loss_styles=loss_styles, loss_style=loss_style, alpha=alpha, loss_denom=loss_denom)
+    out = {}
+    for tag, src in zip(("masked", "plain"), _train_step_sources()):
+        del records[:]
+        scope = dict(ns)
+        exec(src, scope)
+        res = scope["train_step"]()
+        out[tag + "_loss"] = res["loss"].t.item()
+        out[tag + "_loss_c"] = res["loss_c"].t.item()
+        out[tag + "_loss_s"] = res["loss_s"].t.item()
+        assert all(g is not None for g in res["grads"])                            # the tape reaches the pyramid variables
+        gp = torch.autograd.grad(res["loss"].t, [p.t for _, p in records], retain_graph=True)
+        for r, ((c, p), g) in enumerate(zip(records, gp)):
+            out[f"{tag}_content{r}"] = c.t.detach().numpy().copy()
+            out[f"{tag}_pred{r}"] = p.t.detach().numpy().copy()
+            out[f"{tag}_grad{r}"] = g.numpy().copy()
+        out[tag + "_regions"] = len(records)
+    for r, ls in enumerate(loss_styles):
+        out[f"masked_style{r}"] = ls.target.t.detach().numpy().copy()
+    out["plain_style0"] = loss_style.target.t.detach().numpy().copy()
+    out["alpha"] = alpha
+    return out
+
+
 def evaluate(ref, style, content, pred, alpha, dtype=torch.float64):
     """The loss lines of train_step (run_strotss.py:136-141) on given sampled features."""
     st = T(torch.tensor(style, dtype=dtype))
@@ -391,7 +485,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_indices.npz"),
                         **{name: evaluate_indices(wid, h, w, bil, off, index_mask(kind, h, w))
                            for name, (h, w, bil, off, kind) in INDEX_CASES.items()})
-    print("sampler, pyramid, indices written")
+    np.savez_compressed(os.path.join(HERE, "ref_train_step.npz"), **evaluate_train_steps())
+    print("sampler, pyramid, indices, train_step written")
 
 
 if __name__ == "__main__":
