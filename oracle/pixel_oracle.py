@@ -1,6 +1,9 @@
 """TEST INFRASTRUCTURE (not product code): CPU restatement of the pixel-side step of the reference iteration
-(SURVEY.md section 8f "next #3"), used only by tests/ to check the CUDA kernels.  Parity unpinned: the reference
-ships no tests and TensorFlow cannot be installed here; TF op semantics are restated from their documented behaviour.
+(SURVEY.md section 8f "next #3"), used only by tests/ to check the CUDA kernels.  Parity: the pyramid / resize helpers are
+pinned to the reference's own code (tests/golden/make_reference_golden.py executes nn/strotss_utils.py:139-163 and
+nn/utils.py:32-41 over a stand-in for tf.image.resize; this restatement agrees to 1e-12, tests/test_reference_golden.py).
+Unpinned: tf.image.resize itself and Keras RMSprop -- TensorFlow cannot be installed here, their semantics are restated
+from the documented behaviour (and checked against torch's independent F.interpolate / optim.RMSprop).
 
   tf.image.resize(x, size, method='bilinear')   TF2: half-pixel centres, antialias=False
        in = (out + 0.5) * in_size/out_size - 0.5 ; lo = max(floor(in), 0) ; hi = min(ceil(in), in_size - 1) ;

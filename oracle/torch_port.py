@@ -1,6 +1,7 @@
 """torch-CPU port of the reference op sequence with framework autodiff.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED (see strotss_oracle.py).  This file exists for two purposes:
+Parity status as for strotss_oracle.py: held to the golden vectors of the reference's own loss code
+(tests/golden/ref_*.npz, <= 1e-10), TensorFlow's op semantics unpinned.  This file exists for two purposes:
   1. cross-checking the hand-written gradients of strotss_oracle.py against an independent
      autodiff on inputs without ties (torch and TF differ on ties: torch.min(dim) picks one
      index and torch.maximum splits 0.5/0.5 -- the NumPy oracle encodes TF's rules);
