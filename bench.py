@@ -2,17 +2,28 @@
 """Benchmark of the STROTSS loss hot path (BASELINE.json metric: loss+grad evals/sec at
 N=M=16384, D=2179) on B200, with the CPU restatement of the reference timed beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload large|default]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload large|default|masked]
 
 One "step" = one evaluation: total loss (self-similarity + moment matching + relaxed EMD + palette)
 and its gradient w.r.t. the (N, 2179) prediction hypercolumns, style-side preparation excluded
 (constant per scale, run_strotss.py:100,128).  Prints ONE JSON line on rank 0.
+
+Besides the contract's keys the line carries (all measured in this run, outside the main timed region):
+  rowshard   N>1: ONE evaluation sharded by prediction rows over all GPUs -- evals/s, per-phase times and a parity
+             block (scalars, argmins and this rank's gradient rows against a single-GPU evaluation of the same
+             inputs on the same rank; the run FAILS on a mismatch)
+  extra      the other BASELINE workloads in short form: default sample count (N=M=1024, direct and CUDA-graph
+             replay), masked transfer (R=3 regions), seconds per stylised 512-px image and images/s at 1024 px
+             (bench_e2e.py; one job per GPU)
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import glob
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -30,6 +41,7 @@ WORKLOADS = {
     "masked": (1024, 1024),      # BASELINE.json configs[2]: R = 3 regions (N_r, M_r) of SURVEY 8d, grouped evaluation
 }
 MASKED_REGIONS = [(1024, 1024), (700, 1024), (333, 517)]
+REF_BUDGET_S = 150.0             # wall-clock budget of the timed steps of `--impl reference`
 
 
 def f_alg(N, M, D=D_FEAT):
@@ -48,8 +60,41 @@ def peaks():
         with open(path) as f:
             p = json.load(f)
         return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
-                    source="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_traffic(kernel_substr):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the launches of `kernel_substr` in the newest
+    `profiles/r*_ncu_raw.csv` (an `ncu --set full ... --page raw --csv` export of ONE evaluation) that contains that kernel.
+    -> (bytes summed over the captured launches, number of launches, file name) or None."""
+    def key(path):
+        m = re.match(r"r(\d+)_v(\d+)", os.path.basename(path))
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_raw.csv")), key=key, reverse=True):
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+        except OSError:
+            continue
+        if len(rows) < 3 or "Kernel Name" not in rows[0]:
+            continue
+        hdr, units = rows[0], rows[1]
+        try:
+            kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        tot, n = 0.0, 0
+        for r in rows[2:]:
+            if len(r) > max(kn, rd, wr) and kernel_substr in r[kn]:
+                tot += float(r[rd].replace(",", "")) * _UNIT.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * _UNIT.get(units[wr], 1.0)
+                n += 1
+        if n:
+            return tot, n, os.path.relpath(path, ROOT)
+    return None
 
 
 def synth_torch(N, M, D, eps, seed, device):
@@ -119,11 +164,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU baseline: the torch-CPU port of the reference op sequence (oracle/torch_port.py)
 # ------------------------------------------------------------------------------------------
-def cpu_eval_seconds(n_sample, reps, warmup, threads):
+def cpu_eval_seconds(n_sample, reps, warmup, threads, eps=1.0):
     import torch
     from oracle import torch_port as T
     torch.set_num_threads(threads)
-    st, co, pr = synth_torch(n_sample, n_sample, D_FEAT, 1.0, 0, torch.device("cpu"))
+    st, co, pr = synth_torch(n_sample, n_sample, D_FEAT, eps, 0, torch.device("cpu"))
     for _ in range(warmup):
         T.total_loss_and_grad(st, co, pr, ALPHA)
     times = []
@@ -134,63 +179,104 @@ def cpu_eval_seconds(n_sample, reps, warmup, threads):
     return times
 
 
+def workload_name(N, M, eps, kind):
+    if kind == "large":
+        return f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA} eps={eps}"
+    return f"default sample count N=M={N} D={D_FEAT} alpha={ALPHA} eps={eps}"
+
+
 def run_reference(args, N, M):
-    """`--impl reference`: the reference's own CPU path.  TensorFlow is not installable here, so this
-    times the CPU restatement of the reference op sequence (materialised matrices + framework
-    autodiff), all host threads, each step a bounded sample scaled by the reference FLOP ratio."""
+    """`--impl reference`: the reference's own CPU path at the bench's own configuration.  TensorFlow is not installable
+    here (no network, not in the wheelhouse), so this times the CPU restatement of the reference op sequence
+    (oracle/torch_port.py: materialised N x M / N x N / D x D matrices as at nn/losses.py:15,59,62 + framework autodiff)
+    on all host threads.  Every step is ONE FULL evaluation at the workload's size -- nothing is sampled or scaled.  A full
+    evaluation takes seconds on a CPU, so the number of steps is capped by a wall-clock budget (>= 3 timed steps, >= 1
+    warm-up); the line reports the steps actually timed.  The one-thread figure (the reference pins TensorFlow to one
+    thread, nn/rand.py:16-17) is measured on a stated smaller size."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    from oracle import torch_port as T
     threads = len(os.sched_getaffinity(0))
-    n_s = min(N, 2048)
-    scale = f_ref(N, M) / f_ref(n_s, n_s)
-    times = cpu_eval_seconds(n_s, args.steps, args.warmup, threads)
+    torch.set_num_threads(threads)
+    st, co, pr = synth_torch(N, M, D_FEAT, args.eps, 0, torch.device("cpu"))
+    t0 = time.perf_counter()
+    T.total_loss_and_grad(st, co, pr, ALPHA)                       # warm-up 1 (also the cost probe)
+    t_probe = time.perf_counter() - t0
+    warm = max(1, min(args.warmup, int(0.25 * REF_BUDGET_S / max(t_probe, 1e-6))))
+    steps = max(3, min(args.steps, int(REF_BUDGET_S / max(t_probe, 1e-6))))
+    for _ in range(warm - 1):
+        T.total_loss_and_grad(st, co, pr, ALPHA)
+    times = []
+    loss = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        loss, _, _ = T.total_loss_and_grad(st, co, pr, ALPHA)
+        times.append(time.perf_counter() - t0)
     t_step = sum(times) / len(times)
-    value = 1.0 / (t_step * scale)
-    sample = (f"torch-CPU port of nn/losses.py (fp32, materialised matrices, autograd), N=M={n_s} full evaluation per step, "
-              f"{threads} threads; evals/s scaled to N=M={N} by the reference FLOP ratio {scale:.2f}")
+    value = 1.0 / t_step
+    del st, co, pr
+    n_1 = min(N, 1024)
+    t_1s = cpu_eval_seconds(n_1, 3, 1, 1, args.eps)
+    t_1 = sum(t_1s) / len(t_1s)
+    torch.set_num_threads(threads)
+    sample = (f"torch-CPU port of nn/losses.py (fp32, materialised matrices, autograd): {steps} FULL evaluations at N=M={N} "
+              f"({t_step:.2f} s each) after {warm} warm-up, {threads} threads; no sampling, no scaling")
     line = {
         "impl": "reference", "metric": f"loss+grad evals/sec at N=M={N}, D={D_FEAT}", "value": value, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}"
-                   if N > 1024 else f"default sample count N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}", "sampled_as": f"N=M={n_s}"},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(N, M, args.eps, "large" if N > 1024 else "default"), "sampled_as": f"N=M={N} (full size)",
+                   "same_config": True,
+                   "step_budget": f"a full CPU evaluation takes seconds, so the timed steps are capped at {REF_BUDGET_S:.0f} s of wall clock "
+                                  f"(>= 3 steps): {steps} of the {args.steps} requested were timed"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample,
+                         "value_1_thread_at_small_size": 1.0 / t_1,
+                         "sample_1_thread": f"same port pinned to 1 thread (nn/rand.py:16-17), 3 evaluations at N=M={n_1}: {t_1:.3f} s each "
+                                            f"(evals/s at THAT size, not scaled)"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "loss": float(loss),
     }
     print(json.dumps(line), flush=True)
+
+
+def timed_events(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def masked_problem(dev, eps):
+    probs = [synth_torch(N, M, D_FEAT, eps, 100 + r, dev) for r, (N, M) in enumerate(MASKED_REGIONS)]
+    return [p[0] for p in probs], [p[1] for p in probs], [p[2] for p in probs]
 
 
 def run_masked(args, dev, S, _lib):
     """BASELINE configs[2] (masked region-guided transfer): one step = the loss + gradient of one masked train_step
     (run_strotss.py:112-124) over R = 3 ragged regions, grouped (one C-ABI call, regions on concurrent streams)
     against the same regions evaluated one after the other through strotss_eval."""
-    import torch
-    probs = [synth_torch(N, M, D_FEAT, args.eps, 100 + r, dev) for r, (N, M) in enumerate(MASKED_REGIONS)]
-    styles = [p[0] for p in probs]; contents = [p[1] for p in probs]; preds = [p[2] for p in probs]
+    styles, contents, preds = masked_problem(dev, args.eps)
     h = S.Handle(dev)
     h.set_style_targets_grouped(styles)
     singles = []
     for st in styles:
         hs = S.Handle(dev); hs.set_style_target(st); singles.append(hs)
-
-    def timed(fn):
-        for _ in range(max(args.warmup, 3)):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            out = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / args.steps, out
-
+    import torch
     l0 = h.launch_count
-    ms_g, out = timed(lambda: h.eval_grouped(preds, contents, ALPHA, True))
+    ms_g, out = timed_events(torch, lambda: h.eval_grouped(preds, contents, ALPHA, True), args.steps, max(args.warmup, 3))
     launches = (h.launch_count - l0) // (args.steps + max(args.warmup, 3))
-    ms_s, _ = timed(lambda: [hs.eval(p, c, ALPHA, True) for hs, p, c in zip(singles, preds, contents)])
+    ms_s, _ = timed_events(torch, lambda: [hs.eval(p, c, ALPHA, True) for hs, p, c in zip(singles, preds, contents)], args.steps,
+                           max(args.warmup, 3))
     line = {"metric": "masked train_step loss+grad evals/sec, R=3 regions", "value": 1000.0 / ms_g, "unit": "evals/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_g, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -199,6 +285,53 @@ def run_masked(args, dev, S, _lib):
             "gpu_launches_per_step": int(launches), "sequential_ms_per_step": ms_s,
             "loss": float(out[0][_lib.S_TOTAL].item())}
     print(json.dumps(line), flush=True)
+
+
+def extra_workloads(args, dev, S, _lib, torch, world, rank, barrier, max_over_ranks):
+    """Short forms of the other BASELINE workloads, so that the driver's BENCH / SCALE records carry them:
+    default sample count (configs[1]'s per-iteration loss), masked transfer (configs[2]), seconds per stylised image
+    (metric part ii, configs[1]) and 1024-px images/s with one job per GPU (configs[4])."""
+    out = {}
+    steps = 50
+    if rank == 0:
+        # ---- N = M = 1024, direct launches and CUDA-graph replay
+        style, content, pred = synth_torch(1024, 1024, D_FEAT, args.eps, 0, dev)
+        h = S.Handle(dev)
+        h.set_style_target(style)
+        ms_d, _ = timed_events(torch, lambda: h.eval(pred, content, ALPHA, True, False), steps, 5)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            h.eval(pred, content, ALPHA, True, False)
+        ms_g, _ = timed_events(torch, graph.replay, steps, 5)
+        out["default_ms_per_step"] = {"direct": round(ms_d, 4), "graph_replay": round(ms_g, 4), "workload": "N=M=1024, D=2179, loss+grad"}
+        del graph, h
+        # ---- masked transfer, R = 3 regions, one grouped call
+        styles, contents, preds = masked_problem(dev, args.eps)
+        hm = S.Handle(dev)
+        hm.set_style_targets_grouped(styles)
+        ms_m, _ = timed_events(torch, lambda: hm.eval_grouped(preds, contents, ALPHA, True), steps, 5)
+        out["masked_ms_per_step"] = {"grouped": round(ms_m, 4), "workload": f"R=3 regions {MASKED_REGIONS}, one strotss_eval_grouped call"}
+        del hm
+    barrier()
+    if not args.no_image:
+        import bench_e2e
+        # metric part ii: one stylised 512-px image (steady state: the per-scale graphs are captured in an untimed pass);
+        # every rank runs its own job, the slowest rank sets the time
+        r512 = bench_e2e.run_images(dev, level=4, max_iter=200, sample=1024, images=1, warm_iters=3)
+        barrier()
+        t512 = max_over_ranks(r512["seconds_per_image"])
+        out["sec_per_image_512"] = {"value": t512, "unit": "s/image", "images_per_s_all_gpus": world / t512,
+                                    "config": "4 scales x 200 iterations, Sampling(1024), synthetic images, random VGG16 weights "
+                                              "(torch/cuDNN stand-in for the reference's TF/cuDNN path), one job per GPU"}
+        bench_e2e.reset()
+        r1k = bench_e2e.run_images(dev, level=5, max_iter=200, sample=1024, images=1, warm_iters=3)
+        barrier()
+        t1k = max_over_ranks(r1k["seconds_per_image"])
+        out["images_1024"] = {"sec_per_image": t1k, "images_per_s_all_gpus": world / t1k, "jobs": world,
+                              "config": "BASELINE configs[4] in short form: 1024-px long side (--level 5), one job per GPU, "
+                                        "1 timed image per GPU; the 64-pair run is bench_e2e.py --gpus N --level 5 --pairs 64"}
+        bench_e2e.reset()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -211,6 +344,8 @@ def main():
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--eps", type=float, default=1.0, help="pred = content + eps*noise (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short default / masked / image workloads")
+    ap.add_argument("--no-image", action="store_true", help="skip the end-to-end image part of the extra workloads")
     ap.add_argument("--samples", type=int, default=0,
                     help="override the sample count N = M of the workload (SURVEY 8d sweep: 1024 ... 16384)")
     ap.add_argument("--graph", action="store_true",
@@ -238,6 +373,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    from strotss_tensorflow_b200 import hostmem
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -314,9 +450,11 @@ def main():
     # (a) serial: strotss_eval_host, one blocking call per step; (b) pipelined: strotss_eval_host_submit/_wait with two
     # evaluations in flight, so the PCIe copies of neighbouring steps overlap the kernels (independent evaluations --
     # BASELINE "throughput mode").  (b) is the headline e2e; (a) is reported beside it.
-    ph = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory(); ph.copy_(pred)
-    ch = torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory(); ch.copy_(content)
-    gh = [torch.empty(N, D_FEAT, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # staging buffers: pinned, allocated on the NUMA node of this rank's GPU (strotss_tensorflow_b200/hostmem.py)
+    topo = {}
+    ph = hostmem.pinned_empty((N, D_FEAT), local, record=topo); ph.copy_(pred)
+    ch = hostmem.pinned_empty((N, D_FEAT), local); ch.copy_(content)
+    gh = [hostmem.pinned_empty((N, D_FEAT), local) for _ in range(2)]
     sh = [torch.empty(_lib.NUM_SCALARS, dtype=torch.float32) for _ in range(2)]
     for _ in range(2):
         h.eval_host(ph, ch, ALPHA, gh[0], sh[0])
@@ -344,9 +482,30 @@ def main():
     t0 = time.perf_counter()
     pipelined(e2e_steps)
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    e2e_ms_own = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = max_over_ranks(e2e_ms_own)
     e2e_loss = float(sh[(e2e_steps - 1) & 1][_lib.S_TOTAL])
+    # raw host<->device copy rates of this rank's staging buffers (one direction at a time), for the e2e analysis
+    def copy_rate(dst, src, reps=4):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * src.numel() * 4 / (time.perf_counter() - t) / 1e9
     barrier()
+    h2d_gbs = copy_rate(pred, ph)
+    barrier()
+    d2h_gbs = copy_rate(gh[0], grad)
+    pred.copy_(ph)
+    rates = None
+    if world > 1:
+        t = torch.tensor([h2d_gbs, d2h_gbs], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        rates = [[round(float(v), 1) for v in a.tolist()] for a in allr]
+    barrier()
+    del ph, ch, gh
 
     # ---- N>1, replicas mode: also time ONE evaluation row-sharded over all GPUs (same inputs everywhere) ----
     shard_info = None
@@ -359,6 +518,8 @@ def main():
         for _ in range(3):
             hs.eval(pred0, content0, ALPHA, True, False)
         barrier()
+        hs.profile_enable(True)
+        hs.profile_read()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(args.steps):
@@ -366,11 +527,45 @@ def main():
         s1.record()
         barrier()
         ms_shard = max_over_ranks(s0.elapsed_time(s1) / args.steps)
+        sphases = hs.profile_read()
+        hs.profile_enable(False)
         r0s, r1s = hs.shard_rows(N)
+        # parity of the sharded evaluation against a single-GPU evaluation of the same inputs on this rank (outside the timed loop)
+        sc_s, g_s, ra_s, ca_s = hs.eval(pred0, content0, ALPHA, True, True)
+        solo = S.Handle(dev)
+        solo.set_style_target(style0)
+        sc_1, g_1, ra_1, ca_1 = solo.eval(pred0, content0, ALPHA, True, True)
+        torch.cuda.synchronize()
+        d_sc = float((sc_s[:12] - sc_1[:12]).abs().max() / sc_1[:12].abs().max())
+        d_g = float((g_s[r0s:r1s] - g_1[r0s:r1s]).norm() / g_1[r0s:r1s].norm()) if r1s > r0s else 0.0
+        rows_eq = float((ra_s == ra_1).float().mean())
+        cols_eq = float((ca_s[r0s:r1s] == ca_1[r0s:r1s]).float().mean()) if r1s > r0s else 1.0
+        par = torch.tensor([d_sc, d_g, 1.0 - rows_eq, 1.0 - cols_eq], device=dev, dtype=torch.float64)
+        dist.all_reduce(par, op=dist.ReduceOp.MAX)
+        par = [float(v) for v in par.tolist()]
+        # the two evaluations run different tile schedules (the single GPU exploits the symmetry of the self-similarity
+        # matrices, a shard cannot): scalars agree to fp32 summation order, gradient rows to the bf16 rounding of P
+        ok = par[0] <= 1e-4 and par[1] <= 2e-3 and par[2] <= 1e-3 and par[3] <= 1e-3
         shard_info = {"value": 1000.0 / ms_shard, "unit": "evals/s", "ms_per_step": ms_shard, "scaling": "strong",
                       "rows_per_rank": r1s - r0s, "loss": float(sc_s[_lib.S_TOTAL].item()),
-                      "collectives_per_eval": f"1 allreduce-max of 2x{M} packed u64 minima + 1 allreduce-sum of {16 + D_FEAT} floats (NCCL)"}
-        del hs
+                      "collectives_per_eval": hs.collectives_note(M, D_FEAT) if hasattr(hs, "collectives_note") else
+                      f"1 allreduce-max of 2x{M} packed u64 minima + 1 allreduce-sum of {16 + D_FEAT} floats (NCCL)",
+                      "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sphases.items()},
+                      "parity": {"vs": "single-GPU strotss_eval of the same inputs on every rank; max over ranks",
+                                 "scalars_max_rel_diff": par[0], "own_grad_rows_rel_diff": par[1],
+                                 "row_argmin_mismatch_frac": par[2], "col_argmin_mismatch_frac": par[3], "ok": ok}}
+        del hs, solo
+        if not ok:
+            if rank == 0:
+                print(json.dumps({"error": "row-sharded evaluation disagrees with the single-GPU one", "rowshard": shard_info}), flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(1)
+
+    extra = {}
+    if not args.no_extra and args.workload == "large" and args.samples == 0 and graph is None:
+        del pred, content, style, grad
+        torch.cuda.empty_cache()
+        extra = extra_workloads(args, dev, S, _lib, torch, world, rank, barrier, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -380,50 +575,65 @@ def main():
     pk = peaks()
     jobs = 1 if rowshard else world                     # evaluations completed per step across the job
     value = jobs * 1000.0 / ms_step
-    # dominant kernel: self-similarity stage 1 (one launch per 2048-row panel).  Algorithmic work of the
+    timed_region_s = ms_step * args.steps * 1e-3
+    burst = timed_region_s < 1.0                        # MEASURED_PEAKS: burst figure for short regions, sustained for long ones
+    peak = pk["tf_burst"] if burst else pk["tf_sust"]
+    # dominant kernel: self-similarity stage 1 (one launch per 4096-row panel).  Algorithmic work of the
     # launches of one step = the two Gram products Xd, Yd restricted to this rank's rows (2*(2*N^2*D)
     # per evaluation); the kernel executes 3 bf16 K-passes (delta form) over the tiles it visits -- all of them
-    # when row-sharded, the upper block triangle (36/64 at 8 panels) on a single GPU where symmetry is exploited.
+    # when row-sharded, the upper block triangle on a single GPU where symmetry is exploited.
     ss1_ms, ss1_n = phases.get("ss_stage1_gemm", (0.0, 0))
     own_rows = h.shard_rows(N)[1] - h.shard_rows(N)[0] if rowshard else N
     alg_flops_step = 2 * (2.0 * own_rows * N * D_FEAT)
-    # tiles visited / all tiles: everything when row-sharded or for a single panel; on one GPU the exact upper block
-    # triangle of 256 x 256 tiles (rectangular panels, 36/64 at N = 16384, with STROTSS_NO_TRAP=1)
     nt = -(-N // 256)
     if rowshard or N <= 2048:
         visited = 1.0
     elif os.environ.get("STROTSS_NO_TRAP"):
-        ph = int(os.environ.get("STROTSS_PANEL", "4096"))
-        visited = sum(min(ph, N - p * ph) * (N - p * ph) for p in range(-(-own_rows // ph))) / (float(N) * N)
+        pnl = int(os.environ.get("STROTSS_PANEL", "4096"))
+        visited = sum(min(pnl, N - p * pnl) * (N - p * pnl) for p in range(-(-own_rows // pnl))) / (float(N) * N)
     else:
         visited = nt * (nt + 1) / 2.0 / (nt * nt)
     ach = alg_flops_step / (ss1_ms / args.steps * 1e-3) / 1e12 if ss1_n else None
+    lps = ss1_n / args.steps if ss1_n else None
+    traffic = traffic_src = None
+    default_build = not any(os.environ.get(k) for k in ("STROTSS_NO_TRAP", "STROTSS_PANEL", "STROTSS_SS1_MERGED", "STROTSS_NO_PAIR"))
+    if world == 1 and N == 16384 and default_build and lps:
+        tr = ncu_traffic("ss1_pair_merged_kernel")
+        if tr is not None and tr[1] % int(round(lps)) == 0:
+            traffic = tr[0] / (tr[1] / lps)             # bytes per step = all launches of one evaluation
+            traffic_src = tr[2]
+    # algorithmic bytes of stage 1 per evaluation (operands read once, no N x N traffic): x^, y^, delta in bf16
+    dp = -(-D_FEAT // 64) * 64
+    alg_bytes = 3.0 * N * dp * 2
     roof = {"bound": "tensor", "kernel": "ss1_pair_merged_kernel (self-similarity stage 1, cta_group::2; all launches of a step)",
-            "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": (ach / pk["tf_sust"]) if ach else None,
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+            "peak_source": pk["source"] + (": bf16 BURST (timed region %.3f s < 1 s)" % timed_region_s if burst else
+                                           ": bf16 SUSTAINED (timed region %.1f s)" % timed_region_s),
             "frac_of_burst_peak": (ach / pk["tf_burst"]) if ach else None,
-            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one step of the DEFAULT build at this
-            # workload (4096-row panels, triangle walk, merged K loop: profiles/r01_v21_ss1_merged_remd_skew_ncu_summary.txt;
-            # the kernel with three separate K loops moved 1.808e9); other switch settings: not captured
-            "traffic": 1.628e9 if (world == 1 and N == 16384 and not os.environ.get("STROTSS_NO_TRAP")
-                                   and not os.environ.get("STROTSS_PANEL") and not os.environ.get("STROTSS_SS1_MERGED")) else None,
-            "traffic_unit": "bytes per step (all launches of the kernel)",
-            # operands: A 4 panels x 3 x 4096 x 2240 bf16 = 220 MB, B 550 MB; P panels 2080 tiles x 128 KB = 272 MB
-            "algorithmic_bytes": 1.042e9 if (world == 1 and N == 16384) else None,
-            "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-            "launches_per_step": ss1_n / args.steps if ss1_n else None,
+            "frac_of_sustained_peak": (ach / pk["tf_sust"]) if ach else None,
+            "traffic": traffic, "traffic_unit": "DRAM bytes per step (all launches of the kernel in one evaluation; ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": traffic_src,
+            "algorithmic_bytes": alg_bytes if (world == 1 or rowshard) else None,
+            "algorithmic_bytes_note": "three bf16 operands (x^, y^, delta; N x 2240) read once; the bf16 P panel the kernel also writes "
+                                      "(the sign matrix handed to stage 2) is NOT algorithmic traffic: it is the deviation from "
+                                      "'no N x N object reaches HBM' discussed in DESIGN.md",
+            "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+            "launches_per_step": lps,
             "achieved_executed": (ach * 1.5 * visited) if ach else None,
             "executed_over_algorithmic": 1.5 * visited,
+            "frac_executed_of_burst_peak": (ach * 1.5 * visited / pk["tf_burst"]) if ach else None,
             "note": "algorithmic = 2 Gram GEMMs (Xd, Yd); executed = 3 bf16 K-passes over the visited tiles "
-                    "(symmetry: only the upper block triangle, 2080 of 4096 tiles at N = 16384, is visited on a single GPU)"}
+                    "(symmetry: only the upper block triangle, 2080 of 4096 tiles at N = 16384, is visited on a single GPU), so "
+                    "frac can exceed 1; frac_executed_of_burst_peak is the hardware-utilisation figure"}
+    gemm_ms = sum(phases.get(k, (0.0, 0))[0] for k in ("remd_gemm", "cov_fwd_gemm", "cov_bwd_gemm", "ss_stage1_gemm", "ss_stage2_gemm")) / args.steps
+    all_ms = sum(v[0] for v in phases.values()) / args.steps
     line = {
         "metric": f"loss+grad evals/sec at N=M={N}, D={D_FEAT}", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if rowshard else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"large-sample loss microbench N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}"
-                   if args.workload == "large" else f"default sample count N=M={N} D={D_FEAT} alpha={ALPHA} eps={args.eps}",
+        "config": {"workload": workload_name(N, M, args.eps, args.workload),
                    "parallelism": "single GPU" if world == 1 else (
-                       f"one evaluation row-sharded over {world} GPUs by prediction rows; per evaluation one NCCL allreduce-max of "
-                       f"2x{M} packed u64 minima + one allreduce-sum of {16 + D_FEAT} floats" if rowshard
+                       f"one evaluation row-sharded over {world} GPUs by prediction rows" if rowshard
                        else f"{world} independent replicas (one problem per GPU, no collective)"),
                    "l2": "inputs (3 x %.0f MB fp32) exceed the 126 MB L2; no flush" % (N * D_FEAT * 4 / 1e6)
                    if N * D_FEAT * 4 * 3 > 126e6 else "inputs fit in L2 (launch-bound regime)",
@@ -435,41 +645,46 @@ def main():
                 "mode": "strotss_eval_host_submit/_wait, 2 evaluations in flight (host<->device copies of neighbouring steps "
                         "overlap the kernels); every step copies its inputs from pinned host memory and reads scalars + gradient back",
                 "serial_value": jobs * 1000.0 / e2e_serial_ms, "serial_ms_per_step": e2e_serial_ms,
-                "serial_mode": "strotss_eval_host, one blocking call per step", "loss": e2e_loss},
+                "serial_mode": "strotss_eval_host, one blocking call per step", "loss": e2e_loss,
+                "h2d_gbs_this_rank": round(h2d_gbs, 1), "d2h_gbs_this_rank": round(d2h_gbs, 1),
+                "h2d_d2h_gbs_per_rank": rates, "host_placement": topo},
         "gpu_launches": int(launches),
         "roofline": roof,
         "whole_eval": {"f_alg": f_alg(N, M), "tflops_alg": f_alg(N, M) / (ms_step * 1e-3) / 1e12,
                        "frac_of_burst_peak": f_alg(N, M) / (ms_step * 1e-3) / 1e12 / pk["tf_burst"],
                        "frac_of_sustained_peak": f_alg(N, M) / (ms_step * 1e-3) / 1e12 / pk["tf_sust"]},
         "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in phases.items()},
+        "phases_summary": {"gemm_ms": round(gemm_ms, 4), "non_gemm_ms": round(all_ms - gemm_ms, 4)},
         "loss": total,
     }
     if shard_info is not None:
         line["rowshard"] = shard_info
+    if extra:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
+        # the CPU restatement at the bench's own size: ONE full evaluation on all host threads (a second one if the first took
+        # < 8 s), preceded by a small probe; falls back to N = M = 8192 (stated) only if the probe predicts > 40 s
         threads = len(os.sched_getaffinity(0))
-        n_s = min(N, 2048)
-        t_probe = cpu_eval_seconds(n_s, 1, 1, threads)[0]
-        if N >= 4096 and t_probe * (f_ref(4096, 4096) / f_ref(n_s, n_s)) < 12.0:
-            n_s = 4096
-        t_one = t_probe * (f_ref(n_s, n_s) / f_ref(min(N, 2048), min(N, 2048)))
-        reps = max(2, min(24, int(10.0 / max(t_one, 1e-3))))          # ~10 s of all-core CPU work
-        times = cpu_eval_seconds(n_s, reps, 0, threads)
-        t = sum(times) / len(times)
+        t_probe = cpu_eval_seconds(min(N, 2048), 1, 1, threads)[0]
+        predicted = t_probe * f_ref(N, M) / f_ref(min(N, 2048), min(N, 2048))
+        n_s = N if predicted <= 40.0 else min(N, 8192)
+        times = cpu_eval_seconds(n_s, 1, 0, threads)
+        if times[0] < 8.0:
+            times += cpu_eval_seconds(n_s, 1, 0, threads)
+        t = min(times)
         scale = f_ref(N, M) / f_ref(n_s, n_s)
-        # the reference pins TensorFlow to one intra-op / one inter-op thread (nn/rand.py:16-17): time that setting too,
-        # on a smaller sample (N = M = 1024, one evaluation)
         n_1 = min(N, 1024)
-        t_1s = cpu_eval_seconds(n_1, 5, 1, 1)
+        t_1s = cpu_eval_seconds(n_1, 3, 1, 1)
         t_1 = sum(t_1s) / len(t_1s)
-        one_thread = 1.0 / (t_1 * f_ref(N, M) / f_ref(n_1, n_1))
         line["cpu_baseline"] = {
             "value": 1.0 / (t * scale), "unit": "evals/s", "cores": threads, "kind": "port",
-            "value_1_thread": one_thread,
-            "sample_1_thread": f"same port pinned to 1 thread (the reference's own setting, nn/rand.py:16-17), 5 evaluations at "
-                               f"N=M={n_1} ({t_1:.2f} s), scaled by the reference FLOP ratio",
-            "sample": f"torch-CPU port of the reference op sequence (fp32, materialised matrices, autograd), {reps} evaluations at "
-                      f"N=M={n_s} ({t:.2f} s each), scaled to N=M={N} by the reference FLOP ratio {scale:.2f}"}
+            "sample": (f"torch-CPU port of the reference op sequence (fp32, materialised matrices, autograd): {len(times)} FULL "
+                       f"evaluation(s) at N=M={n_s} ({t:.2f} s, best), {threads} threads" +
+                       ("; no scaling" if n_s == N else f"; scaled to N=M={N} by the reference FLOP ratio {scale:.2f}")),
+            "same_config": n_s == N,
+            "value_1_thread_at_small_size": 1.0 / t_1,
+            "sample_1_thread": f"same port pinned to 1 thread (the reference's own setting, nn/rand.py:16-17), 3 evaluations at "
+                               f"N=M={n_1}: {t_1:.3f} s each (evals/s at THAT size, not scaled)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -11,7 +11,9 @@ What is measured and what is not:
     the default graph mode, torch ops with --eager.
 The stylised image is therefore meaningless; only the time is reported.  One JSON line on stdout.
 
-    python bench_e2e.py [--max_iter 200] [--level 4] [--sample 1024]
+    python bench_e2e.py [--max_iter 200] [--level 4] [--sample 1024] [--pairs 1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 bench_e2e.py --gpus 8 --level 5 --pairs 64
+        (BASELINE configs[4]: 64 independent pairs at 1024 px, one process per GPU as the reference's --gpu_id implies)
 """
 from __future__ import annotations
 
@@ -101,50 +103,112 @@ def fold_pyramid_torch(xs):                     # nn/strotss_utils.py:159-163 (t
     return ret
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--max_iter", type=int, default=200)
-    ap.add_argument("--level", type=int, default=4)
-    ap.add_argument("--sample", type=int, default=1024)
-    ap.add_argument("--lr", type=float, default=2e-3)
-    ap.add_argument("--eager", action="store_true", help="launch every iteration op by op instead of replaying a CUDA graph")
-    args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+class _Cfg:
+    def __init__(self, level, sample, lr=2e-3, eager=False):
+        self.level, self.sample, self.lr, self.eager = level, sample, lr, eager
+
+
+_VGG = {}
+
+
+def _setup(dev, sample):
     torch.manual_seed(0)
     gen = torch.Generator(device=dev).manual_seed(0)
     content = torch.rand(1, 3, 321, 481, generator=gen, device=dev)
     style = torch.rand(1, 3, 1600, 1200, generator=gen, device=dev)
-    vgg = VGG16Features().to(dev).to(memory_format=torch.channels_last)
-    sampling = S.Sampling(args.sample, torch.Generator().manual_seed(0))
+    vgg = _VGG.get(dev.index)
+    if vgg is None:
+        vgg = VGG16Features().to(dev).to(memory_format=torch.channels_last)
+        _VGG[dev.index] = vgg
+    sampling = S.Sampling(sample, torch.Generator().manual_seed(0))
 
     def feats(img):
         return [nhwc(img)] + [nhwc(f) for f in vgg(img.contiguous(memory_format=torch.channels_last))]
 
-    def run(max_iter):
-        return _run(args, content, style, sampling, feats, vgg, max_iter)
+    return content, style, vgg, sampling, feats
 
-    run(3)                                       # warm-up: module load, workspace growth, per-scale graph capture
+
+def reset():
+    """Drop the captured per-scale graphs (and their static buffers)."""
+    _SCALE_GRAPHS.clear()
+    torch.cuda.empty_cache()
+
+
+def run_images(dev, level=4, max_iter=200, sample=1024, images=1, warm_iters=3, eager=False, lr=2e-3):
+    """`images` stylised images one after the other on `dev` (the job of ONE GPU in BASELINE configs[4]'s throughput mode,
+    run_strotss.py:70-71,145-152,176-179: `--gpu_id` = one process per GPU).  An untimed pass of `warm_iters` iterations
+    per scale captures the per-scale graphs; the timed images reuse them.  -> dict with seconds_per_image."""
+    cfg = _Cfg(level, sample, lr, eager)
+    content, style, vgg, sampling, feats = _setup(dev, sample)
+    with torch.cuda.device(dev):
+        _run(cfg, content, style, sampling, feats, vgg, warm_iters)
+        torch.cuda.synchronize(dev)
+        t_all = time.perf_counter()
+        per_scale = None
+        for _ in range(images):
+            per_scale = _run(cfg, content, style, sampling, feats, vgg, max_iter)
+        torch.cuda.synchronize(dev)
+        total = time.perf_counter() - t_all
+    return {"seconds": total, "images": images, "seconds_per_image": total / images, "per_scale_last_image": per_scale}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--max_iter", type=int, default=200)
+    ap.add_argument("--level", type=int, default=4, help="number of scales; 4 = 512 px, 5 = 1024 px long side (run_strotss.py:70-71)")
+    ap.add_argument("--sample", type=int, default=1024)
+    ap.add_argument("--lr", type=float, default=2e-3)
+    ap.add_argument("--pairs", type=int, default=1, help="content/style pairs of the whole job (BASELINE configs[4]: 64), split over the GPUs")
+    ap.add_argument("--gpus", type=int, default=1, help="informational; under torchrun every rank drives the GPU LOCAL_RANK")
+    ap.add_argument("--eager", action="store_true", help="launch every iteration op by op instead of replaying a CUDA graph")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    mine = args.pairs // world + (1 if rank < args.pairs % world else 0)       # independent jobs: no data-path collective
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
-    t_all = time.perf_counter()
-    per_scale = run(args.max_iter)
-    torch.cuda.synchronize()
-    total = time.perf_counter() - t_all
-    print(json.dumps({
-        "metric": "end-to-end seconds per stylised image, 512 px long side, default settings", "value": total, "unit": "s/image",
-        "higher_is_better": False, "n_gpus": 1, "data": "synthetic images (content 321x481, style 1600x1200), random VGG16 weights",
-        "config": {"level": args.level, "max_iter": args.max_iter, "sample_size": args.sample, "optimizer": "RMSprop(0.99, 1e-8)",
-                   "vgg": "torch/cuDNN conv stack, fp32 tensors, channels_last (stand-in for the reference's TF/cuDNN path)",
-                   "loss_path": "strotss_tensorflow_b200 (fused sampler + loss/grad kernels)",
-                   "launch": "eager (op by op)" if args.eager else
-                             "one CUDA graph per scale: fold + VGG fwd + sampler + loss/grad + VGG bwd + RMSprop, captured once per "
-                             "process (in the warm-up pass) and reused for every image: a new image only copies its content "
-                             "features / initial pyramid into the graph's buffers and re-prepares the style target; sample indices "
-                             "are drawn on the host and copied into the graph's index buffer each iteration; the loss scalar is "
-                             "read back every iteration",
-                   "pixel_side": "torch ops" if args.eager else "strotss_pyramid_fold / _fold_backward / strotss_rmsprop_step (this repo)",
-                   "warmup": "one untimed pass of 3 iterations per scale (it also captures the per-scale graphs: steady-state "
-                             "per-image time, as for the 2nd..64th image of BASELINE configs[4])"},
-        "per_scale": per_scale}))
+    t_job = time.perf_counter()
+    res = run_images(dev, args.level, args.max_iter, args.sample, max(mine, 1), 3, args.eager, args.lr) if mine > 0 else None
+    own = res["seconds"] if res else 0.0
+    wall = own
+    per_rank = [own]
+    if world > 1:
+        t = torch.tensor([own], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(a.item()) for a in allt]
+        wall = max(per_rank)
+    if rank == 0:
+        px = 2 << (4 + args.level)
+        print(json.dumps({
+            "metric": f"end-to-end seconds per stylised image, {px} px long side, default settings",
+            "value": wall / max(1, -(-args.pairs // world)), "unit": "s/image (per GPU; slowest rank)",
+            "images_per_s": args.pairs / wall, "pairs": args.pairs, "n_gpus": world, "seconds_timed_per_rank": per_rank,
+            "wall_seconds_incl_warmup_and_capture": time.perf_counter() - t_job,
+            "higher_is_better": False, "scaling": "weak (independent jobs, one process per GPU, no collective)",
+            "data": "synthetic images (content 321x481, style 1600x1200), random VGG16 weights",
+            "config": {"level": args.level, "max_iter": args.max_iter, "sample_size": args.sample, "optimizer": "RMSprop(0.99, 1e-8)",
+                       "vgg": "torch/cuDNN conv stack, fp32 tensors, channels_last (stand-in for the reference's TF/cuDNN path)",
+                       "loss_path": "strotss_tensorflow_b200 (fused sampler + loss/grad kernels)",
+                       "launch": "eager (op by op)" if args.eager else
+                                 "one CUDA graph per scale: fold + VGG fwd + sampler + loss/grad + VGG bwd + RMSprop, captured once per "
+                                 "process (in the warm-up pass) and reused for every image: a new image only copies its content "
+                                 "features / initial pyramid into the graph's buffers and re-prepares the style target; sample indices "
+                                 "are drawn on the host and copied into the graph's index buffer each iteration; the loss scalar is "
+                                 "read back every iteration",
+                       "pixel_side": "torch ops" if args.eager else "strotss_pyramid_fold / _fold_backward / strotss_rmsprop_step (this repo)",
+                       "warmup": "one untimed pass of 3 iterations per scale (it also captures the per-scale graphs: steady-state "
+                                 "per-image time, as for the 2nd..64th image of BASELINE configs[4])"},
+            "per_scale": res["per_scale_last_image"] if res else None}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 class ScaleGraph:
@@ -190,7 +254,7 @@ class ScaleGraph:
                 d.copy_(src)
             for v, src in zip(self.variables, S.make_laplacian_pyramid(stylized_nhwc, 5)):
                 v.copy_(src)
-            for slot in self.opt._slots.values():
+            for slot in self.opt.slots():
                 slot.zero_()
         self.loss_fn.handle.set_style_target(style_samples)
 

@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <functional>
 #include <unordered_map>
+#include <atomic>
 
 #include "../../include/strotss_b200.h"
 #include "gemm_core.cuh"
@@ -32,6 +33,15 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: a process that creates handles on several GPUs
+// (strotss_create takes a device index) must configure each kernel once on each of them.  One bit per device, set atomically
+// (the region workers of a grouped evaluation launch concurrently).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool needed(int device) const { return ((mask.load(std::memory_order_acquire) >> (device & 63)) & 1ull) == 0; }
+    void done(int device) { mask.fetch_or(1ull << (device & 63), std::memory_order_release); }
+};
 
 // cast fp32 -> bf16 with zero padding of the K dimension (debug GEMM only)
 __global__ void cast_pad_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst, int ldp) {
@@ -66,8 +76,11 @@ __global__ void mean_scalars_kernel(const float* __restrict__ src, int R, int n,
     mean[k] = s / static_cast<float>(R);
 }
 
-__global__ void copy_scalars_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, float* __restrict__ dst) {
-    if (threadIdx.x < n) dst[threadIdx.x] = src[idx[threadIdx.x]];
+// the slot indices travel by value (kernel parameters): nothing is staged through the host, so the per-function entry points
+// are capturable into a CUDA graph like strotss_eval
+__global__ void copy_scalars_kernel(const float* __restrict__ src, int4 idx, int n, float* __restrict__ dst) {
+    const int t = threadIdx.x;
+    if (t < n) dst[t] = src[t == 0 ? idx.x : (t == 1 ? idx.y : (t == 2 ? idx.z : idx.w))];
 }
 
 }  // namespace
@@ -318,10 +331,10 @@ int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     auto kern = gemm_kernel<BN, NACC, STAGES, EPI_WARPS, Epi, A_MN>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.done(h->device);
     }
     const int tiles = p.tiles_m * p.tiles_n;
     if (tiles <= 0) return 0;
@@ -362,10 +375,10 @@ int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi, B_MODE>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.done(h->device);
     }
     GemmParams<Epi> q = p;
     q.tiles_m = (p.tiles_m + 1) / 2;
@@ -419,10 +432,10 @@ int launch_gemm256s(strotss_ctx* h, const GemmParams<Epi>& p, int skew, cudaStre
     constexpr int smem = STAGES * stage_bytes + Epi::SMEM_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     auto kern = gemm2s_kernel<STAGES, EPI_WARPS, Epi>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.done(h->device);
     }
     if (p.nseg != 1 || p.tri) { h->err = "internal: the skewed-couple kernel takes one segment on a rectangular tile grid"; return STROTSS_ERR_STATE; }
     GemmParams<Epi> q = p;
@@ -474,10 +487,10 @@ int launch_gemm256w(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     constexpr int smem = STAGES * stage_bytes + Epi::SMEM_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     auto kern = gemm2w_kernel<STAGES, EPI_WARPS, Epi, B_MODE>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.done(h->device);
     }
     GemmParams<Epi> q = p;
     q.tiles_m = (p.tiles_m + 1) / 2;
@@ -557,13 +570,13 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
     RET(ensure(h, "pred.sumhat", (size_t)D, &fx.sumhat));
     RET(ensure(h, "content.sumhat", (size_t)D, &fy.sumhat));
     static const bool prep_v1 = (getenv("STROTSS_PREP_V1") != nullptr);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(prep_pair_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPrGroup * 2560 * (int)sizeof(float)));
         CK(cudaFuncSetAttribute(prep_pair_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaFuncSetAttribute(prep_pair_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPrGroup * 2560 * (int)sizeof(float)));
         CK(cudaFuncSetAttribute(prep_pair_rows2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
+        configured.done(h->device);
     }
     float* part;
     if (prep_v1) {
@@ -1044,12 +1057,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                 if (g > sp.tiles_n) g = sp.tiles_n;
                 sp.group_n = static_cast<int>(g);
             }
-            static bool configured = false;
-            if (!configured) {
+            static PerDeviceOnce configured;
+            if (configured.needed(h->device)) {
                 CK(cudaFuncSetAttribute(ss1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1SmemBytes));
                 CK(cudaFuncSetAttribute(ss1_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1PairSmemBytes));
                 CK(cudaFuncSetAttribute(ss1_pair_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1MergedSmemBytes));
-                configured = true;
+                configured.done(h->device);
             }
             if (pair_enabled()) {
                 sp.tiles_m = (p.tiles_m + 1) / 2;              // 256-row pair tiles
@@ -1712,9 +1725,7 @@ int strotss_eval_host_submit(strotss_handle h, const float* pred_host, const flo
 }
 
 static int copy_out(strotss_handle h, const float* sc, const int (&hidx)[4], int n, float* loss, cudaStream_t st) {
-    int* idx; RET(ensure(h, "fn.idx", (size_t)4, &idx));
-    CK(cudaMemcpyAsync(idx, hidx, sizeof(hidx), cudaMemcpyHostToDevice, st));
-    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, idx, n, loss);
+    copy_scalars_kernel<<<1, 32, 0, st>>>(sc, make_int4(hidx[0], hidx[1], hidx[2], hidx[3]), n, loss);
     CKL();
     return 0;
 }

@@ -58,10 +58,12 @@ def _call_sample(xs, indices, bilinear, out=None, grads=None, grad_out=None):
 class _SampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, indices, bilinear, *xs):
+        # which maps need a gradient is a property of the INPUTS: inside forward() autograd is off, so the contiguous copy
+        # of a permuted (e.g. NCHW -> NHWC) map would report requires_grad = False and silently drop its gradient
+        ctx.needs = list(ctx.needs_input_grad[2:])
         xs = [_check_features("feature map", x).contiguous() for x in xs]
         ctx.bilinear = bilinear
         ctx.shapes = [x.shape for x in xs]
-        ctx.needs = [x.requires_grad for x in xs]
         ctx.save_for_backward(indices)
         return _call_sample([x.detach() for x in xs], indices, bilinear)
 

@@ -1,6 +1,8 @@
 """Mirror of the one hot-path function of nn/strotss_utils.py."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from .runtime import shared_handle
@@ -138,14 +140,32 @@ class RMSprop:
 
     def __init__(self, rho: float = 0.9, epsilon: float = 1e-7, learning_rate: float = 1e-3):
         self.rho, self.epsilon, self.lr = float(rho), float(epsilon), float(learning_rate)
+        # id(variable) -> (weak reference to the variable, rms slot).  The reference reuses ONE optimizer across all scales
+        # with fresh variables per scale (run_strotss.py:63,89): a freed variable's id can be handed to a new, differently
+        # shaped one, so a slot is only reused while its weak reference still points at the very same tensor.
         self._slots = {}
+
+    def _slot(self, v: torch.Tensor) -> torch.Tensor:
+        entry = self._slots.get(id(v))
+        if entry is not None:
+            ref, slot = entry
+            if ref() is v and slot.shape == v.shape and slot.device == v.device:
+                return slot
+        for key in [k for k, (ref, _) in self._slots.items() if ref() is None]:
+            del self._slots[key]                      # variables of earlier scales that were collected
+        slot = torch.zeros_like(v)
+        self._slots[id(v)] = (weakref.ref(v), slot)
+        return slot
+
+    def slots(self):
+        """The live rms slots (e.g. to zero them when a captured graph is reused for a new image)."""
+        return [slot for ref, slot in self._slots.values() if ref() is not None]
 
     def build(self, var_list):
         """Create the rms slots now (Keras creates them at the first apply_gradients).  Call this before capturing
         apply_gradients into a CUDA graph: a slot created inside the capture would be re-zeroed by every replay."""
         for v in var_list:
-            if id(v) not in self._slots:
-                self._slots[id(v)] = torch.zeros_like(v)
+            self._slot(v)
 
     def apply_gradients(self, grads_and_vars):
         pairs = [(g, v) for g, v in grads_and_vars if g is not None]
@@ -157,10 +177,7 @@ class RMSprop:
             _check_features("variable", v); _check_features("gradient", g)
             if not v.is_contiguous() or g.shape != v.shape:
                 raise ValueError("variables must be contiguous and gradients shaped like them")
-            key = id(v)
-            if key not in self._slots:
-                self._slots[key] = torch.zeros_like(v)
-            slots.append(self._slots[key])
+            slots.append(self._slot(v))
         gs = [g.contiguous() for g, _ in pairs]
         dev = pairs[0][1].device
         vp = (_C.c_void_p * n)(*[v.data_ptr() for _, v in pairs])

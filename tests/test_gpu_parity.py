@@ -375,6 +375,28 @@ def test_evaluation_is_cuda_graph_capturable(S, cuda_device):
     assert abs(sc[0].item() - ref) / ref <= LOSS_RTOL
 
 
+def test_per_function_entry_points_are_cuda_graph_capturable(S, cuda_device):
+    """strotss_relaxed_emd / strotss_moment_matching / strotss_self_similarity stage nothing through the host (the scalar
+    slots they copy out travel as kernel arguments), so a replayed capture gives the answers of a direct call -- also after
+    the capturing call's stack frame is long gone and on new data."""
+    st, co, pr = O.synth_problem(300, 260, 2179, eps=0.2, seed=93)
+    h = S.Handle(cuda_device)
+    x, y, c = _t(st, cuda_device), _t(pr, cuda_device), _t(co, cuda_device)
+    for fn in (lambda: h.relaxed_emd(x, y, "cosine", True)[:2], lambda: h.relaxed_emd(x[:, :3].contiguous(), y[:, :3].contiguous(), "both", True)[:2],
+               lambda: h.moment_matching(x, y, True), lambda: h.self_similarity(y, c, True)):
+        want, gwant = fn()                                                 # warm-up: workspace growth
+        want, gwant = want.clone(), gwant.clone()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out, grad = fn()
+        _ = [np.zeros(64) for _ in range(8)]                                # churn the host stack / heap between capture and replay
+        out.zero_(); grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+        assert torch.allclose(grad, gwant, rtol=1e-5, atol=1e-10)
+
+
 def test_wide_features_take_the_general_preparation_path(S, cuda_device):
     """D > 2560 exceeds the fused row pass (10 columns per thread) and must fall back, not fail."""
     st, co, pr = O.synth_problem(200, 180, 2700, eps=0.1, seed=51)
@@ -553,6 +575,25 @@ def test_sampler_backward_matches_autograd(S, cuda_device):
         assert float((a.grad.double().cpu() - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max())
 
 
+def test_sampler_gradient_reaches_non_contiguous_maps(S, cuda_device):
+    """A permuted (NCHW -> NHWC view) feature map is copied inside the sampler; its gradient must still arrive."""
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    nchw = [torch.rand(1, c, hh, ww, generator=g, device=cuda_device, requires_grad=True) for (hh, ww, c) in [(24, 32, 3), (12, 16, 8)]]
+    views = [t.permute(0, 2, 3, 1) for t in nchw]
+    assert not views[1].is_contiguous()
+    samp = S.Sampling(64, torch.Generator().manual_seed(0))
+    idx = samp._make_indices(views[0], True)
+    out = samp._sample(views, idx, True)
+    wgt = torch.rand(out.shape, generator=g, device=cuda_device)
+    (out * wgt).sum().backward()
+    ref_in = [t.detach().clone().requires_grad_(True) for t in nchw]
+    ref = samp._sample([t.permute(0, 2, 3, 1).contiguous() for t in ref_in], idx, True)
+    (ref * wgt).sum().backward()
+    for a, b in zip(nchw, ref_in):
+        assert a.grad is not None and float(a.grad.abs().sum()) > 0
+        assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7)
+
+
 def test_sampler_feeds_the_loss_path(S, cuda_device):
     """train_step shape of the path (run_strotss.py:134-141): sample content/pred maps at the same points,
     evaluate the fused loss, and carry the gradient back to the prediction's feature maps."""
@@ -651,15 +692,18 @@ def test_full_size_properties(S, cuda_device):
     assert abs(sc4[_lib.S_LOSS_C].item()) <= 1e-6
 
 
-def test_full_size_against_the_fp64_restatement(S, cuda_device):
+@pytest.mark.parametrize("eps", [1.0, 0.1, 0.01])
+def test_full_size_against_the_fp64_restatement(S, cuda_device, eps):
     """N = M = 16384, D = 2179 (the bench workload, BASELINE.json configs[3]) against the fp64 restatement of the
     reference op sequence (oracle/torch_port.py: materialised matrices + autograd), evaluated on the same device in
-    float64 -- the one place where the full size can be checked value by value rather than through invariants."""
+    float64 -- the one place where the full size can be checked value by value rather than through invariants.
+    eps = 1 is the bench's decorrelated setting; 0.1 and 0.01 are the near-content regime the optimiser lives in and
+    the precision stress of the bf16 operands."""
     import bench
     from oracle import torch_port as T
     from strotss_tensorflow_b200 import _lib
     N = M = 16384
-    style, content, pred = bench.synth_torch(N, M, 2179, 1.0, 0, cuda_device)
+    style, content, pred = bench.synth_torch(N, M, 2179, eps, 0, cuda_device)
     h = S.Handle(cuda_device)
     h.set_style_target(style)
     sc, grad, _, _ = h.eval(pred, content, 16.0, True)

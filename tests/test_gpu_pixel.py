@@ -131,6 +131,28 @@ def test_rmsprop_updates_all_variables_in_one_launch(S, cuda_device):
         assert np.abs(t.double().cpu().numpy() - r).max() <= 1e-5 * max(1.0, np.abs(r).max())
 
 
+def test_rmsprop_one_optimizer_over_two_scales(S, cuda_device):
+    """The reference keeps ONE optimizer for all scales and creates fresh variables per scale (run_strotss.py:63,89): the
+    variables of the first scale are freed, their ids may be reused by larger ones, and every new variable must start from
+    a zero slot of its own shape (Keras semantics)."""
+    opt = S.RMSprop(rho=0.99, epsilon=1e-8, learning_rate=2e-3)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    for scale, shape in enumerate([(1, 8, 12, 3), (1, 16, 24, 3), (1, 32, 48, 3)]):
+        import gc
+        variables = [torch.rand(shape, generator=g, device=cuda_device) for _ in range(3)]
+        start = [v.clone() for v in variables]
+        grads = [torch.rand(shape, generator=g, device=cuda_device) - 0.5 for _ in range(3)]
+        opt.apply_gradients(zip(grads, variables))
+        torch.cuda.synchronize()
+        for v, v0, gr in zip(variables, start, grads):
+            rms = (1 - 0.99) * gr * gr                                   # zero slot at the first step of every scale
+            want = v0 - 2e-3 * gr / (rms.sqrt() + 1e-8)
+            assert torch.allclose(v, want, rtol=1e-5, atol=1e-7), f"scale {scale}: stale optimizer slot"
+        assert len(opt.slots()) == 3
+        del variables, start, grads
+        gc.collect()
+
+
 def test_pixel_side_argument_errors(S, cuda_device):
     with pytest.raises(ValueError):
         S.make_laplacian(torch.zeros(2, 4, 4, 3, device=cuda_device))           # batch must be 1
