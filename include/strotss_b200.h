@@ -60,6 +60,13 @@ const char* strotss_last_error(strotss_handle h);
 const char* strotss_version(void);
 /* bytes of device workspace currently held by the handle */
 size_t strotss_workspace_bytes(strotss_handle h);
+/* Output buffers for bindings whose tensors are immutable (TensorFlow: INTEGRATION.md): device memory on the handle's GPU,
+ * owned by the caller until strotss_device_free.  The tf.custom_gradient adapter wraps such a buffer in a DLPack capsule
+ * (tf.experimental.dlpack.from_dlpack) instead of writing into an EagerTensor.  No reference counterpart (TensorFlow's
+ * allocator does this inside every op, e.g. for the result of tf.matmul at nn/losses.py:15). */
+int strotss_device_alloc(strotss_handle h, size_t bytes, void** out);
+int strotss_device_free(strotss_handle h, void* ptr);
+
 /* kernels launched by this handle since creation (the bench's gpu_launches counter) */
 long long strotss_launch_count(strotss_handle h);
 
@@ -205,7 +212,10 @@ int strotss_rmsprop_step(strotss_handle h, int nvars, float* const* vars, float*
 int strotss_debug_gemm(strotss_handle h, const float* A, int m, const float* B, int n, int k, float alpha,
                        float* C, int tile_n, void* stream);
 
-/* Test hook for the MN-major (transposed-A) operand path: At is k x m; C (+)= alpha * At^T . B^T. */
+/* Test hook for the MN-major (transposed-A) operand path: At is k x m; C (+)= alpha * At^T . B^T.
+ * `accumulate` is a bit set: 1 = add to C; 2 = run the CTA-pair kernel with the MN-major A operand (how stage 2 of the
+ * self-similarity reads the row-major x^); 4 = CTA-pair kernel, Gram matrix C = alpha * At^T At with BOTH operands
+ * MN-major from the one matrix (the covariance; needs n == m, B is not read). */
 int strotss_debug_gemm_ta(strotss_handle h, const float* At, int m, const float* B, int n, int k, float alpha,
                           float* C, int accumulate, void* stream);
 

@@ -25,6 +25,8 @@ SIGNATURES = {
     "strotss_version": (C.c_char_p, []),
     "strotss_workspace_bytes": (C.c_size_t, [_vp]),
     "strotss_launch_count": (_ll, [_vp]),
+    "strotss_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "strotss_device_free": (_i, [_vp, _vp]),
     "strotss_profile_enable": (_i, [_vp, _i]),
     "strotss_profile_num_phases": (_i, []),
     "strotss_profile_phase_name": (C.c_char_p, [_i]),

@@ -87,9 +87,9 @@ __global__ void copy_scalars_kernel(const float* __restrict__ src, int4 idx, int
 
 // Phases timed with CUDA events on the launching stream when profiling is enabled.
 enum Phase { PH_PREP = 0, PH_REMD_GEMM, PH_REMD_MISC, PH_PALETTE, PH_COV_FWD, PH_COV_BWD, PH_MOM_MISC, PH_SS_VEC, PH_SS1, PH_SS2,
-             PH_SS_MISC, PH_FINALIZE, PH_COUNT };
+             PH_SS_MISC, PH_FINALIZE, PH_EXCHANGE, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"prep", "remd_gemm", "remd_misc", "palette", "cov_fwd_gemm", "cov_bwd_gemm", "moment_misc",
-                                            "ss_vectors", "ss_stage1_gemm", "ss_stage2_gemm", "ss_misc", "finalize"};
+                                            "ss_vectors", "ss_stage1_gemm", "ss_stage2_gemm", "ss_misc", "finalize", "exchange"};
 struct PhaseRec { int id; cudaEvent_t a, b; };
 
 // Prepared operands of one (n x D) fp32 feature matrix.
@@ -97,6 +97,7 @@ struct Feat {
     const float* x = nullptr; long long ld = 0; int n = 0; int np = 0;
     float* inv = nullptr; float* mean = nullptr; float* sumhat = nullptr;
     bf16* xh = nullptr; bf16* cen = nullptr; bf16* dlt = nullptr; bf16* xhT = nullptr; bf16* cenT = nullptr;
+    float* u = nullptr; float* w = nullptr; float* sclamp = nullptr;      // self-similarity vectors, if the row pass made them
     float* rec = nullptr;       // palette records for the backward pass
     float* srec = nullptr;      // palette records for the candidate search
 };
@@ -364,17 +365,17 @@ bool pair_enabled() {
 int bbox256() { return pair_enabled() ? 128 : 256; }
 
 // p.tiles_m counts 128-row blocks (as for the single-CTA kernel); converted to 256-row pair tiles here.
-template <int NACC, int EPI_WARPS = 4, int B_MODE = 0, class Epi>
+template <int NACC, int EPI_WARPS = 4, int B_MODE = 0, int A_MODE = 0, class Epi>
 int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     if (!pair_enabled()) {
-        if constexpr (B_MODE != 0) { h->err = "internal: MN-major B needs the CTA-pair kernels"; return STROTSS_ERR_STATE; }
+        if constexpr (B_MODE != 0 || A_MODE != 0) { h->err = "internal: MN-major operands need the CTA-pair kernels"; return STROTSS_ERR_STATE; }
         else return launch_gemm<256, NACC, 4, EPI_WARPS>(h, p, st);
     }
     using Cfg = PairCfg<NACC>;
     constexpr int STAGES = 6;
     constexpr int smem = STAGES * Cfg::STAGE_BYTES + Epi::SMEM_BYTES + (2 * STAGES + 2 * Cfg::ACC_STAGES) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi, B_MODE>;
+    auto kern = gemm2_kernel<NACC, STAGES, EPI_WARPS, Epi, B_MODE, A_MODE>;
     static PerDeviceOnce configured;
     if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -480,13 +481,13 @@ bool wide_enabled() {
     return on;
 }
 
-template <int B_MODE = 0, class Epi>
+template <int B_MODE = 0, int A_MODE = 0, class Epi>
 int launch_gemm256w(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     constexpr int STAGES = 4, EPI_WARPS = 8;
     constexpr int stage_bytes = 3 * 128 * BK * 2;
     constexpr int smem = STAGES * stage_bytes + Epi::SMEM_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
-    auto kern = gemm2w_kernel<STAGES, EPI_WARPS, Epi, B_MODE>;
+    auto kern = gemm2w_kernel<STAGES, EPI_WARPS, Epi, B_MODE, A_MODE>;
     static PerDeviceOnce configured;
     if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -511,6 +512,9 @@ int launch_gemm256w(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     CKL();
     return 0;
 }
+
+// Rows [r0, r1) of the prediction owned by this rank (everything for a single GPU).
+struct Shard { int r0, r1; int n() const { return r1 - r0; } };
 
 // ---- operand preparation --------------------------------------------------------------
 struct PrepWant { bool mean, sumhat, xh, cen, dlt, xhT, cenT, rec; };
@@ -618,6 +622,62 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
     return 0;
 }
 
+// Streaming two-pass preparation (rows_stats3_kernel / rows_emit3_kernel): needs contiguous, 16-byte aligned rows and the
+// CTA-pair GEMM kernels (which read the row-major x^ / cen through MN-major descriptors where a transposed operand used to be).
+bool prep3_usable(const float* x, long long ldx, const float* y, long long ldy, int D, int Dp) {
+    static const bool off = (getenv("STROTSS_PREP_V2") != nullptr) || (getenv("STROTSS_PREP_V1") != nullptr);
+    return !off && pair_enabled() && ldx == D && ldy == D && Dp <= kRpMaxCols * kRpThreads &&
+           (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+}
+
+// cen_rows: rows whose centred operand (x - mean) is written -- all of them unless the covariance is row-sharded
+int prep_pred_content3(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, const float* y, int n, int D, int Dp, Shard cen_rows,
+                       cudaStream_t st) {
+    PhaseTimer _pt(h, PH_PREP, st);
+    fx.x = x; fx.ld = D; fx.n = n; fx.np = round_up(n, 64);
+    fy.x = y; fy.ld = D; fy.n = n; fy.np = fx.np;
+    RET(ensure(h, "pred.inv", (size_t)n, &fx.inv));
+    RET(ensure(h, "content.inv", (size_t)n, &fy.inv));
+    RET(ensure(h, "pred.xh", (size_t)n * Dp, &fx.xh));
+    RET(ensure(h, "content.xh", (size_t)n * Dp, &fy.xh));
+    RET(ensure(h, "pred.dlt", (size_t)n * Dp, &fx.dlt));
+    RET(ensure(h, "pred.cen", (size_t)n * Dp, &fx.cen));
+    RET(ensure(h, "pred.mean", (size_t)D, &fx.mean));
+    RET(ensure(h, "pred.sumhat", (size_t)D, &fx.sumhat));
+    RET(ensure(h, "content.sumhat", (size_t)D, &fy.sumhat));
+    RET(ensure(h, "ss.u", (size_t)n, &fx.u));
+    RET(ensure(h, "ss.w", (size_t)n, &fx.w));
+    RET(ensure(h, "ss.sclamp", (size_t)n, &fx.sclamp));
+    const int smem1 = 2 * rows_stage_floats(D) * (int)sizeof(float);
+    const int smem2 = smem1 + 3 * Dp * (int)sizeof(float);
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
+        CK(cudaFuncSetAttribute(rows_stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * rows_stage_floats(2560) * (int)sizeof(float)));
+        CK(cudaFuncSetAttribute(rows_emit3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (2 * rows_stage_floats(2560) + 3 * 2560) * (int)sizeof(float)));
+        configured.done(h->device);
+    }
+    int rpb = round_up((n + h->num_sms - 1) / h->num_sms, kRpGroup);
+    if (rpb < kRpGroup) rpb = kRpGroup;
+    const int nblk = (n + rpb - 1) / rpb;
+    float* part;
+    RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
+    RowsArgs a{};
+    a.x = x; a.y = y; a.n = n; a.D = D; a.Dp = Dp; a.rows_per_block = rpb;
+    a.inv_x = fx.inv; a.inv_y = fy.inv; a.part = part;
+    rows_stats3_kernel<<<nblk, kRpThreads, smem1, st>>>(a);
+    CKL();
+    colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+    CKL();
+    a.mean = fx.mean; a.sumhx = fx.sumhat; a.sumhy = fy.sumhat;
+    a.xh = fx.xh; a.yh = fy.xh; a.dlt = fx.dlt; a.cen = fx.cen; a.cen_r0 = cen_rows.r0; a.cen_r1 = cen_rows.r1;
+    a.u = fx.u; a.w = fx.w; a.sclamp = fx.sclamp;
+    rows_emit3_kernel<<<nblk, kRpThreads, smem2, st>>>(a);
+    CKL();
+    fx.xhT = nullptr; fx.cenT = nullptr;      // the GEMMs read x^ / cen through MN-major descriptors
+    return 0;
+}
+
 int prep_rec(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long ld, int n, int convert, cudaStream_t st) {
     PhaseTimer _pt(h, PH_PREP, st);
     RET(ensure(h, (std::string(tag) + ".rec").c_str(), (size_t)n * 8, &f.rec));
@@ -640,9 +700,6 @@ int cov_store(strotss_ctx* h, const Feat& f, int D, int Dp, float* V, cudaStream
 }
 
 // ---- the three loss terms, each leaving its gradient contribution in workspace buffers --
-// Rows [r0, r1) of the prediction owned by this rank (everything for a single GPU).
-struct Shard { int r0, r1; int n() const { return r1 - r0; } };
-
 // Slots of the float block that is summed over ranks once per evaluation.
 enum { PS_REMD_RY = 0, PS_PAL_RY = 1, PS_SS_LOSS = 2, PS_V = 16 };
 
@@ -860,8 +917,16 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     bf16* Sg; float* part;
     RET(ensure(h, "mom.Sg", (size_t)Dp * Dp, &Sg, /*zero_on_alloc=*/true));
     GemmParams<EpiCovFwd<256>> p{};
-    RET(make_tmap(h, &p.tmA[0], pred.cenT, D, pred.np, pred.np, BM));
-    RET(make_tmap(h, &p.tmB[0], pred.cenT, D, pred.np, pred.np, bbox256()));
+    // no transposed copy (streaming row pass): cen (N x Dp, features contiguous) is both operands, read MN-major; rows >= N are
+    // TMA zero fill
+    const bool mn = (pred.cenT == nullptr);
+    if (mn) {
+        RET(make_tmap_mn(h, &p.tmA[0], pred.cen, D, N, Dp));
+        p.tmB[0] = p.tmA[0];
+    } else {
+        RET(make_tmap(h, &p.tmA[0], pred.cenT, D, pred.np, pred.np, BM));
+        RET(make_tmap(h, &p.tmB[0], pred.cenT, D, pred.np, pred.np, bbox256()));
+    }
     p.nseg = 1; p.seg_kblocks[0] = pred.np / BK; p.seg_acc[0] = 0;
     p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
     // one partial per (128-row block, column tile, epilogue warp); a pair tile always has two row blocks
@@ -874,7 +939,11 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     // computed; off-diagonal tiles count twice in the loss and write both Sg blocks
     p.tri = pair_enabled() ? 1 : 0; p.epi.sym = p.tri; p.epi.diag_cols = 256;
     if (!part_zeroed) CK(cudaMemsetAsync(part, 0, sizeof(float) * npart, st));
-    { PhaseTimer _pt(h, PH_COV_FWD, st); RET((launch_gemm256<1>(h, p, st))); }
+    {
+        PhaseTimer _pt(h, PH_COV_FWD, st);
+        if (mn) RET((launch_gemm256<1, 4, 1, 1>(h, p, st)));
+        else RET((launch_gemm256<1>(h, p, st)));
+    }
     RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
     {
         PhaseTimer _pt(h, PH_MOM_MISC, st);
@@ -954,15 +1023,19 @@ int ss1_small(strotss_ctx* h, const Feat& x, const Feat& y, int N, int Dp, int r
 // (both to be summed over ranks), ss2 rows (local), coef (global indexing, this rank's rows valid).
 int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh, int D, int Dp, float* loss_partial,
                    float* v_partial, bool want_grad, SsOut& out, cudaStream_t st) {
-    float *u, *w, *sclamp, *loss_part, *r_part, *rowloss;
-    RET(ensure(h, "ss.u", (size_t)N, &u));
-    RET(ensure(h, "ss.w", (size_t)N, &w));
-    RET(ensure(h, "ss.sclamp", (size_t)N, &sclamp));
-    {
+    float *u = x.u, *w = x.w, *sclamp = x.sclamp, *loss_part, *r_part, *rowloss;
+    if (!u) {                             // (the streaming row pass already made them)
+        RET(ensure(h, "ss.u", (size_t)N, &u));
+        RET(ensure(h, "ss.w", (size_t)N, &w));
+        RET(ensure(h, "ss.sclamp", (size_t)N, &sclamp));
         PhaseTimer _pt(h, PH_SS_VEC, st);
         ss_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
         CKL();
     }
+    // stage 2 multiplies P with x^: either the transposed copy x^T (K-major A) or, when the row pass made none, x^ itself read
+    // through MN-major descriptors (CTA-pair kernels)
+    const bool amn = (x.xhT == nullptr);
+    if (amn && want_grad && !pair_enabled()) { h->err = "internal: stage 2 without x^T needs the CTA-pair kernels"; return STROTSS_ERR_STATE; }
     constexpr int kSsBN = 256, kSsEpiWarps = 8, kSsSplit = kSsEpiWarps / 4;
     static const int small_max = getenv("STROTSS_SS1_SMALL_MAX") ? atoi(getenv("STROTSS_SS1_SMALL_MAX")) : 2048;
     const bool small = sh.n() <= small_max && N <= small_max;           // single panel, few tiles
@@ -1007,6 +1080,32 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         out.ld = Dp;
     }
     cudaStream_t st2 = overlap ? h->aux : st;
+    // STROTSS_P_PERSIST=1 (experiment, see DESIGN.md "P panel"): pin the P panel in L2 with an access-policy window on the
+    // launching streams, so that what stage 1 writes is still cache-resident when stage 2 reads it; meaningful with panels
+    // that fit the persisting carve-out next to the streamed operands (STROTSS_PANEL=2048: 64 MB at N = 16384)
+    static const bool p_persist = getenv("STROTSS_P_PERSIST") && atoi(getenv("STROTSS_P_PERSIST")) != 0;
+    bool window_set = false;
+    if (p_persist && Pbuf[0]) {
+        static PerDeviceOnce limit_set;
+        int max_persist = 0, max_window = 0;
+        CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device));
+        CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
+        if (limit_set.needed(h->device)) {
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist)));
+            limit_set.done(h->device);
+        }
+        size_t bytes = static_cast<size_t>(panel) * np * sizeof(bf16);
+        if (bytes > static_cast<size_t>(max_window)) bytes = static_cast<size_t>(max_window);
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = Pbuf[0];
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = bytes <= static_cast<size_t>(max_persist) ? 1.f : static_cast<float>(max_persist) / static_cast<float>(bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        if (st2 != st) CK(cudaStreamSetAttribute(st2, cudaStreamAttributeAccessPolicyWindow, &attr));
+        window_set = true;
+    }
     int pidx = 0;
     for (int r0 = sh.r0; r0 < sh.r1; r0 += panel, ++pidx) {
         const int rows = (sh.r1 - r0 < panel) ? (sh.r1 - r0) : panel;
@@ -1103,7 +1202,8 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                 // instruction writes 32 consecutive floats of one ss2 row (coalesced), also for the accumulating 2b.
                 // stage 2a: ss2[panel rows][d] (+)= sum_{j >= c0} P[i][j] x^[j][d]
                 GemmParams<EpiStoreTr<256>> q{};
-                RET(make_tmap(h, &q.tmA[0], x.xhT + c0, D, np - c0, np, BM));
+                if (amn) RET(make_tmap_mn(h, &q.tmA[0], x.xh + static_cast<long long>(c0) * Dp, D, N - c0, Dp));
+                else RET(make_tmap(h, &q.tmA[0], x.xhT + c0, D, np - c0, np, BM));
                 RET(make_tmap(h, &q.tmB[0], P + c0, rows, np - c0, np, 128));
                 q.nseg = 1; q.seg_kblocks[0] = (np - c0) / BK; q.seg_acc[0] = 0;
                 q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (rows + 255) / 256;
@@ -1115,28 +1215,30 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     //   segment 1: sum over the panel rows above it of P[i][these columns]^T  (same panel read MN-major)
                     // Both segments accumulate into one TMEM tile and together span N - c0 columns for every tile.
                     q.kb_lo_mul[0] = 256 / BK;
-                    RET(make_tmap(h, &q.tmA[1], x.xhT + r0, D, rows, np, BM));
+                    if (amn) RET(make_tmap_mn(h, &q.tmA[1], x.xh + static_cast<long long>(r0) * Dp, D, rows, Dp));
+                    else RET(make_tmap(h, &q.tmA[1], x.xhT + r0, D, rows, np, BM));
                     RET(make_tmap_mn(h, &q.tmB[1], P + r0, rows, rows, np));
                     q.nseg = 2; q.seg_kblocks[1] = (rows + BK - 1) / BK; q.seg_acc[1] = 0;
                     q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
                     if (wide_enabled()) {
                         q.tiles_n = (rows + 511) / 512;
-                        RET((launch_gemm256w<2>(h, q, st2)));
+                        if (amn) RET((launch_gemm256w<2, 1>(h, q, st2))); else RET((launch_gemm256w<2>(h, q, st2)));
                     } else {
-                        RET((launch_gemm256<1, 8, 2>(h, q, st2)));
+                        if (amn) RET((launch_gemm256<1, 8, 2, 1>(h, q, st2))); else RET((launch_gemm256<1, 8, 2>(h, q, st2)));
                     }
                 } else if (wide_enabled()) {
                     q.tiles_n = (rows + 511) / 512;
-                    RET((launch_gemm256w<0>(h, q, st2)));
+                    if (amn) RET((launch_gemm256w<0, 1>(h, q, st2))); else RET((launch_gemm256w<0>(h, q, st2)));
                 } else {
-                    RET((launch_gemm256<1, 8>(h, q, st2)));
+                    if (amn) RET((launch_gemm256<1, 8, 0, 1>(h, q, st2))); else RET((launch_gemm256<1, 8>(h, q, st2)));
                 }
                 if (sym && r0 + panel < N) {
                     // stage 2b: ss2[j][d] += sum_{i in panel} P[i][j] x^[i][d] for the rows j right of the panel;
                     // B = P^T is read from the row-major panel through MN-major descriptors
                     const int m0 = r0 + panel, mext = N - m0;
                     GemmParams<EpiStoreTr<256>> t{};
-                    RET(make_tmap(h, &t.tmA[0], x.xhT + r0, D, rows, np, BM));
+                    if (amn) RET(make_tmap_mn(h, &t.tmA[0], x.xh + static_cast<long long>(r0) * Dp, D, rows, Dp));
+                    else RET(make_tmap(h, &t.tmA[0], x.xhT + r0, D, rows, np, BM));
                     RET(make_tmap_mn(h, &t.tmB[0], P + m0, mext, rows, np));
                     t.nseg = 1; t.seg_kblocks[0] = (rows + BK - 1) / BK; t.seg_acc[0] = 0;
                     t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
@@ -1144,9 +1246,9 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     t.epi.alpha = 1.f; t.epi.col_off = 0; t.epi.accumulate = (r0 > 0) ? 1 : 0;
                     if (wide_enabled()) {
                         t.tiles_n = (mext + 511) / 512;
-                        RET((launch_gemm256w<1>(h, t, st2)));
+                        if (amn) RET((launch_gemm256w<1, 1>(h, t, st2))); else RET((launch_gemm256w<1>(h, t, st2)));
                     } else {
-                        RET((launch_gemm256<1, 8, 1>(h, t, st2)));
+                        if (amn) RET((launch_gemm256<1, 8, 1, 1>(h, t, st2))); else RET((launch_gemm256<1, 8, 1>(h, t, st2)));
                     }
                 }
             } else {
@@ -1184,6 +1286,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         cudaEvent_t e; RET(seq_event(h, 2 * (npanels - 1) + 1, &e));
         CK(cudaStreamWaitEvent(st, e, 0));
     }
+    if (window_set) {                      // later kernels of these streams get no window; the persisting lines age out normally
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        if (st2 != st) CK(cudaStreamSetAttribute(st2, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
         ss_rows_kernel<<<(sh.n() + 31) / 32, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
@@ -1199,8 +1307,13 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             const int nblk = (sh.n() + rpb - 1) / rpb;
             float* vpart;
             RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
-            weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
-                                                         out.coef + sh.r0, vpart, rpb);
+            // v = sum_i coef_i x^_i: from the bf16 x^ rows (half the bytes of x; the rounding errors of 16384 rows average out)
+            static const bool v_fp32 = (getenv("STROTSS_V_FP32") != nullptr);
+            if (x.xh && !v_fp32)
+                weighted_colsum_bf16_kernel<<<nblk, 256, 0, st>>>(x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
+            else
+                weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
+                                                             out.coef + sh.r0, vpart, rpb);
             CKL();
             colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(vpart, nblk, D, 1.f, v_partial);
             CKL();
@@ -1226,6 +1339,7 @@ int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) 
 //   allreduce-sum over the float block (partial column sums, self-similarity loss, v vector)
 int exchange(strotss_ctx* h, unsigned long long* best, size_t nbest, float* partials, size_t npartials, cudaStream_t st) {
     if (h->world <= 1 || !h->nccl_comm) return 0;
+    PhaseTimer _pt(h, PH_EXCHANGE, st);      // includes the wait for the slowest rank to arrive
     NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
     NCK(nccl().AllReduce(partials, partials, npartials, kNcclFloat32, kNcclSum, h->nccl_comm, st));
     return 0;
@@ -1295,6 +1409,22 @@ size_t strotss_workspace_bytes(strotss_handle h) {
     size_t b = h->ws_bytes;
     for (auto* c : h->regions) b += c->ws_bytes;
     return b;
+}
+
+int strotss_device_alloc(strotss_handle h, size_t bytes, void** out) {
+    RET(check_handle(h));
+    if (!out || bytes == 0) { h->err = "device_alloc: bad argument"; return STROTSS_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(out, bytes));
+    return 0;
+}
+
+int strotss_device_free(strotss_handle h, void* ptr) {
+    RET(check_handle(h));
+    if (!ptr) return 0;
+    CK(cudaSetDevice(h->device));
+    CK(cudaFree(ptr));
+    return 0;
 }
 
 long long strotss_launch_count(strotss_handle h) {
@@ -1435,7 +1565,9 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaEventRecord(h->ev_join, s_pal));
     }
 
-    if (with_content && Dp <= 2560) {
+    if (with_content && prep3_usable(pred, ld_pred, content, ld_content, D, Dp)) {
+        RET(prep_pred_content3(h, fp, fc, pred, content, N, D, Dp, Shard{0, N}, st));
+    } else if (with_content && Dp <= 2560) {
         RET(prep_pred_content(h, fp, fc, pred, ld_pred, content, ld_content, N, D, Dp, want_grad, st));
     } else if (with_content) {
         // very wide features: the fused row pass keeps 10 columns per thread; use the general two-kernel path
@@ -2030,14 +2162,26 @@ int strotss_debug_gemm_ta(strotss_handle h, const float* At, int m, const float*
     RET(ensure(h, "dbg.a", (size_t)k * mp, &a16));
     RET(ensure(h, "dbg.b", (size_t)n * kp, &b16));
     cast_pad_kernel<<<(unsigned)(((long long)k * mp + 255) / 256), 256, 0, st>>>(At, k, m, a16, mp); CKL();
-    cast_pad_kernel<<<(unsigned)(((long long)n * kp + 255) / 256), 256, 0, st>>>(B, n, k, b16, kp); CKL();
+    if (!(accumulate & 4)) { cast_pad_kernel<<<(unsigned)(((long long)n * kp + 255) / 256), 256, 0, st>>>(B, n, k, b16, kp); CKL(); }
     GemmParams<EpiStoreT<256>> p{};
     RET(make_tmap_mn(h, &p.tmA[0], a16, m, k, mp));
     RET(make_tmap(h, &p.tmB[0], b16, n, k, kp, 256));
     p.nseg = 1; p.seg_kblocks[0] = kp / BK; p.seg_acc[0] = 0;
     p.tiles_m = (m + BM - 1) / BM; p.tiles_n = (n + 255) / 256;
     p.epi.C = C; p.epi.ldc = n; p.epi.rows = m; p.epi.cols = n; p.epi.alpha = alpha; p.epi.row_off = 0;
-    p.epi.accumulate = accumulate ? 1 : 0;
+    p.epi.accumulate = (accumulate & 1) ? 1 : 0;
+    if (accumulate & 6) {
+        // bit 1: the CTA-pair kernel with an MN-major A operand (stage 2 of the self-similarity reads x^ this way);
+        // bit 2: additionally B := A^T stored the same way (the covariance: C = At^T At, both operands MN-major; n must equal m)
+        if (!pair_enabled()) { h->err = "debug_gemm_ta: the MN-major pair variants need the CTA-pair kernels"; return STROTSS_ERR_STATE; }
+        if (accumulate & 4) {
+            if (n != m) { h->err = "debug_gemm_ta: the Gram variant needs n == m"; return STROTSS_ERR_ARG; }
+            p.tmB[0] = p.tmA[0];
+            return launch_gemm256<1, 4, 1, 1>(h, p, st);
+        }
+        RET(make_tmap(h, &p.tmB[0], b16, n, k, kp, 128));
+        return launch_gemm256<1, 4, 0, 1>(h, p, st);
+    }
     return launch_gemm<256, 1, 4, 4, true>(h, p, st);
 }
 

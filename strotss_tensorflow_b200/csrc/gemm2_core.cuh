@@ -36,7 +36,10 @@ struct PairCfg {
 // B_MODE 1: the B operand is read from a matrix stored K x N (N contiguous) through MN-major descriptors; its tensor
 // map has dims {N, K} and box {64, 64} (each CTA stages its 128 columns of B as two 64-wide chunks).
 // B_MODE 2: chosen per segment at run time (p.seg_bmn[s]); both layouts stage the same 16 KB per CTA and K block.
-template <int NACC, int STAGES, int EPI_WARPS, class Epi, int B_MODE = 0>
+// A_MODE 1: the A operand of EVERY segment is read from a matrix stored K x M (M contiguous) the same way (tensor map dims
+// {M, K}, box {64, 64}, each CTA stages its 128 rows of A as two 64-wide chunks): the row-major bf16 operands x^ / cen
+// then serve as the "transposed" operands of stage 2 and of the covariance without a transposed copy in HBM.
+template <int NACC, int STAGES, int EPI_WARPS, class Epi, int B_MODE = 0, int A_MODE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
 gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
@@ -93,7 +96,12 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         uint8_t* sB = sA + Cfg::A_BYTES;
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-                        tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
+                        if constexpr (A_MODE == 1) {
+                            tma_load_2d_2cta(sA, &p.tmA[s], lead_full, arow, kb * BK);
+                            tma_load_2d_2cta(sA + Cfg::A_BYTES / 2, &p.tmA[s], lead_full, arow + 64, kb * BK);
+                        } else {
+                            tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
+                        }
                         if (bmn) {
                             tma_load_2d_2cta(sB, &p.tmB[s], lead_full, brow, kb * BK);
                             tma_load_2d_2cta(sB + Cfg::B_BYTES / 2, &p.tmB[s], lead_full, brow + 64, kb * BK);
@@ -107,8 +115,9 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc_k = make_idesc_bf16(BM2, BN, false, false);
-            constexpr uint32_t idesc_mn = make_idesc_bf16(BM2, BN, false, true);
+            constexpr uint32_t idesc_k = make_idesc_bf16(BM2, BN, A_MODE == 1, false);
+            constexpr uint32_t idesc_mn = make_idesc_bf16(BM2, BN, A_MODE == 1, true);
+            constexpr uint32_t a_step = (A_MODE == 1) ? (16 * 128) >> 4 : 2;
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
@@ -130,14 +139,14 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t adesc = (A_MODE == 1) ? make_mnmajor_sw128_desc(a_addr, Cfg::A_BYTES / 2) : make_kmajor_sw128_desc(a_addr);
                         const uint64_t bdesc = bmn ? make_mnmajor_sw128_desc(a_addr + Cfg::A_BYTES, Cfg::B_BYTES / 2)
                                                    : make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
                         const int ksteps = (p.k_tail_steps && kb == p.seg_kblocks[s] - 1) ? p.k_tail_steps : BK / 16;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             if (k < ksteps)
-                                umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,
+                                umma_bf16_2cta(d_addr, adesc + a_step * k, bdesc + b_step * k, idesc,
                                                ((touched >> acc) & 1u) | (k > 0 ? 1u : 0u));
                         touched |= (1u << acc);
                         umma_commit_2cta(&empty[stage], 3);
@@ -192,7 +201,7 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
 // accumulator halves fill TMEM, so the epilogue of a tile is not hidden behind the next tile's MMAs -- worth it where K is long
 // (stage 2 of the self-similarity: 32..256 K blocks per tile).  Sub-tile `sub` covers B rows tn*512 + sub*256 ..; the optional
 // tile-dependent K ranges of GemmParams apply per 256-row sub-tile index 2*tn + sub (an MMA is skipped outside its range).
-template <int STAGES, int EPI_WARPS, class Epi, int B_MODE = 0>
+template <int STAGES, int EPI_WARPS, class Epi, int B_MODE = 0, int A_MODE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 32 * EPI_WARPS, 1)
 gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
     static_assert(EPI_WARPS == 8, "8 epilogue warps");
@@ -252,7 +261,12 @@ gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         uint8_t* sA = smem + stage * STAGE_BYTES;
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
-                        tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
+                        if constexpr (A_MODE == 1) {
+                            tma_load_2d_2cta(sA, &p.tmA[s], lead_full, arow, kb * BK);
+                            tma_load_2d_2cta(sA + A_BYTES / 2, &p.tmA[s], lead_full, arow + 64, kb * BK);
+                        } else {
+                            tma_load_2d_2cta(sA, &p.tmA[s], lead_full, kb * BK, arow);
+                        }
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
                             uint8_t* sB = sA + A_BYTES + sub * B_BYTES;
@@ -270,8 +284,9 @@ gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc_k = make_idesc_bf16(BM2, 256, false, false);
-            constexpr uint32_t idesc_mn = make_idesc_bf16(BM2, 256, false, true);
+            constexpr uint32_t idesc_k = make_idesc_bf16(BM2, 256, A_MODE == 1, false);
+            constexpr uint32_t idesc_mn = make_idesc_bf16(BM2, 256, A_MODE == 1, true);
+            constexpr uint32_t a_step = (A_MODE == 1) ? (16 * 128) >> 4 : 2;
             int stage = 0; uint32_t phase = 0;
             uint32_t aphase = 0;
             for (int t = pair; t < num_tiles; t += npairs) {
@@ -291,7 +306,7 @@ gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                        const uint64_t adesc = (A_MODE == 1) ? make_mnmajor_sw128_desc(a_addr, A_BYTES / 2) : make_kmajor_sw128_desc(a_addr);
                         const int ksteps = (p.k_tail_steps && kb == p.seg_kblocks[s] - 1) ? p.k_tail_steps : BK / 16;
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
@@ -303,7 +318,7 @@ gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
                                 if (k < ksteps)
-                                    umma_bf16_2cta(d_addr, adesc + 2 * k, bdesc + b_step * k, idesc,
+                                    umma_bf16_2cta(d_addr, adesc + a_step * k, bdesc + b_step * k, idesc,
                                                    ((touched >> sub) & 1u) | (k > 0 ? 1u : 0u));
                             touched |= (1u << sub);
                         }

@@ -80,6 +80,30 @@ __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __res
     }
 }
 
+// the same from the normalised bf16 rows: part[b][d] = sum_{r in block b} coef[r] * xh[r][d]   (two columns per thread)
+__global__ void __launch_bounds__(256) weighted_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ xh, long long ld, int n, int D,
+                                                                   const float* __restrict__ coef, float* __restrict__ part, int rpb) {
+    __shared__ float s_w[kRowsPerBlock];
+    const int r0 = blockIdx.x * rpb;
+    if (threadIdx.x < rpb) {
+        const int r = r0 + threadIdx.x;
+        s_w[threadIdx.x] = (r < n) ? coef[r] : 0.f;
+    }
+    __syncthreads();
+    const int rows = min(rpb, n - r0);
+    for (int d = 2 * threadIdx.x; d < D; d += 2 * blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < rows; ++rr) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xh + static_cast<long long>(r0 + rr) * ld + d);
+            a0 = fmaf(__low2float(v), s_w[rr], a0);
+            a1 = fmaf(__high2float(v), s_w[rr], a1);
+        }
+        part[static_cast<long long>(blockIdx.x) * D + d] = a0;
+        if (d + 1 < D) part[static_cast<long long>(blockIdx.x) * D + d + 1] = a1;
+    }
+}
+
 // out[d] = scale * sum_b part[b][d]   (fixed order: 8 interleaved block groups, then a fixed tree)
 // block = 32 columns x 8 block-groups
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ part, int nblocks, int D, float scale,
@@ -455,6 +479,202 @@ __global__ void __launch_bounds__(256, 3) prep_pair_rows2_kernel(const float* __
     for (int c = 0; c < kMaxCols; ++c) {
         const int d = threadIdx.x + c * 256;
         if (d < D) { pb[d] = ax[c]; pb[D + d] = ahx[c]; pb[2 * D + d] = ahy[c]; }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// Streaming row passes of the fused evaluation (prediction x and content y, both n x D fp32 with CONTIGUOUS, 16-byte
+// aligned rows).  Groups of kRpGroup = 4 rows -- 4 * D floats are contiguous and a multiple of 16 bytes for any D -- are
+// fetched by ONE elected thread with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) into a two-stage
+// shared-memory ring: the memory system always has a 2 x 35 KB request in flight per block and no thread spends issue
+// slots on loads.  The row pass needs the column sums of ALL rows before it can emit the centred operand and the
+// self-similarity vectors, so it is two passes over x and y -- the same number of reads as one row pass plus
+// ss_vectors_kernel, without the third read and the transposed operands of emit_operands2_kernel (the GEMMs read the
+// row-major operands through MN-major descriptors instead):
+//   pass 1 (rows_stats3_kernel):  inv_x, inv_y, column partials  part[b][0] = sum x, [1] = sum x^, [2] = sum y^
+//   pass 2 (rows_emit3_kernel):   x^, y^, delta = x^ - y^, cen = x - mean (bf16, row-major, zero K padding) and
+//                                 u, w, sclamp (exactly what ss_vectors_kernel computes, from the rows already in smem)
+// A ragged last group (n % 4 rows) is loaded by all threads with ordinary loads.
+// --------------------------------------------------------------------------------------
+constexpr int kRpGroup = 4;
+constexpr int kRpThreads = 256;
+constexpr int kRpMaxCols = 10;            // columns per thread in the column sums: Dp <= 2560
+
+struct RowsArgs {
+    const float* x; const float* y; int n, D, Dp;
+    int rows_per_block;                   // multiple of kRpGroup
+    float* inv_x; float* inv_y;
+    float* part;                          // pass 1: [blocks][3][D]
+    const float* mean; const float* sumhx; const float* sumhy;          // pass 2
+    __nv_bfloat16* xh; __nv_bfloat16* yh; __nv_bfloat16* dlt; __nv_bfloat16* cen;
+    int cen_r0, cen_r1;                   // rows whose centred operand is written (all rows, or this rank's shard)
+    float* u; float* w; float* sclamp;
+};
+
+__host__ __device__ constexpr int rows_stage_floats(int D) { return 2 * kRpGroup * D; }
+
+// Stage the row group starting at row r into (sx | sy): bulk copies for a full group (elected thread), ordinary loads
+// by every thread for the ragged last group (zero fill for the missing rows).  Returns true if the group went by bulk copy.
+__device__ __forceinline__ bool rows_group_is_bulk(const RowsArgs& a, int r) { return r + kRpGroup <= a.n; }
+
+__device__ __forceinline__ void rows_issue_bulk(const RowsArgs& a, int r, float* stage, uint64_t* bar) {
+    const uint32_t bytes = static_cast<uint32_t>(kRpGroup) * a.D * 4u;
+    fence_proxy_async();                  // the stage was last read through the generic proxy
+    mbar_arrive_expect_tx(bar, 2 * bytes);
+    bulk_load_1d(stage, a.x + static_cast<long long>(r) * a.D, bytes, bar);
+    bulk_load_1d(stage + kRpGroup * a.D, a.y + static_cast<long long>(r) * a.D, bytes, bar);
+}
+
+__device__ __forceinline__ void rows_load_ragged(const RowsArgs& a, int r, float* stage) {
+    const int live = (a.n - r) * a.D;     // floats that exist (fewer than a full group)
+    const float* xs = a.x + static_cast<long long>(r) * a.D;
+    const float* ys = a.y + static_cast<long long>(r) * a.D;
+    for (int e = threadIdx.x; e < kRpGroup * a.D; e += kRpThreads) {
+        stage[e] = e < live ? xs[e] : 0.f;
+        stage[kRpGroup * a.D + e] = e < live ? ys[e] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(kRpThreads, 1) rows_stats3_kernel(const RowsArgs a) {
+    extern __shared__ __align__(16) float rp_smem[];      // [2 stages][x | y][kRpGroup][D]
+    __shared__ uint64_t full[2];
+    __shared__ float s_inv[2][kRpGroup];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.D;
+    const int row_base = blockIdx.x * a.rows_per_block;
+    const int row_end = min(a.n, row_base + a.rows_per_block);
+    const int stage_floats = rows_stage_floats(D);
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_barrier_init(); }
+    __syncthreads();
+    float ax[kRpMaxCols], ahx[kRpMaxCols], ahy[kRpMaxCols];
+#pragma unroll
+    for (int c = 0; c < kRpMaxCols; ++c) { ax[c] = 0.f; ahx[c] = 0.f; ahy[c] = 0.f; }
+    if (threadIdx.x == 0 && row_base < row_end && rows_group_is_bulk(a, row_base)) rows_issue_bulk(a, row_base, rp_smem, &full[0]);
+    int g = 0;
+    for (int r = row_base; r < row_end; r += kRpGroup, ++g) {
+        const int s = g & 1;
+        float* stage = rp_smem + s * stage_floats;
+        const int rn = r + kRpGroup;
+        if (threadIdx.x == 0 && rn < row_end && rows_group_is_bulk(a, rn)) rows_issue_bulk(a, rn, rp_smem + (s ^ 1) * stage_floats, &full[s ^ 1]);
+        if (rows_group_is_bulk(a, r)) mbar_wait(&full[s], (g >> 1) & 1);
+        else { rows_load_ragged(a, r, stage); __syncthreads(); }
+        const float* sx = stage;
+        const float* sy = stage + kRpGroup * D;
+        {   // warp w: squared norm of row (w & 3) of x (w < 4) or y
+            const float* src = (warp < kRpGroup ? sx : sy) + (warp & (kRpGroup - 1)) * D;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int d = lane;
+            for (; d + 96 < D; d += 128) {
+                const float v0 = src[d], v1 = src[d + 32], v2 = src[d + 64], v3 = src[d + 96];
+                s0 = fmaf(v0, v0, s0); s1 = fmaf(v1, v1, s1); s2 = fmaf(v2, v2, s2); s3 = fmaf(v3, v3, s3);
+            }
+            for (; d < D; d += 32) { const float v = src[d]; s0 = fmaf(v, v, s0); }
+            const float ss = warp_sum((s0 + s1) + (s2 + s3));
+            if (lane == 0) {
+                const int row = r + (warp & (kRpGroup - 1));
+                const float iv = rsqrtf(fmaxf(ss, kL2NEps));
+                s_inv[warp / kRpGroup][warp & (kRpGroup - 1)] = iv;
+                if (row < a.n) { if (warp < kRpGroup) a.inv_x[row] = iv; else a.inv_y[row] = iv; }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < kRpMaxCols; ++c) {
+            const int d = threadIdx.x + c * kRpThreads;
+            if (d < D) {
+#pragma unroll
+                for (int rr = 0; rr < kRpGroup; ++rr) {
+                    const float xv = sx[rr * D + d], yv = sy[rr * D + d];
+                    ax[c] += xv;
+                    ahx[c] = fmaf(xv, s_inv[0][rr], ahx[c]);
+                    ahy[c] = fmaf(yv, s_inv[1][rr], ahy[c]);
+                }
+            }
+        }
+        __syncthreads();                  // stage s (and s_inv) may be overwritten from here on
+    }
+    float* pb = a.part + static_cast<long long>(blockIdx.x) * 3 * D;
+#pragma unroll
+    for (int c = 0; c < kRpMaxCols; ++c) {
+        const int d = threadIdx.x + c * kRpThreads;
+        if (d < D) { pb[d] = ax[c]; pb[D + d] = ahx[c]; pb[2 * D + d] = ahy[c]; }
+    }
+}
+
+__global__ void __launch_bounds__(kRpThreads, 1) rows_emit3_kernel(const RowsArgs a) {
+    extern __shared__ __align__(16) float rp_smem[];      // [2 stages][x | y][kRpGroup][D] | mean[Dp] | sumhx[Dp] | sumhy[Dp]
+    __shared__ uint64_t full[2];
+    __shared__ float s_dot[2][kRpGroup][2][2];           // [stage][row][half][x | y]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.D, Dp = a.Dp;
+    const int row_base = blockIdx.x * a.rows_per_block;
+    const int row_end = min(a.n, row_base + a.rows_per_block);
+    const int stage_floats = rows_stage_floats(D);
+    float* s_mean = rp_smem + 2 * stage_floats;
+    float* s_shx = s_mean + Dp;
+    float* s_shy = s_shx + Dp;
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0 && row_base < row_end && rows_group_is_bulk(a, row_base)) rows_issue_bulk(a, row_base, rp_smem, &full[0]);
+    for (int d = threadIdx.x; d < Dp; d += kRpThreads) {
+        const bool ok = d < D;
+        s_mean[d] = (ok && a.mean) ? a.mean[d] : 0.f;
+        s_shx[d] = ok ? a.sumhx[d] : 0.f;
+        s_shy[d] = ok ? a.sumhy[d] : 0.f;
+    }
+    __syncthreads();
+    const int rr = warp >> 1, half = warp & 1;            // two warps per row, 64-column chunks dealt alternately
+    const float fN = static_cast<float>(a.n);
+    int g = 0;
+    for (int r = row_base; r < row_end; r += kRpGroup, ++g) {
+        const int s = g & 1;
+        float* stage = rp_smem + s * stage_floats;
+        const int rn = r + kRpGroup;
+        if (threadIdx.x == 0 && rn < row_end && rows_group_is_bulk(a, rn)) rows_issue_bulk(a, rn, rp_smem + (s ^ 1) * stage_floats, &full[s ^ 1]);
+        const int row = r + rr;
+        const bool live = row < a.n;
+        const float ix = live ? a.inv_x[row] : 0.f, iy = live ? a.inv_y[row] : 0.f;
+        if (rows_group_is_bulk(a, r)) mbar_wait(&full[s], (g >> 1) & 1);
+        else { rows_load_ragged(a, r, stage); __syncthreads(); }
+        const float* sx = stage + rr * D;
+        const float* sy = stage + (kRpGroup + rr) * D;
+        const bool wcen = a.cen && row >= a.cen_r0 && row < a.cen_r1;
+        const long long off = static_cast<long long>(row) * Dp;
+        float dx0 = 0.f, dx1 = 0.f, dy0 = 0.f, dy1 = 0.f;
+        if (live) {
+#pragma unroll 2
+            for (int d = half * 64 + 2 * lane; d < Dp; d += 128) {
+                const bool ok0 = d < D, ok1 = d + 1 < D;
+                const float x0 = ok0 ? sx[d] : 0.f, x1 = ok1 ? sx[d + 1] : 0.f;
+                const float y0 = ok0 ? sy[d] : 0.f, y1 = ok1 ? sy[d + 1] : 0.f;
+                const float hx0 = x0 * ix, hx1 = x1 * ix, hy0 = y0 * iy, hy1 = y1 * iy;
+                *reinterpret_cast<uint32_t*>(a.xh + off + d) = pack_bf16x2(hx0, hx1);
+                *reinterpret_cast<uint32_t*>(a.yh + off + d) = pack_bf16x2(hy0, hy1);
+                *reinterpret_cast<uint32_t*>(a.dlt + off + d) = pack_bf16x2(hx0 - hy0, hx1 - hy1);
+                if (wcen)
+                    *reinterpret_cast<uint32_t*>(a.cen + off + d) = pack_bf16x2(ok0 ? x0 - s_mean[d] : 0.f, ok1 ? x1 - s_mean[d + 1] : 0.f);
+                dx0 = fmaf(x0, s_shx[d], dx0); dx1 = fmaf(x1, s_shx[d + 1 < Dp ? d + 1 : d], dx1);
+                dy0 = fmaf(y0, s_shy[d], dy0); dy1 = fmaf(y1, s_shy[d + 1 < Dp ? d + 1 : d], dy1);
+            }
+        }
+        const float dx = warp_sum(dx0 + dx1), dy = warp_sum(dy0 + dy1);
+        if (lane == 0) { s_dot[s][rr][half][0] = dx; s_dot[s][rr][half][1] = dy; }
+        __syncthreads();                  // stage s may be overwritten; the dot-product halves are visible
+        if (threadIdx.x < kRpGroup) {
+            const int j = r + threadIdx.x;
+            if (j < a.n) {
+                // s_j = N - x^_j . sum_i x^_i,  t_j likewise (column sums of Xd, Yd); see ss_vectors_kernel
+                const float ddx = (s_dot[s][threadIdx.x][0][0] + s_dot[s][threadIdx.x][1][0]) * a.inv_x[j];
+                const float ddy = (s_dot[s][threadIdx.x][0][1] + s_dot[s][threadIdx.x][1][1]) * a.inv_y[j];
+                const float sv = fN - ddx, tv = fN - ddy;
+                const float sc = fmaxf(sv, kColsumClamp), tcl = fmaxf(tv, kColsumClamp);
+                const bool plain = (sv >= kColsumClamp) && (tv >= kColsumClamp);
+                const float tms = plain ? (ddx - ddy) : (tcl - sc);
+                a.u[j] = 1.f / sc;
+                a.w[j] = tms / (sc * tcl);
+                a.sclamp[j] = (sv >= kColsumClamp) ? 1.f : 0.f;
+            }
+        }
     }
 }
 

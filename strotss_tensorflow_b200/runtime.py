@@ -272,8 +272,10 @@ class Handle:
                  "strotss_debug_gemm")
         return Cm
 
-    def debug_gemm_ta(self, At, B, alpha=1.0, C=None):
-        """C (+)= alpha * At^T @ B^T with At given (k, m): exercises the MN-major A descriptor path."""
+    def debug_gemm_ta(self, At, B, alpha=1.0, C=None, variant=0):
+        """C (+)= alpha * At^T @ B^T with At given (k, m): exercises the MN-major A descriptor path.  variant 0: single-CTA
+        kernel; 1: CTA-pair kernel, B K-major; 2: CTA-pair kernel computing the Gram matrix At^T At (both operands MN-major;
+        B is ignored except for its row count, which must equal m)."""
         At = _check_features("At", At).contiguous()
         B = _check_features("B", B).contiguous()
         k, m = At.shape
@@ -281,7 +283,8 @@ class Handle:
         acc = C is not None
         if C is None:
             C = torch.empty(m, n, device=At.device, dtype=torch.float32)
-        self._ck(self.lib.strotss_debug_gemm_ta(self._h, _ptr(At), m, _ptr(B), n, k, float(alpha), _ptr(C), 1 if acc else 0,
+        flags = (1 if acc else 0) | (2 if variant == 1 else 0) | (4 if variant == 2 else 0)
+        self._ck(self.lib.strotss_debug_gemm_ta(self._h, _ptr(At), m, _ptr(B), n, k, float(alpha), _ptr(C), flags,
                                                 _stream(At.device)), "strotss_debug_gemm_ta")
         return C
 

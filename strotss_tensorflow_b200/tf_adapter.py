@@ -1,29 +1,37 @@
-"""tf.custom_gradient adapter for the reference's TensorFlow driver.  UNEXECUTED IN THIS ENVIRONMENT:
-TensorFlow is not installed in the build image or on the GPU boxes, so this
-file is the binding a maintainer of the reference would drop next to nn/losses.py; the adapter that
-is actually exercised by the tests is the torch.autograd.Function one (losses.py / modules.py), which
-calls the same C ABI with the same argument meaning.
+"""tf.custom_gradient adapter for the reference's TensorFlow driver (the binding a maintainer of the reference drops
+next to nn/losses.py).
+
+TensorFlow is not installed in the build image or on the GPU boxes, so this module has never run
+against real TensorFlow.  What does run, on the B200 (tests/test_gpu_tf_adapter.py): every line of this file against
+`tests/tf_standin.py`, a stand-in `tensorflow` module on CUDA tensors that provides exactly the API used here
+(tf.custom_gradient, tf.py_function, tf.experimental.dlpack.{to,from}_dlpack, tf.test.experimental.sync_devices,
+tf.GradientTape, ...) with TensorFlow's documented semantics -- the control flow, the DLPack pointer hand-over, the C-ABI
+calls and the gradients are therefore exercised; TensorFlow's own behaviour behind those API names is not.
 
 Usage inside run_strotss.py (replacing `from nn.losses import ...`):
 
     from strotss_tensorflow_b200.tf_adapter import relaxed_emd, moment_matching, self_similarity, StyleLoss, ContentLoss
 
-Mechanics: the forward is a tf.py_function (train_step is a @tf.function graph, run_strotss.py:104,131;
-N is dynamic in masked mode, nn/strotss_utils.py:113).  GPU EagerTensors are handed over zero-copy through
-DLPack; the raw device pointers go to the C ABI on TensorFlow's compute stream is not exposed, so the
-adapter synchronises the device before and after the call (one sync per evaluation; the reference
-already syncs three scalars per iteration for tqdm, run_strotss.py:150-152).
+Mechanics: the forward is a tf.py_function (train_step is a @tf.function graph, run_strotss.py:104,131; N is dynamic in
+masked mode, nn/strotss_utils.py:113).  Inputs are GPU EagerTensors handed over zero-copy through DLPack (read-only use).
+Outputs are NOT written into TensorFlow tensors (those are immutable): the library allocates them
+(strotss_device_alloc), the kernels write there, and the buffer enters TensorFlow through
+tf.experimental.dlpack.from_dlpack with a deleter that returns it (strotss_device_free).  TensorFlow does not expose its
+compute stream, so the adapter runs on the legacy default stream and synchronises the device before the call (the
+producers of the inputs have finished) and after it (the outputs are complete before TensorFlow reads them); the reference
+already synchronises three scalars per iteration for tqdm (run_strotss.py:150-152).
 """
 from __future__ import annotations
 
 import ctypes as C
+import re
 
 from . import _lib
 
-try:                                    # pragma: no cover - TensorFlow is absent in this image
+try:
     import tensorflow as tf
     _HAVE_TF = True
-except Exception:                        # ModuleNotFoundError here
+except Exception:                        # ModuleNotFoundError in this image
     tf = None
     _HAVE_TF = False
 
@@ -34,7 +42,16 @@ def _require_tf():
                            "Use the torch adapter (strotss_tensorflow_b200.losses) instead.")
 
 
-class _Handles:                          # pragma: no cover
+def _device_index(t) -> int:
+    """'/job:localhost/replica:0/task:0/device:GPU:1' -> 1 (the GPU the tensor lives on; --gpu_id, nn/utils.py:73-85)."""
+    m = re.search(r"GPU:(\d+)", str(getattr(t, "device", "")))
+    if not m:
+        raise RuntimeError(f"tensor is on {getattr(t, 'device', '?')!r}: the STROTSS loss path runs on a GPU only (no CPU fallback)")
+    return int(m.group(1))
+
+
+class _Handles:
+    """One library handle per GPU for the stateless functions."""
     lib = None
     by_device = {}
 
@@ -49,36 +66,114 @@ class _Handles:                          # pragma: no cover
             cls.by_device[device_index] = h
         return h
 
+    @classmethod
+    def close(cls):
+        for h in cls.by_device.values():
+            cls.lib.strotss_destroy(h)
+        cls.by_device = {}
 
-def _dev_ptr(t):                         # pragma: no cover
-    """EagerTensor on GPU -> (raw device pointer, keep-alive capsule) via DLPack."""
+
+# ---- DLPack -------------------------------------------------------------------------------------------------------------
+class _DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int), ("device_id", C.c_int)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", _DLDevice), ("ndim", C.c_int), ("dtype", _DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+class _DLManagedTensor(C.Structure):
+    pass
+
+
+_DELETER = C.CFUNCTYPE(None, C.POINTER(_DLManagedTensor))
+_DLManagedTensor._fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", C.c_void_p), ("deleter", _DELETER)]
+_KDL_CUDA, _KDL_FLOAT = 2, 2
+_live = {}                                # address of a DLManagedTensor -> everything that must outlive the capsule
+
+C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+C.pythonapi.PyCapsule_New.restype = C.py_object
+C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+
+
+def _dev_ptr(t):
+    """GPU EagerTensor -> (raw device pointer, keep-alive capsule) via DLPack; the tensor is only read."""
     cap = tf.experimental.dlpack.to_dlpack(t)
-    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
-    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
-    managed = C.pythonapi.PyCapsule_GetPointer(cap, b"dltensor")
-    data = C.cast(managed, C.POINTER(C.c_void_p))[0]         # DLTensor.data is the first field
-    return C.c_void_p(data), cap
+    managed = C.cast(C.pythonapi.PyCapsule_GetPointer(cap, b"dltensor"), C.POINTER(_DLManagedTensor))
+    dl = managed.contents.dl_tensor
+    return C.c_void_p((dl.data or 0) + dl.byte_offset), cap
 
 
-def _reshape_2d(x):                      # pragma: no cover  (nn/losses.py:31-36)
+@_DELETER
+def _free_output(managed_ptr):
+    rec = _live.pop(C.addressof(managed_ptr.contents), None)
+    if rec is not None:
+        lib, handle, data = rec[0], rec[1], rec[2]
+        lib.strotss_device_free(handle, data)
+
+
+class _Output:
+    """fp32 device buffer of `shape`, owned by the library until TensorFlow's DLPack deleter returns it."""
+
+    def __init__(self, lib, handle, device_index: int, shape):
+        self.lib, self.handle, self.shape = lib, handle, tuple(int(s) for s in shape)
+        n = 1
+        for s in self.shape:
+            n *= s
+        self.ptr = C.c_void_p()
+        _lib.check(lib, handle, lib.strotss_device_alloc(handle, max(n, 1) * 4, C.byref(self.ptr)), "strotss_device_alloc")
+        self.device_index = device_index
+
+    def to_tf(self):
+        """Zero-copy TensorFlow tensor over the buffer (ownership moves to TensorFlow's DLPack consumer)."""
+        shape = (C.c_int64 * max(len(self.shape), 1))(*self.shape)
+        m = _DLManagedTensor()
+        m.dl_tensor.data = self.ptr.value
+        m.dl_tensor.device = _DLDevice(_KDL_CUDA, self.device_index)
+        m.dl_tensor.ndim = len(self.shape)
+        m.dl_tensor.dtype = _DLDataType(_KDL_FLOAT, 32, 1)
+        m.dl_tensor.shape = C.cast(shape, C.POINTER(C.c_int64))
+        m.dl_tensor.strides = None
+        m.dl_tensor.byte_offset = 0
+        m.manager_ctx = None
+        m.deleter = _free_output
+        _live[C.addressof(m)] = (self.lib, self.handle, self.ptr, m, shape)
+        cap = C.pythonapi.PyCapsule_New(C.addressof(m), b"dltensor", None)
+        return tf.experimental.dlpack.from_dlpack(cap)
+
+
+def _reshape_2d(x):                      # nn/losses.py:31-36
     x = tf.squeeze(x)
     return tf.reshape(x, (-1, tf.shape(x)[-1]))
 
 
-def _call_self_similarity(x, y):         # pragma: no cover
-    lib = _lib.load()
-    h = _Handles.get(0)
+def _sync():
+    tf.test.experimental.sync_devices()
+
+
+# ---- the three loss functions of nn/losses.py ------------------------------------------------------------------------------
+def _call_self_similarity(x, y):
+    dev = _device_index(x)
+    lib, h = _lib.load(), _Handles.get(dev)
     n, d = int(x.shape[0]), int(x.shape[1])
-    loss = tf.zeros([1], tf.float32)
-    grad = tf.zeros_like(x)
-    (px, kx), (py, ky), (pl, kl), (pg, kg) = _dev_ptr(x), _dev_ptr(y), _dev_ptr(loss), _dev_ptr(grad)
-    tf.test.experimental.sync_devices()
-    _lib.check(lib, h, lib.strotss_self_similarity(h, px, d, py, d, n, d, pl, pg, d, None), "strotss_self_similarity")
-    tf.test.experimental.sync_devices()
-    return loss[0], grad
+    loss, grad = _Output(lib, h, dev, (1,)), _Output(lib, h, dev, (n, d))
+    (px, kx), (py, ky) = _dev_ptr(x), _dev_ptr(y)
+    _sync()
+    code = lib.strotss_self_similarity(h, px, d, py, d, n, d, loss.ptr, grad.ptr, d, None)
+    _sync()
+    loss_t, grad_t = loss.to_tf(), grad.to_tf()
+    _lib.check(lib, h, code, "strotss_self_similarity")
+    del kx, ky
+    return loss_t[0], grad_t
 
 
-def self_similarity(x, y):               # pragma: no cover
+def self_similarity(x, y):
     """nn/losses.py:55-66 (gradient w.r.t. x, the prediction: run_strotss.py:24)."""
     _require_tf()
 
@@ -95,29 +190,30 @@ def self_similarity(x, y):               # pragma: no cover
     return op(_reshape_2d(x), _reshape_2d(y))
 
 
-def _call_pair(fn_name, x, y, distance_code=None):   # pragma: no cover
-    lib = _lib.load()
-    h = _Handles.get(0)
+def _call_pair(fn_name, x, y, distance_code=None):
+    dev = _device_index(y)
+    lib, h = _lib.load(), _Handles.get(dev)
     m, d = int(x.shape[0]), int(x.shape[1])
     n = int(y.shape[0])
-    loss = tf.zeros([4], tf.float32)
-    grad = tf.zeros_like(y)
-    (px, kx), (py, ky), (pl, kl), (pg, kg) = _dev_ptr(x), _dev_ptr(y), _dev_ptr(loss), _dev_ptr(grad)
-    tf.test.experimental.sync_devices()
+    loss, grad = _Output(lib, h, dev, (4,)), _Output(lib, h, dev, (n, d))
+    (px, kx), (py, ky) = _dev_ptr(x), _dev_ptr(y)
+    _sync()
     if fn_name == "relaxed_emd":
-        code = lib.strotss_relaxed_emd(h, px, d, m, py, d, n, d, int(distance_code), pl, pg, d, None, None, None)
+        code = lib.strotss_relaxed_emd(h, px, d, m, py, d, n, d, int(distance_code), loss.ptr, grad.ptr, d, None, None, None)
     else:
-        code = lib.strotss_moment_matching(h, px, d, m, py, d, n, d, pl, pg, d, None)
+        code = lib.strotss_moment_matching(h, px, d, m, py, d, n, d, loss.ptr, grad.ptr, d, None)
+    _sync()
+    loss_t, grad_t = loss.to_tf(), grad.to_tf()
     _lib.check(lib, h, code, "strotss_" + fn_name)
-    tf.test.experimental.sync_devices()
-    return loss[0], grad
+    del kx, ky
+    return loss_t[0], grad_t
 
 
-def relaxed_emd(x, y, distance: str = "cosine"):     # pragma: no cover
+def relaxed_emd(x, y, distance: str = "cosine"):
     """nn/losses.py:69-80 (gradient w.r.t. y, the prediction: run_strotss.py:36,39)."""
     _require_tf()
     if distance not in _lib.DIST_CODES:
-        raise KeyError(distance)
+        raise KeyError(distance)          # dist_metrics[distance], nn/losses.py:74
     code = _lib.DIST_CODES[distance]
 
     @tf.custom_gradient
@@ -130,7 +226,7 @@ def relaxed_emd(x, y, distance: str = "cosine"):     # pragma: no cover
     return op(_reshape_2d(x), _reshape_2d(y))
 
 
-def moment_matching(x, y):               # pragma: no cover
+def moment_matching(x, y):
     """nn/losses.py:39-52 (gradient w.r.t. y)."""
     _require_tf()
 
@@ -144,17 +240,17 @@ def moment_matching(x, y):               # pragma: no cover
     return op(_reshape_2d(x), _reshape_2d(y))
 
 
-def convert_rgb_to_yuv(x):               # pragma: no cover  (nn/strotss_utils.py:166-167; K=3, stays a TF op)
+def convert_rgb_to_yuv(x):               # nn/strotss_utils.py:166-167; K = 3, stays a TensorFlow op
     _require_tf()
     return tf.image.rgb_to_yuv(x[:, :3])
 
 
-class ContentLoss:                       # pragma: no cover  (run_strotss.py:21-24)
+class ContentLoss:                       # run_strotss.py:21-24
     def __call__(self, target, prediction):
         return self_similarity(prediction, target)
 
 
-class StyleLoss:                         # pragma: no cover  (run_strotss.py:27-40)
+class StyleLoss:                         # run_strotss.py:27-40
     def __init__(self, target, alpha: float):
         self.target = target
         self.inv_alpha = 1 / max(alpha, 1)
@@ -166,7 +262,7 @@ class StyleLoss:                         # pragma: no cover  (run_strotss.py:27-
         return l_m + l_remd + (self.inv_alpha * l_palette)
 
 
-class StrotssLoss:                       # pragma: no cover
+class StrotssLoss:
     """Fused evaluation for the reference's train_step (run_strotss.py:136-140): one strotss_eval call per iteration
     instead of four ops, with the style-side statistics cached per scale (strotss_set_style_target).
 
@@ -176,29 +272,46 @@ class StrotssLoss:                       # pragma: no cover
     Masked mode (:97-125): build one StrotssLoss per region exactly as the reference builds one StyleLoss per region, or
     bind strotss_set_style_targets_grouped / strotss_eval_grouped the same way (see modules.MaskedStrotssLoss)."""
 
-    def __init__(self, target, alpha: float, device_index: int = 0):
+    def __init__(self, target, alpha: float):
         _require_tf()
         self.alpha = float(alpha)
         self.lib = _lib.load()
-        self.h = C.c_void_p()
-        _lib.check(self.lib, self.h, self.lib.strotss_create(device_index, C.byref(self.h)), "strotss_create")
         t = _reshape_2d(target)
+        self.device_index = _device_index(t)          # the handle lives on the GPU of the style features
+        self.h = C.c_void_p()
+        _lib.check(self.lib, self.h, self.lib.strotss_create(self.device_index, C.byref(self.h)), "strotss_create")
         m, d = int(t.shape[0]), int(t.shape[1])
         p, keep = _dev_ptr(t)
-        tf.test.experimental.sync_devices()
-        _lib.check(self.lib, self.h, self.lib.strotss_set_style_target(self.h, p, m, d, d, None), "strotss_set_style_target")
-        tf.test.experimental.sync_devices()
+        _sync()
+        code = self.lib.strotss_set_style_target(self.h, p, m, d, d, None)
+        _sync()
+        _lib.check(self.lib, self.h, code, "strotss_set_style_target")
+        del keep
+
+    def close(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            _sync()
+            self.lib.strotss_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _call(self, content, pred):
         n, d = int(pred.shape[0]), int(pred.shape[1])
-        scalars = tf.zeros([_lib.NUM_SCALARS], tf.float32)
-        grad = tf.zeros_like(pred)
-        (pp, k1), (pc, k2), (ps, k3), (pg, k4) = _dev_ptr(pred), _dev_ptr(content), _dev_ptr(scalars), _dev_ptr(grad)
-        tf.test.experimental.sync_devices()
-        _lib.check(self.lib, self.h, self.lib.strotss_eval(self.h, pp, d, pc, d, n, self.alpha, ps, pg, d, None, None, None),
-                   "strotss_eval")
-        tf.test.experimental.sync_devices()
-        return scalars[_lib.S_TOTAL], scalars[_lib.S_LOSS_C], scalars[_lib.S_LOSS_S], grad
+        scalars = _Output(self.lib, self.h, self.device_index, (_lib.NUM_SCALARS,))
+        grad = _Output(self.lib, self.h, self.device_index, (n, d))
+        (pp, k1), (pc, k2) = _dev_ptr(pred), _dev_ptr(content)
+        _sync()
+        code = self.lib.strotss_eval(self.h, pp, d, pc, d, n, self.alpha, scalars.ptr, grad.ptr, d, None, None, None)
+        _sync()
+        s, g = scalars.to_tf(), grad.to_tf()
+        _lib.check(self.lib, self.h, code, "strotss_eval")
+        del k1, k2
+        return s[_lib.S_TOTAL], s[_lib.S_LOSS_C], s[_lib.S_LOSS_S], g
 
     def __call__(self, content, prediction):
         @tf.custom_gradient

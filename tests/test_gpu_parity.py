@@ -72,6 +72,29 @@ def test_tcgen05_gemm_transposed_a(handle, cuda_device, m, n, k):
     assert (C2.double() - 1.5 * ref).abs().max().item() <= 2 * tol
 
 
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (300, 500, 2048), (2179, 700, 1000), (64, 16, 64), (129, 257, 130)])
+def test_tcgen05_pair_gemm_mn_major_a(handle, cuda_device, m, n, k):
+    """CTA-pair kernel with an MN-major A operand: how stage 2 of the self-similarity reads the row-major x^ as x^T."""
+    g = torch.Generator().manual_seed(2 * m + 5 * n + k)
+    At = torch.randn(k, m, generator=g).to(cuda_device)
+    B = torch.randn(n, k, generator=g).to(cuda_device)
+    ref = At.bfloat16().double().T @ B.bfloat16().double().T
+    C = handle.debug_gemm_ta(At, B, 1.0, variant=1)
+    tol = 1e-5 * k ** 0.5 * ref.abs().max().item() + 1e-6
+    assert (C.double() - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("m,k", [(256, 64), (300, 2048), (2179, 1000), (64, 130), (513, 16384)])
+def test_tcgen05_pair_gemm_gram_both_mn_major(handle, cuda_device, m, k):
+    """Both operands MN-major from ONE row-major matrix: the covariance cen^T cen without a transposed copy."""
+    g = torch.Generator().manual_seed(3 * m + k)
+    At = torch.randn(k, m, generator=g).to(cuda_device)
+    ref = At.bfloat16().double().T @ At.bfloat16().double()
+    C = handle.debug_gemm_ta(At, torch.zeros(m, 1, device=cuda_device), 0.5, variant=2)
+    tol = 1e-5 * k ** 0.5 * ref.abs().max().item() + 1e-6
+    assert (C.double() - 0.5 * ref).abs().max().item() <= tol
+
+
 # ------------------------------------------------------------------------------ relaxed EMD
 @pytest.mark.parametrize("N,M,seed", [(700, 517, 0), (333, 1024, 1), (128, 256, 2), (1, 300, 3), (130, 1, 4),
                                       (2300, 300, 5), (2561, 2100, 6)])       # > 2048: CTA-pair kernels, ragged tile couples
@@ -332,8 +355,10 @@ def test_modules_match_reference_wrappers(S, cuda_device, alpha):
 
 
 def test_row_strides_are_honoured(S, cuda_device):
-    """Inputs may be column slices of wider matrices (row stride > D): the C ABI takes `ld` and must give bit-identical
-    results to the packed copies."""
+    """Inputs may be column slices of wider matrices (row stride > D): the C ABI takes `ld` and must give the results of
+    the packed copies.  Packed, 16-byte aligned rows take the streaming row pass (bulk copies), strided ones the general
+    row pass: same formulas, different summation order of the column sums, so the comparison is to fp32 rounding, the
+    argmins exactly."""
     st, co, pr = O.synth_problem(333, 200, 67, eps=0.1, seed=77)
     def wide(a, pad):
         buf = torch.full((a.shape[0], a.shape[1] + pad), 7.5, device=cuda_device, dtype=torch.float32)
@@ -346,8 +371,11 @@ def test_row_strides_are_honoured(S, cuda_device):
     h2.set_style_target(sw)
     s1, g1, ra1, ca1 = h1.eval(_t(pr, cuda_device), _t(co, cuda_device), 4.0, True, True)
     s2, g2, ra2, ca2 = h2.eval(wide(pr, 13), wide(co, 3), 4.0, True, True)
-    assert torch.equal(s1[:12], s2[:12]) and torch.equal(ra1, ra2) and torch.equal(ca1, ca2)
-    assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-10)          # the scatter branch of the relaxed EMD uses float atomics
+    assert torch.allclose(s1[:12], s2[:12], rtol=2e-5, atol=1e-8) and torch.equal(ra1, ra2) and torch.equal(ca1, ca2)
+    assert float((g1 - g2).norm() / g1.norm()) <= 2e-3            # sign flips of L1 terms that are ~0 to within fp32 rounding
+    # two packed evaluations (the same path twice) are bit-identical in every scalar
+    s3, g3, _, _ = h1.eval(_t(pr, cuda_device), _t(co, cuda_device), 4.0, True, True)
+    assert torch.equal(s1[:12], s3[:12])
 
 
 def test_evaluation_is_cuda_graph_capturable(S, cuda_device):
@@ -639,7 +667,8 @@ print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.no
                                  {"STROTSS_PANEL": "1024"}, {"STROTSS_FINALIZE_GENERIC": "1", "STROTSS_NO_KTAIL": "1", "STROTSS_PREP_V1": "1"},
                                  {"STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_PANEL": "1024"},
                                  {"STROTSS_SS1_MERGED": "0", "STROTSS_REMD_SKEW": "-1"}, {"STROTSS_SS1_TAIL": "0", "STROTSS_REMD_SKEW": "0"},
-                                 {"STROTSS_SS1_TAIL": "40", "STROTSS_REMD_SKEW": "40"}])
+                                 {"STROTSS_SS1_TAIL": "40", "STROTSS_REMD_SKEW": "40"}, {"STROTSS_PREP_V2": "1"},
+                                 {"STROTSS_PREP_V2": "1", "STROTSS_V_FP32": "1", "STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_NO_TRAP": "1"}])
 def test_alternative_kernel_paths(cuda_device, env):
     """The single-CTA GEMM kernels (STROTSS_NO_PAIR), the generic stage-1 epilogue (STROTSS_SS1_GENERIC), the
     single-stream launch order (STROTSS_BRANCHES=0), the two-pass palette search and the two-stream stage-1/stage-2
