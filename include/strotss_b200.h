@@ -61,7 +61,7 @@ const char* strotss_version(void);
 /* bytes of device workspace currently held by the handle */
 size_t strotss_workspace_bytes(strotss_handle h);
 /* Output buffers for bindings whose tensors are immutable (TensorFlow: INTEGRATION.md): device memory on the handle's GPU,
- * owned by the caller until strotss_device_free.  The tf.custom_gradient adapter wraps such a buffer in a DLPack capsule
+ * owned by the caller until strotss_device_free (which may be called after the handle is gone: `h` is ignored there).  The tf.custom_gradient adapter wraps such a buffer in a DLPack capsule
  * (tf.experimental.dlpack.from_dlpack) instead of writing into an EagerTensor.  No reference counterpart (TensorFlow's
  * allocator does this inside every op, e.g. for the result of tf.matmul at nn/losses.py:15). */
 int strotss_device_alloc(strotss_handle h, size_t bytes, void** out);

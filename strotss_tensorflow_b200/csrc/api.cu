@@ -160,6 +160,9 @@ struct strotss_ctx {
     std::unordered_map<TmKey, CUtensorMap, TmHash> tmaps;
     size_t ws_bytes = 0;
     long long launches = 0;
+    // programmatic dependent launch for the kernels of the evaluation path (see pdl_wait in common.cuh); decided per public
+    // call: off while the caller's stream is being captured and with STROTSS_PDL=0
+    bool pdl = false;
     // style target
     bool has_style = false;
     int M = 0, D = 0, Dp = 0, Mp = 0;
@@ -254,6 +257,37 @@ struct strotss_ctx {
     do { int _r = (expr); if (_r != 0) return _r; } while (0)
 
 namespace {
+
+// Launch through cudaLaunchKernelEx so that the launch can carry the programmatic-stream-serialization attribute: the
+// kernel's blocks may then be scheduled while the previous kernel of the stream drains; every kernel launched this way starts
+// with pdl_wait().
+template <class... KArgs, class... Args>
+inline void klaunch(const strotss_ctx* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface through CKL() / cudaGetLastError
+}
+#define KL(kern, grid, block, smem, st, ...) klaunch(h, kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+
+// Measured on B200 (profiles/r02_v5_bench_{pdl,nopdl}*.json): 237.7 / 240.2 evals/s with, 238.3 / 238.6 without at
+// N = M = 16384, and 0.1868 vs 0.1874 ms at N = M = 1024 -- the launches of this path are already issued ahead of the GPU, and
+// a prologue of a few microseconds per GEMM launch is below the run-to-run noise.  Off by default; STROTSS_PDL=1 enables it.
+bool pdl_enabled() {
+    static const bool on = getenv("STROTSS_PDL") && atoi(getenv("STROTSS_PDL")) != 0;
+    return on;
+}
+// decide once per public call (capture status of the caller's stream)
+void set_pdl(strotss_ctx* h, cudaStream_t st) {
+    h->pdl = false;
+    if (!pdl_enabled()) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return; }
+    h->pdl = (cap == cudaStreamCaptureStatusNone);
+}
 
 struct PhaseTimer {
     strotss_ctx* h; cudaStream_t st; PhaseRec r; bool on;
@@ -350,7 +384,7 @@ int launch_gemm(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
         q.group_n = static_cast<int>(g);
     }
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    KL(kern, grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st, q);
     CKL();
     return 0;
 }
@@ -396,7 +430,7 @@ int launch_gemm256(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     }
     const int max_pairs = h->num_sms / 2;
     const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    KL(kern, grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st, q);
     CKL();
     return 0;
 }
@@ -453,7 +487,7 @@ int launch_gemm256s(strotss_ctx* h, const GemmParams<Epi>& p, int skew, cudaStre
     }
     const int max_pairs = h->num_sms / 2;
     const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    KL(kern, grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st, q);
     CKL();
     return 0;
 }
@@ -508,7 +542,7 @@ int launch_gemm256w(strotss_ctx* h, const GemmParams<Epi>& p, cudaStream_t st) {
     }
     const int max_pairs = h->num_sms / 2;
     const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-    kern<<<grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st>>>(q);
+    KL(kern, grid, kNonEpiThreads + 32 * EPI_WARPS, smem, st, q);
     CKL();
     return 0;
 }
@@ -530,10 +564,10 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
     RET(ensure(h, (t + ".inv").c_str(), n, &f.inv));
     if (w.mean) { RET(ensure(h, (t + ".mean").c_str(), D, &f.mean)); RET(ensure(h, (t + ".praw").c_str(), (size_t)nblk * D, &part_raw)); }
     if (w.sumhat) { RET(ensure(h, (t + ".sumhat").c_str(), D, &f.sumhat)); RET(ensure(h, (t + ".phat").c_str(), (size_t)nblk * D, &part_hat)); }
-    row_stats_kernel<<<nblk, 256, 0, st>>>(x, ld, n, D, f.inv, part_raw, part_hat, rpb);
+    KL(row_stats_kernel, nblk, 256, 0, st, x, ld, n, D, f.inv, part_raw, part_hat, rpb);
     CKL();
-    if (w.mean) { colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(part_raw, nblk, D, 1.f / n, f.mean); CKL(); }
-    if (w.sumhat) { colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(part_hat, nblk, D, 1.f, f.sumhat); CKL(); }
+    if (w.mean) { KL(colsum_finish_kernel, (D + 31) / 32, 256, 0, st, part_raw, nblk, D, 1.f / n, f.mean); CKL(); }
+    if (w.sumhat) { KL(colsum_finish_kernel, (D + 31) / 32, 256, 0, st, part_hat, nblk, D, 1.f, f.sumhat); CKL(); }
     EmitArgs a{};
     a.x = x; a.ldx = ld; a.n = n; a.D = D; a.Dp = Dp; a.np = f.np; a.inv = f.inv; a.mean = f.mean;
     if (w.xh) { RET(ensure(h, (t + ".xh").c_str(), (size_t)n * Dp, &f.xh)); a.xh = f.xh; }
@@ -546,13 +580,13 @@ int prep_features(strotss_ctx* h, const char* tag, Feat& f, const float* x, long
     if (w.cenT) { RET(ensure(h, (t + ".cenT").c_str(), (size_t)D * f.np, &f.cenT)); a.cenT = f.cenT; }
     if (w.xh || w.cen || w.dlt || w.xhT || w.cenT) {
         dim3 grid(Dp / 64, f.np / 64);
-        emit_operands_kernel<<<grid, 256, 0, st>>>(a);
+        KL(emit_operands_kernel, grid, 256, 0, st, a);
         CKL();
     }
     if (w.rec) {
         RET(ensure(h, (t + ".rec").c_str(), (size_t)n * 8, &f.rec));
         RET(ensure(h, (t + ".srec").c_str(), (size_t)n * 8, &f.srec));
-        pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, rec_convert, f.rec, f.srec);
+        KL(pal_prep_kernel, (n + 127) / 128, 128, 0, st, x, ld, n, rec_convert, f.rec, f.srec);
         CKL();
     }
     return 0;
@@ -587,10 +621,10 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
         const int rpb = rows_per_block(h, n, kPrRowsPerBlock, kPrGroup);      // 16 / 8 rows per block at N = 16384: 3 % / 8 % slower
         const int nblk = (n + rpb - 1) / rpb;
         RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
-        prep_pair_rows_kernel<<<nblk, 256, 2 * kPrGroup * Dp * (int)sizeof(float), st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh,
+        KL(prep_pair_rows_kernel, nblk, 256, 2 * kPrGroup * Dp * (int)sizeof(float), st, x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh,
                                                                                        fy.xh, fx.dlt, part, rpb);
         CKL();
-        colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+        KL(colsum3_finish_kernel, dim3((D + 31) / 32, 3), 256, 0, st, part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
         CKL();
     } else {
         // double-buffered row pass: 72 KB of staging per block, three blocks per SM, one wave of blocks
@@ -598,10 +632,10 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
         if (rpb < kPrGroup) rpb = kPrGroup;
         const int nblk = (n + rpb - 1) / rpb;
         RET(ensure(h, "pred.part3", (size_t)nblk * 3 * D, &part));
-        prep_pair_rows2_kernel<<<nblk, 256, 4 * kPrGroup * Dp * (int)sizeof(float), st>>>(x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh,
+        KL(prep_pair_rows2_kernel, nblk, 256, 4 * kPrGroup * Dp * (int)sizeof(float), st, x, ldx, y, ldy, n, D, Dp, fx.inv, fy.inv, fx.xh,
                                                                                         fy.xh, fx.dlt, part, rpb);
         CKL();
-        colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+        KL(colsum3_finish_kernel, dim3((D + 31) / 32, 3), 256, 0, st, part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
         CKL();
     }
     EmitArgs a{};
@@ -612,11 +646,11 @@ int prep_pred_content(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, long l
     }
     RET(ensure(h, "pred.cenT", (size_t)D * fx.np, &fx.cenT)); a.cenT = fx.cenT;
     if (prep_v1) {
-        emit_operands_kernel<<<dim3(Dp / 64, fx.np / 64), 256, 0, st>>>(a);
+        KL(emit_operands_kernel, dim3(Dp / 64, fx.np / 64), 256, 0, st, a);
     } else {
         const int tx = Dp / 64, ty = fx.np / 64;
         const int grid = tx * ty < 5 * h->num_sms ? tx * ty : 5 * h->num_sms;
-        emit_operands2_kernel<<<grid, 256, 0, st>>>(a, tx, ty);
+        KL(emit_operands2_kernel, grid, 256, 0, st, a, tx, ty);
     }
     CKL();
     return 0;
@@ -665,14 +699,14 @@ int prep_pred_content3(strotss_ctx* h, Feat& fx, Feat& fy, const float* x, const
     RowsArgs a{};
     a.x = x; a.y = y; a.n = n; a.D = D; a.Dp = Dp; a.rows_per_block = rpb;
     a.inv_x = fx.inv; a.inv_y = fy.inv; a.part = part;
-    rows_stats3_kernel<<<nblk, kRpThreads, smem1, st>>>(a);
+    KL(rows_stats3_kernel, nblk, kRpThreads, smem1, st, a);
     CKL();
-    colsum3_finish_kernel<<<dim3((D + 31) / 32, 3), 256, 0, st>>>(part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
+    KL(colsum3_finish_kernel, dim3((D + 31) / 32, 3), 256, 0, st, part, nblk, D, 1.f / n, fx.mean, fx.sumhat, fy.sumhat);
     CKL();
     a.mean = fx.mean; a.sumhx = fx.sumhat; a.sumhy = fy.sumhat;
     a.xh = fx.xh; a.yh = fy.xh; a.dlt = fx.dlt; a.cen = fx.cen; a.cen_r0 = cen_rows.r0; a.cen_r1 = cen_rows.r1;
     a.u = fx.u; a.w = fx.w; a.sclamp = fx.sclamp;
-    rows_emit3_kernel<<<nblk, kRpThreads, smem2, st>>>(a);
+    KL(rows_emit3_kernel, nblk, kRpThreads, smem2, st, a);
     CKL();
     fx.xhT = nullptr; fx.cenT = nullptr;      // the GEMMs read x^ / cen through MN-major descriptors
     return 0;
@@ -682,7 +716,7 @@ int prep_rec(strotss_ctx* h, const char* tag, Feat& f, const float* x, long long
     PhaseTimer _pt(h, PH_PREP, st);
     RET(ensure(h, (std::string(tag) + ".rec").c_str(), (size_t)n * 8, &f.rec));
     RET(ensure(h, (std::string(tag) + ".srec").c_str(), (size_t)n * 8, &f.srec));
-    pal_prep_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, ld, n, convert, f.rec, f.srec);
+    KL(pal_prep_kernel, (n + 127) / 128, 128, 0, st, x, ld, n, convert, f.rec, f.srec);
     CKL();
     return 0;
 }
@@ -795,7 +829,7 @@ int remd_local(strotss_ctx* h, const Feat& target, int M, const Feat& pred, int 
     }
     if (ry_partial) {                     // null on a single GPU: remd_finish sums the column minima itself
         PhaseTimer _pm(h, PH_REMD_MISC, st);
-        best_partial_kernel<<<1, 1024, 0, st>>>(rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
+        KL(best_partial_kernel, 1, 1024, 0, st, rs.colbest + sh.r0, sh.n(), 1.f, ry_partial);
         CKL();
     }
     return 0;
@@ -805,7 +839,7 @@ int remd_finish(strotss_ctx* h, const Feat& target, int M, int N, Shard sh, int 
                 float* scalars, int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad, int32_t* row_arg,
                 int32_t* col_arg, cudaStream_t st) {
     PhaseTimer _pm(h, PH_REMD_MISC, st);
-    remd_finish_kernel<<<1, 1024, 0, st>>>(rs.rowbest, M, ry_sum, N, 1.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
+    KL(remd_finish_kernel, 1, 1024, 0, st, rs.rowbest, M, ry_sum, N, 1.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
                                            row_arg, rs.colbest, sh.r0, sh.r1, col_arg);
     CKL();
     rs.g = nullptr; rs.ldg = 0;
@@ -813,9 +847,9 @@ int remd_finish(strotss_ctx* h, const Feat& target, int M, int N, Shard sh, int 
         RET(ensure(h, "remd.g", (size_t)sh.n() * D, &rs.g));
         rs.ldg = D;
         // scatter branch only (both kernels return immediately in the gather branch, which finalize handles)
-        cond_zero_kernel<<<2 * h->num_sms, 256, 0, st>>>(rs.g, (long long)sh.n() * D, scalars, slot_branch);
+        KL(cond_zero_kernel, 2 * h->num_sms, 256, 0, st, rs.g, (long long)sh.n() * D, scalars, slot_branch);
         CKL();
-        remd_backward_kernel<<<(M + 7) / 8, 256, 0, st>>>(rs.rowbest, M, sh.r0, sh.r1, target.x, target.ld, target.inv, D, scalars,
+        KL(remd_backward_kernel, (M + 7) / 8, 256, 0, st, rs.rowbest, M, sh.r0, sh.r1, target.x, target.ld, target.inv, D, scalars,
                                                           slot_branch, rs.g, rs.ldg);
         CKL();
     }
@@ -835,7 +869,7 @@ int pal_launch(strotss_ctx* h, const float* q, int nq, const float* k, int nk, i
     const int kchunk = round_up((nk + ks - 1) / ks, kPalKeyTile);
     ks = (nk + kchunk - 1) / kchunk;
     dim3 grid(qblocks, ks);
-    pal_min_kernel<<<grid, kPalThreads, 0, st>>>(q, nq, k, nk, kchunk, mode, kidx_base, best);
+    KL(pal_min_kernel, grid, kPalThreads, 0, st, q, nq, k, nk, kchunk, mode, kidx_base, best);
     CKL();
     return 0;
 }
@@ -869,15 +903,15 @@ int pal_local(strotss_ctx* h, const float* asrec, int M, const float* bsrec, int
         const dim3 grid(qblocks, ks);
         const float* keys = bsrec + (size_t)sh.r0 * 8;
         if (mode == STROTSS_DIST_BOTH)
-            pal_min2_kernel<2><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
+            KL(pal_min2_kernel<2>, grid, kPalThreads, 0, st, asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
         else if (mode == STROTSS_DIST_L2)
-            pal_min2_kernel<1><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
+            KL(pal_min2_kernel<1>, grid, kPalThreads, 0, st, asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
         else
-            pal_min2_kernel<0><<<grid, kPalThreads, 0, st>>>(asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
+            KL(pal_min2_kernel<0>, grid, kPalThreads, 0, st, asrec, nq, keys, nk, kchunk, sh.r0, ps.rowbest, ps.colbest + sh.r0);
         CKL();
     }
     if (ry_partial) {
-        best_partial_kernel<<<1, 1024, 0, st>>>(ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
+        KL(best_partial_kernel, 1, 1024, 0, st, ps.colbest + sh.r0, sh.n(), 0.f, ry_partial);
         CKL();
     }
     return 0;
@@ -887,7 +921,7 @@ int pal_finish(strotss_ctx* h, const float* arec, int M, const float* brec, int 
                const float* ry_sum, float* scalars, int slot_loss, int slot_rx, int slot_ry, int slot_branch, bool want_grad,
                int32_t* row_arg, int32_t* col_arg, cudaStream_t st, float* g_zeroed = nullptr) {
     PhaseTimer _pt(h, PH_PALETTE, st);
-    remd_finish_kernel<<<1, 1024, 0, st>>>(ps.rowbest, M, ry_sum, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
+    KL(remd_finish_kernel, 1, 1024, 0, st, ps.rowbest, M, ry_sum, N, 0.f, scalars, slot_loss, slot_rx, slot_ry, slot_branch,
                                            row_arg, ps.colbest, sh.r0, sh.r1, col_arg);
     CKL();
     ps.g = nullptr;
@@ -899,7 +933,7 @@ int pal_finish(strotss_ctx* h, const float* arec, int M, const float* brec, int 
             CK(cudaMemsetAsync(ps.g, 0, sizeof(float) * (size_t)sh.n() * 4, st));
         }
         const int rows = M > sh.n() ? M : sh.n();
-        pal_backward_kernel<<<(rows + 127) / 128, 128, 0, st>>>(ps.rowbest, M, ps.colbest, N, sh.r0, sh.r1, arec, brec, mode,
+        KL(pal_backward_kernel, (rows + 127) / 128, 128, 0, st, ps.rowbest, M, ps.colbest, N, sh.r0, sh.r1, arec, brec, mode,
                                                                 convert, scalars, slot_branch, ps.g);
         CKL();
     }
@@ -947,7 +981,7 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
     RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
     {
         PhaseTimer _pt(h, PH_MOM_MISC, st);
-        moment_finish_kernel<<<1, 1024, 0, st>>>(pred.mean, mu_x, D, part, npart, out.gmu, scalars);
+        KL(moment_finish_kernel, 1, 1024, 0, st, pred.mean, mu_x, D, part, npart, out.gmu, scalars);
         CKL();
     }
     out.Q = nullptr; out.ldq = 0; out.q_scale = 0.f;
@@ -1029,7 +1063,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         RET(ensure(h, "ss.w", (size_t)N, &w));
         RET(ensure(h, "ss.sclamp", (size_t)N, &sclamp));
         PhaseTimer _pt(h, PH_SS_VEC, st);
-        ss_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
+        KL(ss_vectors_kernel, (N + 7) / 8, 256, 0, st, x.x, x.ld, x.inv, x.sumhat, y.x, y.ld, y.inv, y.sumhat, N, D, u, w, sclamp);
         CKL();
     }
     // stage 2 multiplies P with x^: either the transposed copy x^T (K-major A) or, when the row pass made none, x^ itself read
@@ -1177,15 +1211,15 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
                     static const int tail_blocks = getenv("STROTSS_SS1_TAIL") ? atoi(getenv("STROTSS_SS1_TAIL")) : 4;
                     sp.tail_blocks = tail_blocks < 0 ? 0 : tail_blocks;
                     const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-                    if (merged) ss1_pair_merged_kernel<<<grid, kSs1Threads, kSs1MergedSmemBytes, st>>>(sp);
-                    else ss1_pair_kernel<<<grid, kSs1Threads, kSs1PairSmemBytes, st>>>(sp);
+                    if (merged) KL(ss1_pair_merged_kernel, grid, kSs1Threads, kSs1MergedSmemBytes, st, sp);
+                    else KL(ss1_pair_kernel, grid, kSs1Threads, kSs1PairSmemBytes, st, sp);
                     CKL();
                 }
             } else {
                 const int tiles = sp.tiles_m * sp.tiles_n;
                 if (tiles > 0) {
                     PhaseTimer _pt(h, PH_SS1, st);
-                    ss1_kernel<<<tiles < h->num_sms ? tiles : h->num_sms, kSs1Threads, kSs1SmemBytes, st>>>(sp);
+                    KL(ss1_kernel, tiles < h->num_sms ? tiles : h->num_sms, kSs1Threads, kSs1SmemBytes, st, sp);
                     CKL();
                 }
             }
@@ -1294,12 +1328,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
     if (sh.n() > 0) {
-        ss_rows_kernel<<<(sh.n() + 31) / 32, 256, 0, st>>>(loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
+        KL(ss_rows_kernel, (sh.n() + 31) / 32, 256, 0, st, loss_part, r_part, nslots, N, sh.r0, sh.r1, u, sclamp, out.coef, rowloss,
                                                              sym ? 1 : 0, trap ? 256 : panel, trap ? ss_split : (panel / ss_bn) * ss_split, rcol_part,
                                                              trap ? (256 / BM) * 4 : (panel / BM) * 4);
         CKL();
     }
-    reduce_sum_kernel<<<1, 1024, 0, st>>>(rowloss + sh.r0, sh.n(), 1.f, loss_partial);
+    KL(reduce_sum_kernel, 1, 1024, 0, st, rowloss + sh.r0, sh.n(), 1.f, loss_partial);
     CKL();
     if (want_grad) {
         if (sh.n() > 0) {
@@ -1310,12 +1344,12 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             // v = sum_i coef_i x^_i: from the bf16 x^ rows (half the bytes of x; the rounding errors of 16384 rows average out)
             static const bool v_fp32 = (getenv("STROTSS_V_FP32") != nullptr);
             if (x.xh && !v_fp32)
-                weighted_colsum_bf16_kernel<<<nblk, 256, 0, st>>>(x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
+                KL(weighted_colsum_bf16_kernel, nblk, 256, 0, st, x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
             else
-                weighted_colsum_kernel<<<nblk, 256, 0, st>>>(x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
+                KL(weighted_colsum_kernel, nblk, 256, 0, st, x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
                                                              out.coef + sh.r0, vpart, rpb);
             CKL();
-            colsum_finish_kernel<<<(D + 31) / 32, 256, 0, st>>>(vpart, nblk, D, 1.f, v_partial);
+            KL(colsum_finish_kernel, (D + 31) / 32, 256, 0, st, vpart, nblk, D, 1.f, v_partial);
             CKL();
         } else {
             CK(cudaMemsetAsync(v_partial, 0, sizeof(float) * D, st));
@@ -1328,8 +1362,8 @@ int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) 
     if (nrows <= 0) return 0;
     PhaseTimer _pt(h, PH_FINALIZE, st);
     static const bool generic = (getenv("STROTSS_FINALIZE_GENERIC") != nullptr);
-    if (a.D <= kFinU * 256 && !generic) finalize_grad_1b_kernel<<<nrows, 256, 0, st>>>(a);
-    else finalize_grad_kernel<<<nrows, 256, sizeof(float) * a.D, st>>>(a);
+    if (a.D <= kFinU * 256 && !generic) KL(finalize_grad_1b_kernel, nrows, 256, 0, st, a);
+    else KL(finalize_grad_kernel, nrows, 256, sizeof(float) * a.D, st, a);
     CKL();
     return 0;
 }
@@ -1419,12 +1453,19 @@ int strotss_device_alloc(strotss_handle h, size_t bytes, void** out) {
     return 0;
 }
 
+// The buffer may outlive the handle that allocated it (a framework frees an output tensor whenever its last reference
+// dies), so nothing of `h` is touched here: the device comes from the pointer itself.
 int strotss_device_free(strotss_handle h, void* ptr) {
-    RET(check_handle(h));
+    (void)h;
     if (!ptr) return 0;
-    CK(cudaSetDevice(h->device));
-    CK(cudaFree(ptr));
-    return 0;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) { cudaGetLastError(); return STROTSS_ERR_ARG; }
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) return STROTSS_ERR_CUDA;
+    if (cudaSetDevice(attr.device) != cudaSuccess) return STROTSS_ERR_CUDA;
+    const cudaError_t e = cudaFree(ptr);
+    cudaSetDevice(prev);
+    return e == cudaSuccess ? 0 : STROTSS_ERR_CUDA;
 }
 
 long long strotss_launch_count(strotss_handle h) {
@@ -1502,6 +1543,7 @@ int strotss_set_style_target(strotss_handle h, const float* style, int M, int D,
 
 static int set_style_impl(strotss_handle h, const float* style, int M, int D, long long ld, cudaStream_t st) {
     h->has_style = false;
+    set_pdl(h, st);
     h->M = M; h->D = D; h->Dp = round_up(D, BK); h->Mp = round_up(M, 64);
     // private copy: later evaluations must not depend on the caller keeping `style` alive
     float* copy;
@@ -1521,6 +1563,7 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
                      bool with_content, bool sharded, cudaStream_t st, float grad_scale = 1.f) {
     const int D = h->D, Dp = h->Dp, M = h->M;
     const bool want_grad = grad != nullptr;
+    set_pdl(h, st);
     const float inv_alpha = 1.f / (alpha > 1.f ? alpha : 1.f);
     const float denom = with_content ? (2.f + alpha + inv_alpha) : 1.f;
     const Shard sh = shard_of(h, N, sharded);
@@ -1607,7 +1650,7 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, ry_pal, scalars, S_LPAL, S_PAL_RX,
                        S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, st, pal_g));
     }
-    combine_scalars_kernel<<<1, 32, 0, st>>>(scalars, with_content ? alpha : 0.f, inv_alpha, denom,
+    KL(combine_scalars_kernel, 1, 32, 0, st, scalars, with_content ? alpha : 0.f, inv_alpha, denom,
                                              with_content ? partials + PS_SS_LOSS : nullptr, 1.f / N);
     CKL();
     if (want_grad) {
@@ -1872,6 +1915,7 @@ int strotss_relaxed_emd(strotss_handle h, const float* x, long long ldx, int M, 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
+    set_pdl(h, st);
     float* sc; unsigned long long* best; float* partials;
     RET(ensure(h, "fn.scalars", (size_t)S_COUNT, &sc));
     RET(ensure(h, "fn.best", (size_t)M, &best));
@@ -1929,6 +1973,7 @@ int strotss_moment_matching(strotss_handle h, const float* x, long long ldx, int
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
+    set_pdl(h, st);
     const int Dp = round_up(D, BK);
     const bool want_grad = grad_y != nullptr;
     float* sc;
@@ -1963,6 +2008,7 @@ int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, con
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaSetDevice(h->device));
+    set_pdl(h, st);
     const int Dp = round_up(D, BK);
     const bool want_grad = grad_x != nullptr;
     float* partials;
@@ -1974,7 +2020,7 @@ int strotss_self_similarity(strotss_handle h, const float* x, long long ldx, con
     RET(prep_features(h, "fn.x", fx, x, ldx, N, D, Dp, wx, &fy, 0, st));
     SsOut so;
     RET(self_sim_local(h, fx, fy, N, Shard{0, N}, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
-    reduce_sum_kernel<<<1, 32, 0, st>>>(partials + PS_SS_LOSS, 1, 1.f / N, loss);
+    KL(reduce_sum_kernel, 1, 32, 0, st, partials + PS_SS_LOSS, 1, 1.f / N, loss);
     CKL();
     if (want_grad) {
         FinalizeArgs a{};

@@ -30,6 +30,16 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the evaluation path may be launched with cudaLaunchAttributeProgrammaticStreamSerialization: its blocks can
+// then be scheduled while the previous kernel of the stream is still draining, and pdl_wait() blocks until that kernel has
+// completed and its writes are visible.  pdl_wait() is the FIRST statement that could observe or overwrite anything another
+// kernel touches (only barrier init / TMEM allocation / descriptor prefetch may precede it); it is a no-op for an ordinary
+// launch.  pdl_trigger() lets the NEXT kernel's blocks start as soon as SM resources free up; single-wave kernels call it at
+// once (a waiting dependent then never competes with blocks of this grid that are still to be scheduled).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));

@@ -75,6 +75,8 @@ gemm2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     cluster_sync_all();                 // barriers of BOTH CTAs are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                      // persistent single-wave grid: dependents may be scheduled as CTAs exit
+    pdl_wait();                         // the previous kernel of the stream has completed; its writes are visible
 
     const int num_tiles = num_tiles_of(p);
 
@@ -238,6 +240,8 @@ gemm2w_kernel(const __grid_constant__ GemmParams<Epi> p) {
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                      // persistent single-wave grid: dependents may be scheduled as CTAs exit
+    pdl_wait();                         // the previous kernel of the stream has completed; its writes are visible
     const int num_tiles = num_tiles_of(p);
 
     // K-block range of segment s for the whole tile (union over the two sub-tiles) and per sub-tile
@@ -416,6 +420,8 @@ gemm2s_kernel(const __grid_constant__ GemmParams<Epi> p) {
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                      // persistent single-wave grid: dependents may be scheduled as CTAs exit
+    pdl_wait();                         // the previous kernel of the stream has completed; its writes are visible
     const int num_tiles = num_tiles_of(p);
     const int K = p.seg_kblocks[0];
     const int skew = p.skew < K ? (p.skew > 0 ? p.skew : 0) : K;

@@ -19,7 +19,7 @@ namespace sb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kNonEpiThreads = 128;           // warps 0..3: TMA, MMA, TMEM alloc, spare
-constexpr int kMaxSeg = 3;
+constexpr int kMaxSeg = 10;          // the row-sharded stage 2 sums up to world + 2 operand blocks into one accumulator
 constexpr int kSmemBudget = 232448 - 1024;   // 227 KB minus alignment slack
 
 template <int BN, int NACC>
@@ -131,6 +131,8 @@ gemm_kernel(const __grid_constant__ GemmParams<Epi> p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                      // persistent single-wave grid: dependents may be scheduled as CTAs exit
+    pdl_wait();                         // the previous kernel of the stream has completed; its writes are visible
 
     const int num_tiles = num_tiles_of(p);
 
@@ -393,6 +395,8 @@ struct EpiSS1 {
         // strictly right of the panel (col0 >= panel_end) also account for their mirror images:
         int sym, panel_end;
         float* rcol_part;                     // [row_blocks * 4][N]: per-warp column sums of sign_col * Xd
+        int p_col0;                           // column of the matrix stored in column 0 of P (row-sharded jobs keep one
+                                              // contiguous [rows][cols] block per column range; 0 for a full-width panel)
     };
     struct State {};
     __device__ static void init(State&, const Params&, int, int) {}
@@ -446,10 +450,10 @@ struct EpiSS1 {
                 }
                 packed[e >> 1] = pack_bf16x2(pv[0], pv[1]);
             }
-            if (P.write_p && rvalid && colbase < P.ldp) {
+            if (P.write_p && rvalid && colbase - P.p_col0 < P.ldp) {
                 // ldp is a multiple of 64 and colbase a multiple of 32, so a 32-wide chunk is
                 // either fully inside the padded row or fully outside it.
-                uint4* dst = reinterpret_cast<uint4*>(prow + colbase);
+                uint4* dst = reinterpret_cast<uint4*>(prow + (colbase - P.p_col0));
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
                     dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);

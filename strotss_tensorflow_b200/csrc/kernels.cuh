@@ -28,6 +28,7 @@ enum Scalar {
 __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, long long ld, int n, int D,
                                                         float* __restrict__ inv, float* __restrict__ part_raw,
                                                         float* __restrict__ part_hat, int rpb) {
+    pdl_wait();
     __shared__ float s_inv[kRowsPerBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * rpb;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __restrict__ x, long long ld, int n, int D,
                                                               const float* __restrict__ inv, const float* __restrict__ coef,
                                                               float* __restrict__ part, int rpb) {
+    pdl_wait();
     __shared__ float s_w[kRowsPerBlock];
     const int r0 = blockIdx.x * rpb;
     if (threadIdx.x < rpb) {
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __res
 // the same from the normalised bf16 rows: part[b][d] = sum_{r in block b} coef[r] * xh[r][d]   (two columns per thread)
 __global__ void __launch_bounds__(256) weighted_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ xh, long long ld, int n, int D,
                                                                    const float* __restrict__ coef, float* __restrict__ part, int rpb) {
+    pdl_wait();
     __shared__ float s_w[kRowsPerBlock];
     const int r0 = blockIdx.x * rpb;
     if (threadIdx.x < rpb) {
@@ -108,6 +111,8 @@ __global__ void __launch_bounds__(256) weighted_colsum_bf16_kernel(const __nv_bf
 // block = 32 columns x 8 block-groups
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ part, int nblocks, int D, float scale,
                                                             float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sh[8][33];
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int d = blockIdx.x * 32 + c;
@@ -150,6 +155,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // Persistent, double-buffered variant for the calls without a delta operand (the fused evaluation): every block walks the
 // 64 x 64 tiles with stride gridDim.x and fetches its next tile with cp.async while it converts and stores the current one.
 __global__ void __launch_bounds__(256) emit_operands2_kernel(const EmitArgs a, int tiles_x, int tiles_y) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sx[2][64][65];
     __shared__ float s_inv[2][64], s_mean[2][64];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -217,6 +224,7 @@ __global__ void __launch_bounds__(256) emit_operands2_kernel(const EmitArgs a, i
 }
 
 __global__ void __launch_bounds__(256) emit_operands_kernel(const EmitArgs a) {
+    pdl_wait();
     __shared__ float sx[64][65];
     __shared__ float sy[64][65];
     __shared__ float s_inv[64], s_invy[64], s_mean[64];
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(256, 4) prep_pair_rows_kernel(const float* __r
                                                              __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ yh,
                                                              __nv_bfloat16* __restrict__ dlt, float* __restrict__ part,
                                                              int rows_per_block) {
+    pdl_wait();
     extern __shared__ float sm[];          // [2][kPrGroup][Dp]
     __shared__ float s_inv[2][kPrGroup];
     float* sx = sm;
@@ -387,6 +396,8 @@ __global__ void __launch_bounds__(256, 3) prep_pair_rows2_kernel(const float* __
                                                                  __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ yh,
                                                                  __nv_bfloat16* __restrict__ dlt, float* __restrict__ part,
                                                                  int rows_per_block) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float sm[];          // [2 buffers][x | y][kPrGroup][Dp]
     __shared__ float s_inv[2][kPrGroup];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -536,6 +547,8 @@ __device__ __forceinline__ void rows_load_ragged(const RowsArgs& a, int r, float
 }
 
 __global__ void __launch_bounds__(kRpThreads, 1) rows_stats3_kernel(const RowsArgs a) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) float rp_smem[];      // [2 stages][x | y][kRpGroup][D]
     __shared__ uint64_t full[2];
     __shared__ float s_inv[2][kRpGroup];
@@ -602,6 +615,8 @@ __global__ void __launch_bounds__(kRpThreads, 1) rows_stats3_kernel(const RowsAr
 }
 
 __global__ void __launch_bounds__(kRpThreads, 1) rows_emit3_kernel(const RowsArgs a) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) float rp_smem[];      // [2 stages][x | y][kRpGroup][D] | mean[Dp] | sumhx[Dp] | sumhy[Dp]
     __shared__ uint64_t full[2];
     __shared__ float s_dot[2][kRpGroup][2][2];           // [stage][row][half][x | y]
@@ -682,6 +697,8 @@ __global__ void __launch_bounds__(kRpThreads, 1) rows_emit3_kernel(const RowsArg
 __global__ void __launch_bounds__(256) colsum3_finish_kernel(const float* __restrict__ part, int nblocks, int D,
                                                              float scale0, float* __restrict__ out0,
                                                              float* __restrict__ out1, float* __restrict__ out2) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sh[8][33];
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int d = blockIdx.x * 32 + c;
@@ -712,6 +729,7 @@ __global__ void __launch_bounds__(256) ss_vectors_kernel(const float* __restrict
                                                          const float* __restrict__ sumhy,
                                                          int N, int D, float* __restrict__ u, float* __restrict__ w,
                                                          float* __restrict__ sclamp) {
+    pdl_wait();
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= N) return;
@@ -750,6 +768,7 @@ __global__ void __launch_bounds__(256) ss_rows_kernel(const float* __restrict__ 
                                float* __restrict__ coef, float* __restrict__ rowloss,
                                int sym, int panel_rows, int slots_per_panel, const float* __restrict__ rcol_part,
                                int colparts_per_panel) {
+    pdl_wait();
     __shared__ float sl[8][33], sr[8][33];
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int i = r0 + blockIdx.x * 32 + c;
@@ -779,6 +798,8 @@ __global__ void __launch_bounds__(256) ss_rows_kernel(const float* __restrict__ 
 
 // out[slot] = scale * sum_i in[i]      (single block, fixed order)
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sh[32];
     float a = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) a += in[i];
@@ -802,6 +823,8 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) best_partial_kernel(const unsigned long long* __restrict__ best, int n, float offset,
                                                             float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sh[32];
     float a = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) a += offset - best_val(best[i]);
@@ -821,6 +844,8 @@ __global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long l
                                                            int* __restrict__ row_arg,
                                                            const unsigned long long* __restrict__ colbest, int r0, int r1,
                                                            int* __restrict__ col_arg) {
+    pdl_wait();
+    pdl_trigger();
     // ry_sum == nullptr (single GPU): the column sum is taken here as well, over colbest[r0, r1) == all N columns
     __shared__ float sh[32], shb[32];
     float a = 0.f, b = 0.f;
@@ -855,6 +880,7 @@ __global__ void __launch_bounds__(1024) remd_finish_kernel(const unsigned long l
 //   branch X (R_X >= R_Y): g[argmin_i][:] += -(1/M) x^_i for every target row i whose match is owned here:
 //            a scatter with atomics into a zeroed buffer; both kernels below return at once in branch Y.
 __global__ void cond_zero_kernel(float* __restrict__ g, long long n, const float* __restrict__ scalars, int slot_branch) {
+    pdl_wait();
     if (scalars[slot_branch] == 0.f) return;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     float4* g4 = reinterpret_cast<float4*>(g);
@@ -869,6 +895,7 @@ __global__ void __launch_bounds__(256) remd_backward_kernel(const unsigned long 
                                                             const float* __restrict__ inv_s, int D,
                                                             const float* __restrict__ scalars, int slot_branch,
                                                             float* __restrict__ g, long long ldg) {
+    pdl_wait();
     if (scalars[slot_branch] == 0.f) return;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -894,6 +921,7 @@ __constant__ float c_rgb2yuv[9] = {0.299f, -0.14714119f, 0.61497538f,
 // in 13 instructions per pair.
 __global__ void pal_prep_kernel(const float* __restrict__ x, long long ld, int n, int convert, float* __restrict__ rec,
                                 float* __restrict__ srec) {
+    pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const float* xr = x + static_cast<long long>(r) * ld;
@@ -932,6 +960,8 @@ constexpr int kPalKeyTile = 256;
 __global__ void __launch_bounds__(kPalThreads) pal_min_kernel(const float* __restrict__ qrec, int nq, const float* __restrict__ krec, int nk,
                                                               int kchunk, int mode, int kidx_base,
                                                               unsigned long long* __restrict__ best) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float4 sk[kPalKeyTile * 2];
     float a[kPalQT][8];
     float bv[kPalQT];
@@ -986,6 +1016,8 @@ __global__ void __launch_bounds__(kPalThreads) pal_min2_kernel(const float* __re
                                                                int kchunk, int kidx_base,
                                                                unsigned long long* __restrict__ qbest,
                                                                unsigned long long* __restrict__ kbest) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float4 sk[kPalKeyTile * 2];
     float a[kPalQT][7];
     float one[kPalQT];
@@ -1051,6 +1083,7 @@ __global__ void pal_backward_kernel(const unsigned long long* __restrict__ rowbe
                                     const unsigned long long* __restrict__ colbest, int N, int r0, int r1,
                                     const float* __restrict__ arec, const float* __restrict__ brec, int mode, int convert,
                                     const float* __restrict__ scalars, int slot_branch, float* __restrict__ gpal) {
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool bx = scalars[slot_branch] != 0.f;
     int i, j; float wgt;
@@ -1188,6 +1221,8 @@ __global__ void __launch_bounds__(256) sampler_bwd_kernel(const SamplerMaps m, c
 __global__ void __launch_bounds__(1024) moment_finish_kernel(const float* __restrict__ mu_y, const float* __restrict__ mu_x, int D,
                                                              const float* __restrict__ part, int npart,
                                                              float* __restrict__ gmu, float* __restrict__ scalars) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sh[2][32];
     float a = 0.f, b = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -1212,6 +1247,8 @@ __global__ void __launch_bounds__(1024) moment_finish_kernel(const float* __rest
 // loss_s = l_m + l_remd + inv_alpha*l_pal ; total = (alpha*loss_c + loss_s)/denom   (run_strotss.py:40,140)
 __global__ void combine_scalars_kernel(float* __restrict__ s, float alpha, float inv_alpha, float denom,
                                        const float* __restrict__ ss_loss_sum, float inv_n) {
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (ss_loss_sum) s[S_LOSS_C] = *ss_loss_sum * inv_n;
         const float ls = s[S_LM] + s[S_LREMD] + inv_alpha * s[S_LPAL];
@@ -1249,6 +1286,7 @@ constexpr int kFinU = 9;                    // 9 x 256 = 2304 >= 2179: one batch
 // elements of the row in registers across the block reduction and fetches the moment-matching row Q together with the other
 // operands, so a block pays one global-memory latency instead of two.
 __global__ void __launch_bounds__(256) finalize_grad_1b_kernel(const FinalizeArgs a) {
+    pdl_wait();
     __shared__ float sh[8];
     __shared__ float sh2[8];
     __shared__ float s_dot;
@@ -1321,6 +1359,7 @@ __global__ void __launch_bounds__(256) finalize_grad_1b_kernel(const FinalizeArg
 }
 
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinalizeArgs a) {
+    pdl_wait();
     extern __shared__ float sg[];       // D floats: g^
     __shared__ float sh[8];
     __shared__ float sh2[8];

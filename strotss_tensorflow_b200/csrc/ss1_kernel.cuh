@@ -123,6 +123,8 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                      // persistent single-wave grid: dependents may be scheduled as CTAs exit
+    pdl_wait();                         // the previous kernel of the stream has completed; its writes are visible
     const int num_tiles = ss1_num_tiles(p);
     const int ksplit = (p.kblocks > p.tail_blocks) ? p.kblocks - p.tail_blocks : 0;      // MERGED only
     (void)ksplit;
@@ -317,7 +319,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
                 tmem_ld32(lane_addr + dreg * BN + cc * 32, a0);
                 tmem_ld_wait();
                 const int colbase = col0 + cc * 32;
-                const bool pwrite = P.write_p && rvalid && colbase < P.ldp;
+                const bool pwrite = P.write_p && rvalid && colbase - P.p_col0 < P.ldp;
                 // 8 columns at a time: the bf16 P values leave as one 16-byte store, and sign_col * Xd
                 // overwrites the accumulator registers it was computed from (a0[e] is dead by then)
 #pragma unroll
@@ -347,7 +349,7 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
                         packed[e2 >> 1] = pack_bf16x2(pv[0], pv[1]);
                     }
                     if (pwrite)
-                        *reinterpret_cast<uint4*>(prow + colbase + e8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        *reinterpret_cast<uint4*>(prow + (colbase - P.p_col0) + e8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 }
                 if (both) {
                     // transpose-reduce: lane l ends with the sum over the warp's 32 rows of column l

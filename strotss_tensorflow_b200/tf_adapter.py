@@ -91,10 +91,13 @@ class _DLManagedTensor(C.Structure):
     pass
 
 
-_DELETER = C.CFUNCTYPE(None, C.POINTER(_DLManagedTensor))
+_DELETER = C.CFUNCTYPE(None, C.c_void_p)
 _DLManagedTensor._fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", C.c_void_p), ("deleter", _DELETER)]
 _KDL_CUDA, _KDL_FLOAT = 2, 2
-_live = {}                                # address of a DLManagedTensor -> everything that must outlive the capsule
+# address of a DLManagedTensor -> everything that must outlive the capsule.  The table and the deleter thunk below are
+# referenced by raw pointers inside tensors that TensorFlow may free at any later time, so they must survive a reload of
+# this module (importlib.reload re-executes it in the same namespace): they are created once per process.
+_live = globals().get("_live", {})
 
 C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
 C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
@@ -110,12 +113,13 @@ def _dev_ptr(t):
     return C.c_void_p((dl.data or 0) + dl.byte_offset), cap
 
 
-@_DELETER
-def _free_output(managed_ptr):
-    rec = _live.pop(C.addressof(managed_ptr.contents), None)
+def _free_output_impl(managed_addr, _table=_live):
+    rec = _table.pop(managed_addr, None)
     if rec is not None:
-        lib, handle, data = rec[0], rec[1], rec[2]
-        lib.strotss_device_free(handle, data)
+        rec[0].strotss_device_free(None, rec[2])      # the handle may be gone already: the library ignores it here
+
+
+_free_output = globals().get("_free_output") or _DELETER(_free_output_impl)
 
 
 class _Output:

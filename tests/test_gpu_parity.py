@@ -668,7 +668,8 @@ print('REL', abs(sc[0].item() - ref) / ref, abs(np.linalg.norm(g) - np.linalg.no
                                  {"STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_PANEL": "1024"},
                                  {"STROTSS_SS1_MERGED": "0", "STROTSS_REMD_SKEW": "-1"}, {"STROTSS_SS1_TAIL": "0", "STROTSS_REMD_SKEW": "0"},
                                  {"STROTSS_SS1_TAIL": "40", "STROTSS_REMD_SKEW": "40"}, {"STROTSS_PREP_V2": "1"},
-                                 {"STROTSS_PREP_V2": "1", "STROTSS_V_FP32": "1", "STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_NO_TRAP": "1"}])
+                                 {"STROTSS_PREP_V2": "1", "STROTSS_V_FP32": "1", "STROTSS_WIDE": "0"}, {"STROTSS_WIDE": "0", "STROTSS_NO_TRAP": "1"}, {"STROTSS_PDL": "1"},
+                                 {"STROTSS_PDL": "1", "STROTSS_BRANCHES": "0", "STROTSS_PREP_V2": "1"}])
 def test_alternative_kernel_paths(cuda_device, env):
     """The single-CTA GEMM kernels (STROTSS_NO_PAIR), the generic stage-1 epilogue (STROTSS_SS1_GENERIC), the
     single-stream launch order (STROTSS_BRANCHES=0), the two-pass palette search and the two-stream stage-1/stage-2

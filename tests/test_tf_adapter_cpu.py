@@ -72,6 +72,10 @@ def test_output_buffers_enter_through_dlpack_and_are_returned(tfa, monkeypatch):
     del t
     gc.collect()
     assert freed == [C.addressof(lib.buf)] and len(tfa._live) == 0
+    # the deleter thunk and its table survive a reload of the module (tensors created before the reload still point at them)
+    thunk, table = tfa._free_output, tfa._live
+    mod = importlib.reload(tfa)
+    assert mod._free_output is thunk and mod._live is table
 
 
 def test_device_parsing_and_distance_keyerror(tfa):
