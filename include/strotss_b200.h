@@ -227,6 +227,10 @@ int strotss_debug_gemm_ta(strotss_handle h, const float* At, int m, const float*
  * reference interface. */
 int strotss_debug_tile_walk(int walk, int tiles_m, int tiles_n, int group_n, int* tm_out, int* tn_out, int capacity);
 int strotss_debug_couples_pay(int num_sms, int tiles_m128, int tiles_n256, int kblocks, int skew);
+/* Work split of the row-sharded symmetric self-similarity (csrc/ss_jobs.h): returns 1 and the rank's jobs
+ * (r0, r1, c0, c1, diag, kind each; at most 8), the row ranges of mirrored stage-2 products it sends / receives
+ * (peer, r0, r1 each; at most 8) and the three counts -- or 0 if (N, world, panel) falls back to rectangular sharding. */
+int strotss_debug_ss_jobs(int N, int world, int rank, int panel, int* jobs6, int* sends3, int* recvs3, int* counts3);
 
 #ifdef __cplusplus
 }

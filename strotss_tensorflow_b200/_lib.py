@@ -57,6 +57,7 @@ SIGNATURES = {
     "strotss_debug_gemm_ta": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _i, _vp]),
     "strotss_debug_tile_walk": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i]),
     "strotss_debug_couples_pay": (_i, [_i, _i, _i, _i, _i]),
+    "strotss_debug_ss_jobs": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
 }
 
 _lib = None

@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "gemm2_core.cuh"
 #include "ss1_kernel.cuh"
+#include "ss_jobs.h"
 #include "pixel_kernels.cuh"
 #include <cstdlib>
 
@@ -744,6 +745,10 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
     std::string why;
@@ -763,7 +768,12 @@ NcclApi& nccl() {
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(lib, "ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(lib, "ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(lib, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString && api.Send && api.Recv &&
+             api.GroupStart && api.GroupEnd;
     if (!api.ok) api.why = "libnccl is missing a required symbol";
     return api;
 }
@@ -1358,6 +1368,184 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
     return 0;
 }
 
+// Row-sharded evaluation with the symmetry of the self-similarity matrices kept (see ss_jobs.h): a rank computes its share of
+// the upper block triangle -- 1.52 / g units of stage-1 work instead of the 3.0 / g of rectangular row sharding -- as a few
+// rectangular jobs, every tile standing for its mirror image too.  What the mirror images contribute to rows of OTHER ranks
+// leaves through two extra exchanges per evaluation:
+//   * r (N floats, one allreduce-sum): r_j collects sign * Xd over row AND column j, from every rank that computed a tile there;
+//   * the stage-2 products ss2[J] += P[I,J]^T x^[I] of the mirrored tiles (point-to-point ncclSend / ncclRecv inside one group:
+//     each rank sends / receives (g - 1) / 2 blocks of N / g rows, 64 MB at N = 16384 on 8 GPUs).
+// Same outputs as self_sim_local.  Returns 1 if the shape cannot use the scheme (the caller then runs self_sim_local).
+int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh, int D, int Dp, float* loss_partial,
+                         float* v_partial, SsOut& out, cudaStream_t st) {
+    static const bool off = getenv("STROTSS_SHARD_SYM") && atoi(getenv("STROTSS_SHARD_SYM")) == 0;
+    static const bool merged_off = getenv("STROTSS_SS1_MERGED") && atoi(getenv("STROTSS_SS1_MERGED")) == 0;
+    static const bool generic_env = (getenv("STROTSS_SS1_GENERIC") != nullptr);
+    static const int small_max = getenv("STROTSS_SS1_SMALL_MAX") ? atoi(getenv("STROTSS_SS1_SMALL_MAX")) : 2048;
+    static const int panel_rows = getenv("STROTSS_PANEL") ? atoi(getenv("STROTSS_PANEL")) : 4096;
+    if (off || merged_off || generic_env || !pair_enabled() || !x.u || N <= small_max) return 1;
+    SsPlan pl;
+    if (!ss_make_plan(N, h->world, h->rank, round_up(panel_rows < 256 ? 256 : panel_rows, 256), pl)) return 1;
+    if (pl.job[0].r0 != sh.r0 || sh.n() != N / h->world) return 1;
+    const bool amn = (x.xhT == nullptr);
+    const int np = x.np;
+    float *u = x.u, *w = x.w, *sclamp = x.sclamp, *loss_part, *r_part, *rcol_part, *rowloss, *r_full, *ss2full, *recvbuf;
+    const int tiles_n_all = N / kSs1BN;
+    RET(ensure(h, "ss.loss_part", (size_t)tiles_n_all * 2 * N, &loss_part));
+    RET(ensure(h, "ss.r_part", (size_t)tiles_n_all * 2 * N, &r_part));
+    RET(ensure(h, "ss.rcol_part", (size_t)(N / BM) * 4 * N, &rcol_part));
+    RET(ensure(h, "ss.rowloss", (size_t)N, &rowloss));
+    RET(ensure(h, "ss.r_full", (size_t)N, &r_full));
+    RET(ensure(h, "ss.coef", (size_t)N, &out.coef));
+    RET(ensure(h, "ss.ss2", (size_t)sh.n() * Dp, &out.ss2));
+    RET(ensure(h, "ss.ss2full", (size_t)N * Dp, &ss2full));
+    out.ld = Dp;
+    size_t pmax = 0, recv_rows = 0;
+    for (int k = 0; k < pl.njobs; ++k) {
+        const size_t e = (size_t)(pl.job[k].r1 - pl.job[k].r0) * (pl.job[k].c1 - pl.job[k].c0);
+        if (e > pmax) pmax = e;
+    }
+    for (int k = 0; k < pl.nrecv; ++k) recv_rows += pl.recv_r1[k] - pl.recv_r0[k];
+    bf16* P;
+    RET(ensure(h, "ss.P", pmax, &P));
+    RET(ensure(h, "ss.recv", recv_rows * Dp, &recvbuf));
+    static PerDeviceOnce configured;
+    if (configured.needed(h->device)) {
+        CK(cudaFuncSetAttribute(ss1_pair_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1MergedSmemBytes));
+        configured.done(h->device);
+    }
+    static const int tail_blocks = getenv("STROTSS_SS1_TAIL") ? atoi(getenv("STROTSS_SS1_TAIL")) : 4;
+    const int max_pairs = h->num_sms / 2;
+    // first product written into a row range of ss2full stores, later ones accumulate; the ranges of the three job kinds are
+    // disjoint and every kind sweeps its range panel after panel
+    bool fresh_main = true, fresh_wrap = true, fresh_half = true;
+    bool own_rows_in_full = false;
+    int full_row0 = sh.n();
+    for (int k = 0; k < pl.njobs; ++k) {
+        const SsJob jb = pl.job[k];
+        const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
+        {   // ---- stage 1: P[rows][cw] (bf16), loss / r partials
+            Ss1Params sp{};
+            RET(make_tmap(h, &sp.tmA[0], y.xh, N, Dp, Dp, BM)); RET(make_tmap(h, &sp.tmB[0], y.xh, N, Dp, Dp, 128));      // y^ . y^T
+            RET(make_tmap(h, &sp.tmA[1], x.dlt, N, Dp, Dp, BM)); RET(make_tmap(h, &sp.tmB[1], x.xh, N, Dp, Dp, 128));     // delta . x^T
+            RET(make_tmap(h, &sp.tmA[2], y.xh, N, Dp, Dp, BM)); RET(make_tmap(h, &sp.tmB[2], x.dlt, N, Dp, Dp, 128));     // y^ . delta^T
+            sp.kblocks = Dp / BK; sp.k_tail_steps = tail_steps(D);
+            sp.tiles_m = rows / 256; sp.tiles_n = cw / kSs1BN; sp.a_row0 = jb.r0; sp.b_row0 = jb.c0;
+            sp.trap = jb.diag; sp.tail_blocks = tail_blocks < 0 ? 0 : tail_blocks;
+            sp.epi.u = u; sp.epi.w = w; sp.epi.P = P; sp.epi.ldp = cw; sp.epi.panel_row0 = jb.r0; sp.epi.p_col0 = jb.c0;
+            sp.epi.loss_part = loss_part; sp.epi.r_part = r_part; sp.epi.N = N; sp.epi.row_end = jb.r1; sp.epi.write_p = 1;
+            sp.epi.sym = 1; sp.epi.panel_end = 0;              // rectangular job: every tile is mirrored (col0 >= 0)
+            sp.epi.rcol_part = rcol_part;
+            long long gn = (32ll << 20) / (3ll * sp.kblocks * BK * 2 * kSs1BN);
+            if (gn < 4) gn = 4;
+            if (gn > sp.tiles_n) gn = sp.tiles_n;
+            sp.group_n = static_cast<int>(gn);
+            const int tiles = ss1_num_tiles(sp);
+            PhaseTimer _pt(h, PH_SS1, st);
+            KL(ss1_pair_merged_kernel, 2 * (tiles < max_pairs ? tiles : max_pairs), kSs1Threads, kSs1MergedSmemBytes, st, sp);
+            CKL();
+        }
+        PhaseTimer _pt(h, PH_SS2, st);
+        {   // ---- stage 2a: ss2[job rows] (+)= P . x^[job columns]  (+ for a trapezoid the transposed part left of the diagonal)
+            GemmParams<EpiStoreTr<256>> q{};
+            if (amn) RET(make_tmap_mn(h, &q.tmA[0], x.xh + static_cast<long long>(jb.c0) * Dp, D, cw, Dp));
+            else RET(make_tmap(h, &q.tmA[0], x.xhT + jb.c0, D, cw, np, BM));
+            RET(make_tmap(h, &q.tmB[0], P, rows, cw, cw, 128));
+            q.nseg = 1; q.seg_kblocks[0] = cw / BK; q.seg_acc[0] = 0;
+            q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (rows + 255) / 256;
+            q.epi.C = out.ss2 + static_cast<long long>(jb.r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = rows;
+            q.epi.alpha = 1.f; q.epi.col_off = 0; q.epi.accumulate = jb.diag ? 0 : 1;      // a panel's trapezoid job comes first
+            if (jb.diag) {
+                q.kb_lo_mul[0] = 256 / BK;
+                if (amn) RET(make_tmap_mn(h, &q.tmA[1], x.xh + static_cast<long long>(jb.r0) * Dp, D, rows, Dp));
+                else RET(make_tmap(h, &q.tmA[1], x.xhT + jb.r0, D, rows, np, BM));
+                RET(make_tmap_mn(h, &q.tmB[1], P, rows, rows, cw));
+                q.nseg = 2; q.seg_kblocks[1] = (rows + BK - 1) / BK; q.seg_acc[1] = 0;
+                q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
+                if (wide_enabled()) {
+                    q.tiles_n = (rows + 511) / 512;
+                    if (amn) RET((launch_gemm256w<2, 1>(h, q, st))); else RET((launch_gemm256w<2>(h, q, st)));
+                } else {
+                    if (amn) RET((launch_gemm256<1, 8, 2, 1>(h, q, st))); else RET((launch_gemm256<1, 8, 2>(h, q, st)));
+                }
+            } else if (wide_enabled()) {
+                q.tiles_n = (rows + 511) / 512;
+                if (amn) RET((launch_gemm256w<0, 1>(h, q, st))); else RET((launch_gemm256w<0>(h, q, st)));
+            } else {
+                if (amn) RET((launch_gemm256<1, 8, 0, 1>(h, q, st))); else RET((launch_gemm256<1, 8>(h, q, st)));
+            }
+        }
+        // ---- stage 2b: ss2full[J] (+)= P[job rows][J]^T . x^[job rows] for the mirrored columns J
+        const int m0 = jb.diag ? jb.r1 : jb.c0, mext = jb.c1 - m0;
+        if (mext > 0) {
+            GemmParams<EpiStoreTr<256>> t{};
+            if (amn) RET(make_tmap_mn(h, &t.tmA[0], x.xh + static_cast<long long>(jb.r0) * Dp, D, rows, Dp));
+            else RET(make_tmap(h, &t.tmA[0], x.xhT + jb.r0, D, rows, np, BM));
+            RET(make_tmap_mn(h, &t.tmB[0], P + (m0 - jb.c0), mext, rows, cw));
+            t.nseg = 1; t.seg_kblocks[0] = (rows + BK - 1) / BK; t.seg_acc[0] = 0;
+            t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
+            t.epi.C = ss2full + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = mext;
+            t.epi.alpha = 1.f; t.epi.col_off = 0;
+            if (wide_enabled()) t.tiles_n = (mext + 511) / 512;
+            // which range this job writes, and whether an earlier job already stored there
+            bool* fr = jb.kind == 0 ? &fresh_main : (jb.kind == 1 ? &fresh_wrap : &fresh_half);
+            t.epi.accumulate = *fr ? 0 : 1;
+            *fr = false;
+            if (wide_enabled()) { if (amn) RET((launch_gemm256w<1, 1>(h, t, st))); else RET((launch_gemm256w<1>(h, t, st))); }
+            else { if (amn) RET((launch_gemm256<1, 8, 1, 1>(h, t, st))); else RET((launch_gemm256<1, 8, 1>(h, t, st))); }
+            if (jb.diag && m0 < sh.r1) { own_rows_in_full = true; if (m0 - sh.r0 < full_row0) full_row0 = m0 - sh.r0; }
+        }
+    }
+    {   // ---- r, row losses, coefficients
+        PhaseTimer _pm(h, PH_SS_MISC, st);
+        SsJobList jl{};
+        jl.n = pl.njobs;
+        for (int k = 0; k < pl.njobs; ++k) { jl.r0[k] = pl.job[k].r0; jl.r1[k] = pl.job[k].r1; jl.c0[k] = pl.job[k].c0; jl.c1[k] = pl.job[k].c1; jl.diag[k] = pl.job[k].diag; }
+        KL(ss_rows_jobs_kernel, (N + 31) / 32, 256, 0, st, jl, loss_part, r_part, rcol_part, N, 2, rowloss, r_full);
+        CKL();
+        KL(reduce_sum_kernel, 1, 1024, 0, st, rowloss + sh.r0, sh.n(), 1.f, loss_partial);
+        CKL();
+    }
+    {   // ---- exchange: r summed over ranks; mirrored stage-2 products to the ranks that own their rows
+        PhaseTimer _pe(h, PH_EXCHANGE, st);
+        NCK(nccl().AllReduce(r_full, r_full, (size_t)N, kNcclFloat32, kNcclSum, h->nccl_comm, st));
+        NCK(nccl().GroupStart());
+        size_t roff = 0;
+        for (int k = 0; k < pl.nsend; ++k)
+            NCK(nccl().Send(ss2full + static_cast<long long>(pl.send_r0[k]) * Dp, (size_t)(pl.send_r1[k] - pl.send_r0[k]) * Dp, kNcclFloat32,
+                            pl.send_peer[k], h->nccl_comm, st));
+        for (int k = 0; k < pl.nrecv; ++k) {
+            NCK(nccl().Recv(recvbuf + roff * Dp, (size_t)(pl.recv_r1[k] - pl.recv_r0[k]) * Dp, kNcclFloat32, pl.recv_peer[k], h->nccl_comm, st));
+            roff += pl.recv_r1[k] - pl.recv_r0[k];
+        }
+        NCK(nccl().GroupEnd());
+    }
+    PhaseTimer _pm(h, PH_SS_MISC, st);
+    {
+        Ss2AddArgs a{};
+        a.ss2 = out.ss2; a.full = own_rows_in_full ? ss2full + static_cast<long long>(sh.r0) * Dp : nullptr; a.full_row0 = full_row0;
+        a.row_floats = Dp; a.rows = sh.n(); a.nrecv = pl.nrecv;
+        size_t roff = 0;
+        for (int k = 0; k < pl.nrecv; ++k) {
+            a.recv[k] = recvbuf + roff * Dp; a.off[k] = pl.recv_r0[k] - sh.r0; a.cnt[k] = pl.recv_r1[k] - pl.recv_r0[k];
+            roff += a.cnt[k];
+        }
+        KL(ss2_add_kernel, 4 * h->num_sms, 256, 0, st, a);
+        CKL();
+    }
+    KL(ss_coef_kernel, (sh.n() + 255) / 256, 256, 0, st, r_full, u, sclamp, N, sh.r0, sh.r1, out.coef);
+    CKL();
+    const int rpb = rows_per_block(h, sh.n(), kRowsPerBlock, 4);
+    const int nblk = (sh.n() + rpb - 1) / rpb;
+    float* vpart;
+    RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
+    KL(weighted_colsum_bf16_kernel, nblk, 256, 0, st, x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
+    CKL();
+    KL(colsum_finish_kernel, (D + 31) / 32, 256, 0, st, vpart, nblk, D, 1.f, v_partial);
+    CKL();
+    return 0;
+}
+
 int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) {
     if (nrows <= 0) return 0;
     PhaseTimer _pt(h, PH_FINALIZE, st);
@@ -1637,8 +1825,14 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     if (par) CK(cudaEventRecord(h->ev_join2, s_aux));
     RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_mom, mom_part));
     if (par) CK(cudaEventRecord(h->ev_join3, s_mom));
-    if (with_content)
-        RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
+    if (with_content) {
+        int rc = 1;
+        if (exch && want_grad) {
+            rc = self_sim_sharded_sym(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, so, st);
+            if (rc < 0) return rc;
+        }
+        if (rc == 1) RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
+    }
     if (par) {
         CK(cudaStreamWaitEvent(st, h->ev_join, 0));
         CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
@@ -2289,6 +2483,21 @@ int strotss_debug_tile_walk(int walk, int tiles_m, int tiles_n, int group_n, int
 // 1 if couples need less time on num_sms / 2 CTA pairs.  tiles_m128 counts 128-row blocks, tiles_n256 256-column tiles.
 int strotss_debug_couples_pay(int num_sms, int tiles_m128, int tiles_n256, int kblocks, int skew) {
     return couples_pay_rule(num_sms, tiles_m128, tiles_n256, kblocks, skew) ? 1 : 0;
+}
+
+int strotss_debug_ss_jobs(int N, int world, int rank, int panel, int* jobs6, int* sends3, int* recvs3, int* counts3) {
+    if (!jobs6 || !sends3 || !recvs3 || !counts3) return STROTSS_ERR_ARG;
+    SsPlan pl;
+    if (!ss_make_plan(N, world, rank, panel, pl)) return 0;
+    for (int k = 0; k < pl.njobs; ++k) {
+        const SsJob& j = pl.job[k];
+        const int v[6] = {j.r0, j.r1, j.c0, j.c1, j.diag, j.kind};
+        for (int e = 0; e < 6; ++e) jobs6[6 * k + e] = v[e];
+    }
+    for (int k = 0; k < pl.nsend; ++k) { sends3[3 * k] = pl.send_peer[k]; sends3[3 * k + 1] = pl.send_r0[k]; sends3[3 * k + 2] = pl.send_r1[k]; }
+    for (int k = 0; k < pl.nrecv; ++k) { recvs3[3 * k] = pl.recv_peer[k]; recvs3[3 * k + 1] = pl.recv_r0[k]; recvs3[3 * k + 2] = pl.recv_r1[k]; }
+    counts3[0] = pl.njobs; counts3[1] = pl.nsend; counts3[2] = pl.nrecv;
+    return 1;
 }
 
 }  // extern "C"

@@ -796,6 +796,102 @@ __global__ void __launch_bounds__(256) ss_rows_kernel(const float* __restrict__ 
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Row-sharded symmetric self-similarity: a rank computes a list of rectangular "jobs" (own rows x a column range) of the
+// symmetric matrix, every tile accounting for its mirror image as well (see self_sim_sharded_sym in api.cu).  After stage 1
+//   rowloss[i]  = sum of the loss partials of row i over the column tiles of the jobs that contain row i
+//   r_full[j]   = row-form partials (j an own row) + column-form partials (j a column of a job whose tiles were mirrored)
+// r_full is then summed over ranks: every r_j has contributions on exactly the ranks that computed a tile of column/row j.
+// The enumeration order is fixed (8 interleaved groups, then a fixed tree): deterministic.
+// --------------------------------------------------------------------------------------
+constexpr int kMaxSsJobs = 8;
+struct SsJobList {
+    int n;
+    int r0[kMaxSsJobs], r1[kMaxSsJobs], c0[kMaxSsJobs], c1[kMaxSsJobs], diag[kMaxSsJobs];
+};
+
+__global__ void __launch_bounds__(256) ss_rows_jobs_kernel(const SsJobList jobs, const float* __restrict__ loss_part,
+                                                           const float* __restrict__ r_part, const float* __restrict__ rcol_part,
+                                                           int N, int slots_per_tile, float* __restrict__ rowloss,
+                                                           float* __restrict__ r_full) {
+    pdl_wait();
+    __shared__ float sl[8][33], sr[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + c;
+    float l = 0.f, r = 0.f;
+    if (i < N) {
+        int e = 0;                                     // running entry index: entry e is summed by group e % 8
+        for (int k = 0; k < jobs.n; ++k) {
+            if (i >= jobs.r0[k] && i < jobs.r1[k]) {   // row-form partials: one slot per (column tile, column half)
+                const int t0 = (jobs.diag[k] ? i / 256 : jobs.c0[k] / 256) * slots_per_tile;
+                const int t1 = (jobs.c1[k] / 256) * slots_per_tile;
+                for (int t = t0; t < t1; ++t, ++e)
+                    if ((e & 7) == g) {
+                        l += loss_part[static_cast<long long>(t) * N + i];
+                        r += r_part[static_cast<long long>(t) * N + i];
+                    }
+            }
+            if (i >= jobs.c0[k] && i < jobs.c1[k]) {   // column-form partials: one per (128-row block, epilogue warp quadrant)
+                const int b0 = (jobs.r0[k] / 128) * 4;
+                // trapezoid job: only the row tiles above the column's own diagonal tile wrote a column-form partial
+                const int b1 = (jobs.diag[k] ? min((i / 256) * 2, jobs.r1[k] / 128) : jobs.r1[k] / 128) * 4;
+                for (int b = b0; b < b1; ++b, ++e)
+                    if ((e & 7) == g) r += rcol_part[static_cast<long long>(b) * N + i];
+            }
+        }
+    }
+    sl[g][c] = l; sr[g][c] = r;
+    __syncthreads();
+    if (g == 0 && i < N) {
+        float lt = 0.f, rt = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { lt += sl[k][c]; rt += sr[k][c]; }
+        rowloss[i] = lt;
+        r_full[i] = rt;
+    }
+}
+
+// coef_i = (r_i / N) u_i^2 [s_i >= clamp] for the rows [r0, r1) of this rank, r already summed over ranks
+__global__ void ss_coef_kernel(const float* __restrict__ r_full, const float* __restrict__ u, const float* __restrict__ sclamp, int N,
+                               int r0, int r1, float* __restrict__ coef) {
+    pdl_wait();
+    const int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r1) { const float ui = u[i]; coef[i] = (r_full[i] / static_cast<float>(N)) * ui * ui * sclamp[i]; }
+}
+
+// Row-sharded symmetric self-similarity, after the exchange of the mirrored stage-2 products:
+//   ss2[i][:] += full[i][:] (this rank's own products that landed in its own rows, if any) + sum_r recv_r[i - off_r][:]
+constexpr int kMaxSsRecv = 8;
+struct Ss2AddArgs {
+    float* ss2; const float* full;            // both start at the rank's first row; full may be null
+    int full_row0;                            // first row (relative to the rank's first row) that `full` holds products for
+    long long row_floats;                     // floats per row (Dp)
+    int rows;
+    int nrecv;
+    const float* recv[kMaxSsRecv]; int off[kMaxSsRecv], cnt[kMaxSsRecv];
+};
+__global__ void __launch_bounds__(256) ss2_add_kernel(const Ss2AddArgs a) {
+    pdl_wait();
+    const long long per_row4 = a.row_floats / 4;
+    const long long total4 = per_row4 * a.rows;
+    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total4;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(t / per_row4);
+        float4 v = reinterpret_cast<const float4*>(a.ss2)[t];
+        if (a.full && i >= a.full_row0) {
+            const float4 f = reinterpret_cast<const float4*>(a.full)[t];
+            v.x += f.x; v.y += f.y; v.z += f.z; v.w += f.w;
+        }
+        for (int r = 0; r < a.nrecv; ++r) {
+            if (i >= a.off[r] && i < a.off[r] + a.cnt[r]) {
+                const float4 f = reinterpret_cast<const float4*>(a.recv[r])[t - per_row4 * a.off[r]];
+                v.x += f.x; v.y += f.y; v.z += f.z; v.w += f.w;
+            }
+        }
+        reinterpret_cast<float4*>(a.ss2)[t] = v;
+    }
+}
+
 // out[slot] = scale * sum_i in[i]      (single block, fixed order)
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out) {
     pdl_wait();
