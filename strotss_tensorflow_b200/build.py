@@ -14,7 +14,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libstrotss_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "gemm_core.cuh", "gemm2_core.cuh", "kernels.cuh", "ss1_kernel.cuh", "pixel_kernels.cuh", os.path.join("..", "..", "include", "strotss_b200.h")]
+HEADERS = ["common.cuh", "gemm_core.cuh", "gemm2_core.cuh", "kernels.cuh", "ss1_kernel.cuh", "ss_jobs.h", "pixel_kernels.cuh", os.path.join("..", "..", "include", "strotss_b200.h")]
 
 
 def _nvcc() -> str:

@@ -34,6 +34,9 @@ struct SsPlan {
     int nsend, nrecv;
     int send_peer[kSsJobsMax], send_r0[kSsJobsMax], send_r1[kSsJobsMax];
     int recv_peer[kSsJobsMax], recv_r0[kSsJobsMax], recv_r1[kSsJobsMax];
+    // rows of the SENDER whose tiles stand behind an entry: the P block of an entry is (src rows) x (r0..r1 of the receiver)
+    int send_src_r0[kSsJobsMax], send_src_r1[kSsJobsMax];
+    int recv_src_r0[kSsJobsMax], recv_src_r1[kSsJobsMax];
 };
 
 // false: this (N, world, panel) cannot use the scheme (ragged blocks, too many jobs) -- the caller falls back to rectangular
@@ -68,6 +71,8 @@ inline bool ss_make_plan(int N, int world, int rank, int panel, SsPlan& pl) {
     }
     for (int d = 1; d <= h; ++d) {
         const int to = (rank + d) % world, from = (rank - d + world) % world;
+        pl.send_src_r0[pl.nsend] = a; pl.send_src_r1[pl.nsend] = b;
+        pl.recv_src_r0[pl.nrecv] = from * per; pl.recv_src_r1[pl.nrecv] = (from + 1) * per;
         pl.send_peer[pl.nsend] = to; pl.send_r0[pl.nsend] = to * per; pl.send_r1[pl.nsend] = (to + 1) * per; ++pl.nsend;
         pl.recv_peer[pl.nrecv] = from; pl.recv_r0[pl.nrecv] = a; pl.recv_r1[pl.nrecv] = b; ++pl.nrecv;
     }
@@ -75,10 +80,24 @@ inline bool ss_make_plan(int N, int world, int rank, int panel, SsPlan& pl) {
         const int peer = (rank + world / 2) % world;
         const bool low = rank < world / 2;
         // low rank: computed (own rows) x (first half of the peer's rows) -> sends those rows' products, receives whole own block
+        pl.send_src_r0[pl.nsend] = low ? a : a + per / 2; pl.send_src_r1[pl.nsend] = b;
+        pl.recv_src_r0[pl.nrecv] = low ? peer * per + per / 2 : peer * per; pl.recv_src_r1[pl.nrecv] = (peer + 1) * per;
         pl.send_peer[pl.nsend] = peer; pl.send_r0[pl.nsend] = peer * per; pl.send_r1[pl.nsend] = peer * per + (low ? per / 2 : per); ++pl.nsend;
         pl.recv_peer[pl.nrecv] = peer; pl.recv_r0[pl.nrecv] = a; pl.recv_r1[pl.nrecv] = low ? b : a + per / 2; ++pl.nrecv;
     }
     return true;
+}
+
+// Element offset of the P block that `from` sends inside the receive buffer of the rank whose plan is `pl` (blocks are stored one
+// after another in the order of the receive list, each as [source rows][receiver rows]); -1 if `from` sends nothing there.
+inline long long ss_recv_offset(const SsPlan& pl, int from, long long* total = nullptr) {
+    long long off = 0, found = -1;
+    for (int k = 0; k < pl.nrecv; ++k) {
+        if (pl.recv_peer[k] == from && found < 0) found = off;
+        off += static_cast<long long>(pl.recv_src_r1[k] - pl.recv_src_r0[k]) * (pl.recv_r1[k] - pl.recv_r0[k]);
+    }
+    if (total) *total = off;
+    return found;
 }
 
 }  // namespace sb
