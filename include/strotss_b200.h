@@ -232,6 +232,12 @@ int strotss_debug_couples_pay(int num_sms, int tiles_m128, int tiles_n256, int k
  * (peer, r0, r1 each; at most 8) and the three counts -- or 0 if (N, world, panel) falls back to rectangular sharding. */
 int strotss_debug_ss_jobs(int N, int world, int rank, int panel, int* jobs6, int* sends3, int* recvs3, int* counts3);
 
+/* Sign-block copies of the same work split when the bf16 blocks of the mirrored tiles travel to the ranks that own their rows
+ * (CUDA-IPC peer windows, csrc/ss_jobs.h): returns the number of copies of `rank` (-1: the split falls back) and, per copy,
+ * (job, peer, element offset in the peer's window, row length there, i0, i1, j0, j1); *window_elems = bf16 elements of the
+ * rank's own window. */
+int strotss_debug_ss_copies(int N, int world, int rank, int panel, long long* copies8, int capacity, long long* window_elems);
+
 #ifdef __cplusplus
 }
 #endif

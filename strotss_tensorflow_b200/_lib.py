@@ -58,6 +58,7 @@ SIGNATURES = {
     "strotss_debug_tile_walk": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i]),
     "strotss_debug_couples_pay": (_i, [_i, _i, _i, _i, _i]),
     "strotss_debug_ss_jobs": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "strotss_debug_ss_copies": (_i, [_i, _i, _i, _i, C.POINTER(C.c_longlong), _i, C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

@@ -190,6 +190,12 @@ struct strotss_ctx {
     // multi-GPU row sharding (NCCL through dlopen; see strotss_comm_*)
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
+    // peer window of the row-sharded self-similarity: a receive buffer of this rank that every other rank maps through CUDA
+    // IPC, so that sign-matrix blocks travel by copy engine over NVLink (no SM, no NCCL kernel) underneath the GEMMs
+    void* win_local = nullptr; size_t win_bytes = 0;
+    std::vector<void*> win_remote;       // [world]; own entry = win_local
+    int win_state = 0;                   // 0 untried, 1 usable, -1 unavailable (IPC refused): fall back to the product exchange
+    cudaStream_t comm_st = nullptr;      // copies into peer windows
     // optional per-phase CUDA-event timing
     bool profiling = false;
     std::vector<PhaseRec> recs;
@@ -220,6 +226,10 @@ struct strotss_ctx {
         if (pipe_compute) cudaStreamDestroy(pipe_compute);
         if (pipe_d2h) cudaStreamDestroy(pipe_d2h);
         for (auto& kv : bufs) cudaFree(kv.second.first);
+        for (size_t i = 0; i < win_remote.size(); ++i)
+            if (win_remote[i] && win_remote[i] != win_local) cudaIpcCloseMemHandle(win_remote[i]);
+        if (win_local) cudaFree(win_local);
+        if (comm_st) cudaStreamDestroy(comm_st);
         if (h_scalars) cudaFreeHost(h_scalars);
         for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto& e : pool) cudaEventDestroy(e);
@@ -745,6 +755,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -753,7 +764,7 @@ struct NcclApi {
     bool ok = false;
     std::string why;
 };
-enum { kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclMax = 2 };
+enum { kNcclUint8 = 1, kNcclInt32 = 2, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };
 
 NcclApi& nccl() {
     static NcclApi api;
@@ -767,12 +778,13 @@ NcclApi& nccl() {
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
     api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(lib, "ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(lib, "ncclRecv"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(lib, "ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString && api.Send && api.Recv &&
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString && api.Send && api.Recv &&
              api.GroupStart && api.GroupEnd;
     if (!api.ok) api.why = "libnccl is missing a required symbol";
     return api;
@@ -791,6 +803,70 @@ Shard shard_of(const strotss_ctx* h, int N, bool sharded) {
     if (r0 > N) r0 = N;
     if (r1 > N) r1 = N;
     return Shard{r0, r1};
+}
+
+// ---- peer window: a receive buffer of every rank, mapped by all the others through CUDA IPC --------------------------
+// Collective over the communicator (every rank calls it with the same size at the same point of an evaluation).  Returns 0
+// with h->win_state = 1 when all ranks could map all windows, 0 with win_state = -1 when any rank could not (the caller then
+// keeps the NCCL exchange), < 0 on a hard error.  The handles travel through the communicator itself (ncclAllGather of the
+// 64-byte IPC handles); the agreement is an allreduce-min of a flag.
+// Re-allocation is safe without further synchronisation: a rank only gets here after its previous evaluation's last
+// collective, which every peer enters after its copies into this rank's window have completed (see self_sim_sharded_sym).
+int peer_window_ensure(strotss_ctx* h, size_t bytes, cudaStream_t st) {
+    static const bool off = getenv("STROTSS_PEER_WINDOW") && atoi(getenv("STROTSS_PEER_WINDOW")) == 0;
+    if (off || h->win_state < 0) { h->win_state = -1; return 0; }
+    if (h->win_state == 1 && h->win_bytes >= bytes) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        h->err = "row-sharded evaluation: the peer window cannot be created while the stream is being captured (run one evaluation first)";
+        return STROTSS_ERR_STATE;
+    }
+    CK(cudaDeviceSynchronize());
+    for (size_t i = 0; i < h->win_remote.size(); ++i)
+        if (h->win_remote[i] && h->win_remote[i] != h->win_local) cudaIpcCloseMemHandle(h->win_remote[i]);
+    h->win_remote.assign(h->world, nullptr);
+    if (h->win_local) { cudaFree(h->win_local); h->ws_bytes -= h->win_bytes; h->win_local = nullptr; h->win_bytes = 0; }
+    if (!h->comm_st) CK(cudaStreamCreateWithFlags(&h->comm_st, cudaStreamNonBlocking));
+    const size_t alloc = (bytes + (1u << 21) - 1) >> 21 << 21;
+    int good = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&h->win_local, alloc) != cudaSuccess) { cudaGetLastError(); h->win_local = nullptr; good = 0; }
+    if (good && cudaIpcGetMemHandle(&mine, h->win_local) != cudaSuccess) { cudaGetLastError(); good = 0; }
+    // exchange: [world] handles, then a flag
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    unsigned char* stage;
+    RET(ensure(h, "comm.ipc", (size_t)h->world * 64 + 16, &stage));
+    CK(cudaMemcpyAsync(stage + (size_t)h->rank * 64, &mine, 64, cudaMemcpyHostToDevice, st));
+    NCK(nccl().AllGather(stage + (size_t)h->rank * 64, stage, 64, kNcclUint8, h->nccl_comm, st));
+    std::vector<cudaIpcMemHandle_t> all(h->world);
+    CK(cudaMemcpyAsync(all.data(), stage, (size_t)h->world * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (good) {
+        for (int r = 0; r < h->world && good; ++r) {
+            if (r == h->rank) { h->win_remote[r] = h->win_local; continue; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+            h->win_remote[r] = p;
+        }
+    }
+    int* flag = reinterpret_cast<int*>(stage + (size_t)h->world * 64);
+    CK(cudaMemcpyAsync(flag, &good, sizeof(int), cudaMemcpyHostToDevice, st));
+    NCK(nccl().AllReduce(flag, flag, 1, kNcclInt32, kNcclMin, h->nccl_comm, st));
+    int all_good = 0;
+    CK(cudaMemcpyAsync(&all_good, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!all_good) {
+        for (size_t i = 0; i < h->win_remote.size(); ++i)
+            if (h->win_remote[i] && h->win_remote[i] != h->win_local) cudaIpcCloseMemHandle(h->win_remote[i]);
+        h->win_remote.clear();
+        if (h->win_local) { cudaFree(h->win_local); h->win_local = nullptr; }
+        h->win_state = -1;
+        return 0;
+    }
+    h->win_bytes = alloc; h->ws_bytes += alloc; h->win_state = 1;
+    return 0;
 }
 
 // ---- the loss terms: "local" part (before the exchange) and "finish" part (after it) --------
@@ -1389,8 +1465,15 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     if (pl.job[0].r0 != sh.r0 || sh.n() != N / h->world) return 1;
     const bool amn = (x.xhT == nullptr);
     const int np = x.np;
-    float *u = x.u, *w = x.w, *sclamp = x.sclamp, *loss_part, *r_part, *rcol_part, *rowloss, *r_full, *ss2full, *recvbuf;
+    float *u = x.u, *w = x.w, *sclamp = x.sclamp, *loss_part, *r_part, *rcol_part, *rowloss, *r_full, *ss2full, *recvbuf = nullptr;
     const int tiles_n_all = N / kSs1BN;
+    // Mirrored tiles: either their bf16 sign blocks P[I,J] go to the rank that owns rows J -- copy engine into its peer window,
+    // underneath the GEMMs; the owner multiplies them itself -- or, without a usable window, the fp32 products go through NCCL.
+    long long win_elems = 0;
+    ss_recv_offset(pl, -1, &win_elems);
+    RET(peer_window_ensure(h, static_cast<size_t>(win_elems) * sizeof(bf16), st));
+    const bool pwin = (h->win_state == 1);
+    const int panel_arg = round_up(panel_rows < 256 ? 256 : panel_rows, 256);
     RET(ensure(h, "ss.loss_part", (size_t)tiles_n_all * 2 * N, &loss_part));
     RET(ensure(h, "ss.r_part", (size_t)tiles_n_all * 2 * N, &r_part));
     RET(ensure(h, "ss.rcol_part", (size_t)(N / BM) * 4 * N, &rcol_part));
@@ -1408,7 +1491,7 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     for (int k = 0; k < pl.nrecv; ++k) recv_rows += pl.recv_r1[k] - pl.recv_r0[k];
     bf16* P;
     RET(ensure(h, "ss.P", pmax, &P));
-    RET(ensure(h, "ss.recv", recv_rows * Dp, &recvbuf));
+    if (!pwin) RET(ensure(h, "ss.recv", recv_rows * Dp, &recvbuf));
     static PerDeviceOnce configured;
     if (configured.needed(h->device)) {
         CK(cudaFuncSetAttribute(ss1_pair_merged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSs1MergedSmemBytes));
@@ -1419,6 +1502,16 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     // first product written into a row range of ss2full stores, later ones accumulate; the ranges of the three job kinds are
     // disjoint and every kind sweeps its range panel after panel
     bool fresh_main = true, fresh_wrap = true, fresh_half = true;
+    bool copy_pending = false;
+    cudaEvent_t ev_copied = nullptr;
+    if (pwin) RET(seq_event(h, 39, &ev_copied));
+    // 256 x 512 tiles only where they do not leave half of the CTA pairs without a tile (a wide tile costs ~1.8 narrow ones)
+    const int tm256 = (D + 255) / 256;
+    auto wide_pays = [&](int out_rows) {
+        if (!wide_enabled()) return false;
+        const int wt = tm256 * ((out_rows + 511) / 512), nt = tm256 * ((out_rows + 255) / 256);
+        return ((wt + max_pairs - 1) / max_pairs) * 1.8 < static_cast<double>((nt + max_pairs - 1) / max_pairs);
+    };
     bool own_rows_in_full = false;
     int full_row0 = sh.n();
     for (int k = 0; k < pl.njobs; ++k) {
@@ -1441,9 +1534,34 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
             if (gn > sp.tiles_n) gn = sp.tiles_n;
             sp.group_n = static_cast<int>(gn);
             const int tiles = ss1_num_tiles(sp);
+            if (copy_pending) {      // the copy engine still reads the previous job's blocks out of P
+                PhaseTimer _pe(h, PH_EXCHANGE, st);
+                CK(cudaStreamWaitEvent(st, ev_copied, 0));
+                copy_pending = false;
+            }
             PhaseTimer _pt(h, PH_SS1, st);
             KL(ss1_pair_merged_kernel, 2 * (tiles < max_pairs ? tiles : max_pairs), kSs1Threads, kSs1MergedSmemBytes, st, sp);
             CKL();
+        }
+        if (pwin) {      // blocks of this job that mirror into other ranks' rows: [source rows][receiver rows] in the owner's window
+            SsCopy cp[kSsJobsMax];
+            const int ncp = ss_job_copies(N, h->world, h->rank, panel_arg, pl, k, cp);
+            if (ncp < 0) { h->err = "internal: sign-block copy plan"; return STROTSS_ERR_STATE; }
+            if (ncp > 0) {
+                cudaEvent_t ev_s1;
+                RET(seq_event(h, 40 + k, &ev_s1));
+                CK(cudaEventRecord(ev_s1, st));
+                CK(cudaStreamWaitEvent(h->comm_st, ev_s1, 0));
+                for (int c = 0; c < ncp; ++c) {
+                    bf16* dst = static_cast<bf16*>(h->win_remote[cp[c].peer]) + cp[c].dst_off;
+                    const bf16* src = P + static_cast<long long>(cp[c].i0 - jb.r0) * cw + (cp[c].j0 - jb.c0);
+                    CK(cudaMemcpy2DAsync(dst, static_cast<size_t>(cp[c].ld) * sizeof(bf16), src, static_cast<size_t>(cw) * sizeof(bf16),
+                                         static_cast<size_t>(cp[c].j1 - cp[c].j0) * sizeof(bf16), cp[c].i1 - cp[c].i0,
+                                         cudaMemcpyDeviceToDevice, h->comm_st));
+                }
+                CK(cudaEventRecord(ev_copied, h->comm_st));
+                copy_pending = true;
+            }
         }
         PhaseTimer _pt(h, PH_SS2, st);
         {   // ---- stage 2a: ss2[job rows] (+)= P . x^[job columns]  (+ for a trapezoid the transposed part left of the diagonal)
@@ -1455,6 +1573,7 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
             q.tiles_m = (D + BM - 1) / BM; q.tiles_n = (rows + 255) / 256;
             q.epi.C = out.ss2 + static_cast<long long>(jb.r0 - sh.r0) * Dp; q.epi.ldc = Dp; q.epi.rows = D; q.epi.cols = rows;
             q.epi.alpha = 1.f; q.epi.col_off = 0; q.epi.accumulate = jb.diag ? 0 : 1;      // a panel's trapezoid job comes first
+            const bool wide = wide_pays(rows);
             if (jb.diag) {
                 q.kb_lo_mul[0] = 256 / BK;
                 if (amn) RET(make_tmap_mn(h, &q.tmA[1], x.xh + static_cast<long long>(jb.r0) * Dp, D, rows, Dp));
@@ -1462,21 +1581,23 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
                 RET(make_tmap_mn(h, &q.tmB[1], P, rows, rows, cw));
                 q.nseg = 2; q.seg_kblocks[1] = (rows + BK - 1) / BK; q.seg_acc[1] = 0;
                 q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
-                if (wide_enabled()) {
+                if (wide) {
                     q.tiles_n = (rows + 511) / 512;
                     if (amn) RET((launch_gemm256w<2, 1>(h, q, st))); else RET((launch_gemm256w<2>(h, q, st)));
                 } else {
                     if (amn) RET((launch_gemm256<1, 8, 2, 1>(h, q, st))); else RET((launch_gemm256<1, 8, 2>(h, q, st)));
                 }
-            } else if (wide_enabled()) {
+            } else if (wide) {
                 q.tiles_n = (rows + 511) / 512;
                 if (amn) RET((launch_gemm256w<0, 1>(h, q, st))); else RET((launch_gemm256w<0>(h, q, st)));
             } else {
                 if (amn) RET((launch_gemm256<1, 8, 0, 1>(h, q, st))); else RET((launch_gemm256<1, 8>(h, q, st)));
             }
         }
-        // ---- stage 2b: ss2full[J] (+)= P[job rows][J]^T . x^[job rows] for the mirrored columns J
-        const int m0 = jb.diag ? jb.r1 : jb.c0, mext = jb.c1 - m0;
+        // ---- stage 2b: ss2full[J] (+)= P[job rows][J]^T . x^[job rows] for the mirrored columns J -- all of them when the
+        // products are exchanged, only those of this rank's own block (later panels) when the sign blocks travel instead
+        const int m0 = jb.diag ? jb.r1 : jb.c0;
+        const int mext = pwin ? (jb.diag ? (jb.c1 < sh.r1 ? jb.c1 : sh.r1) - m0 : 0) : jb.c1 - m0;
         if (mext > 0) {
             GemmParams<EpiStoreTr<256>> t{};
             if (amn) RET(make_tmap_mn(h, &t.tmA[0], x.xh + static_cast<long long>(jb.r0) * Dp, D, rows, Dp));
@@ -1486,12 +1607,13 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
             t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (mext + 255) / 256;
             t.epi.C = ss2full + static_cast<long long>(m0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = mext;
             t.epi.alpha = 1.f; t.epi.col_off = 0;
-            if (wide_enabled()) t.tiles_n = (mext + 511) / 512;
+            const bool wide = wide_pays(mext);
+            if (wide) t.tiles_n = (mext + 511) / 512;
             // which range this job writes, and whether an earlier job already stored there
             bool* fr = jb.kind == 0 ? &fresh_main : (jb.kind == 1 ? &fresh_wrap : &fresh_half);
             t.epi.accumulate = *fr ? 0 : 1;
             *fr = false;
-            if (wide_enabled()) { if (amn) RET((launch_gemm256w<1, 1>(h, t, st))); else RET((launch_gemm256w<1>(h, t, st))); }
+            if (wide) { if (amn) RET((launch_gemm256w<1, 1>(h, t, st))); else RET((launch_gemm256w<1>(h, t, st))); }
             else { if (amn) RET((launch_gemm256<1, 8, 1, 1>(h, t, st))); else RET((launch_gemm256<1, 8, 1>(h, t, st))); }
             if (jb.diag && m0 < sh.r1) { own_rows_in_full = true; if (m0 - sh.r0 < full_row0) full_row0 = m0 - sh.r0; }
         }
@@ -1508,25 +1630,66 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     }
     {   // ---- exchange: r summed over ranks; mirrored stage-2 products to the ranks that own their rows
         PhaseTimer _pe(h, PH_EXCHANGE, st);
+        // A rank enters this collective only after its copies into the peers' windows have completed, so leaving it means every
+        // block destined for this rank has landed.  (The window is not overwritten early either: a peer starts the copies of its
+        // next evaluation after this evaluation's last collective, which this rank enters after it has consumed the window.)
+        if (copy_pending) { CK(cudaStreamWaitEvent(st, ev_copied, 0)); copy_pending = false; }
         NCK(nccl().AllReduce(r_full, r_full, (size_t)N, kNcclFloat32, kNcclSum, h->nccl_comm, st));
-        NCK(nccl().GroupStart());
-        size_t roff = 0;
-        for (int k = 0; k < pl.nsend; ++k)
-            NCK(nccl().Send(ss2full + static_cast<long long>(pl.send_r0[k]) * Dp, (size_t)(pl.send_r1[k] - pl.send_r0[k]) * Dp, kNcclFloat32,
-                            pl.send_peer[k], h->nccl_comm, st));
-        for (int k = 0; k < pl.nrecv; ++k) {
-            NCK(nccl().Recv(recvbuf + roff * Dp, (size_t)(pl.recv_r1[k] - pl.recv_r0[k]) * Dp, kNcclFloat32, pl.recv_peer[k], h->nccl_comm, st));
-            roff += pl.recv_r1[k] - pl.recv_r0[k];
+        if (!pwin) {
+            NCK(nccl().GroupStart());
+            size_t roff = 0;
+            for (int k = 0; k < pl.nsend; ++k)
+                NCK(nccl().Send(ss2full + static_cast<long long>(pl.send_r0[k]) * Dp, (size_t)(pl.send_r1[k] - pl.send_r0[k]) * Dp, kNcclFloat32,
+                                pl.send_peer[k], h->nccl_comm, st));
+            for (int k = 0; k < pl.nrecv; ++k) {
+                NCK(nccl().Recv(recvbuf + roff * Dp, (size_t)(pl.recv_r1[k] - pl.recv_r0[k]) * Dp, kNcclFloat32, pl.recv_peer[k], h->nccl_comm, st));
+                roff += pl.recv_r1[k] - pl.recv_r0[k];
+            }
+            NCK(nccl().GroupEnd());
         }
-        NCK(nccl().GroupEnd());
+    }
+    if (pwin) {
+        // ---- stage 2c: ss2[J] += sum over the received blocks  P[I,J]^T . x^[I]  (B = the window, MN-major; A = x^ rows of the
+        // block's source rank, MN-major); blocks with the same output rows share one launch and one accumulator
+        PhaseTimer _pt(h, PH_SS2, st);
+        bool done[kSsJobsMax] = {};
+        for (int k = 0; k < pl.nrecv; ++k) {
+            if (done[k]) continue;
+            const int o0 = pl.recv_r0[k], o1 = pl.recv_r1[k], orow = o1 - o0;
+            GemmParams<EpiStoreTr<256>> t{};
+            int ns = 0;
+            long long off = 0;
+            for (int e = 0; e < pl.nrecv; ++e) {
+                const int nsrc = pl.recv_src_r1[e] - pl.recv_src_r0[e], nout = pl.recv_r1[e] - pl.recv_r0[e];
+                if (e >= k && !done[e] && pl.recv_r0[e] == o0 && pl.recv_r1[e] == o1) {
+                    if (amn) RET(make_tmap_mn(h, &t.tmA[ns], x.xh + static_cast<long long>(pl.recv_src_r0[e]) * Dp, D, nsrc, Dp));
+                    else RET(make_tmap(h, &t.tmA[ns], x.xhT + pl.recv_src_r0[e], D, nsrc, np, BM));
+                    RET(make_tmap_mn(h, &t.tmB[ns], static_cast<const bf16*>(h->win_local) + off, nout, nsrc, nout));
+                    t.seg_kblocks[ns] = nsrc / BK; t.seg_acc[ns] = 0;
+                    ++ns;
+                    done[e] = true;
+                }
+                off += static_cast<long long>(nsrc) * nout;
+            }
+            t.nseg = ns;
+            t.tiles_m = (D + BM - 1) / BM; t.tiles_n = (orow + 255) / 256;
+            t.epi.C = out.ss2 + static_cast<long long>(o0 - sh.r0) * Dp; t.epi.ldc = Dp; t.epi.rows = D; t.epi.cols = orow;
+            t.epi.alpha = 1.f; t.epi.col_off = 0; t.epi.accumulate = 1;
+            if (wide_pays(orow)) {
+                t.tiles_n = (orow + 511) / 512;
+                if (amn) RET((launch_gemm256w<1, 1>(h, t, st))); else RET((launch_gemm256w<1>(h, t, st)));
+            } else {
+                if (amn) RET((launch_gemm256<1, 8, 1, 1>(h, t, st))); else RET((launch_gemm256<1, 8, 1>(h, t, st)));
+            }
+        }
     }
     PhaseTimer _pm(h, PH_SS_MISC, st);
-    {
+    if (!pwin || own_rows_in_full) {
         Ss2AddArgs a{};
         a.ss2 = out.ss2; a.full = own_rows_in_full ? ss2full + static_cast<long long>(sh.r0) * Dp : nullptr; a.full_row0 = full_row0;
-        a.row_floats = Dp; a.rows = sh.n(); a.nrecv = pl.nrecv;
+        a.row_floats = Dp; a.rows = sh.n(); a.nrecv = pwin ? 0 : pl.nrecv;
         size_t roff = 0;
-        for (int k = 0; k < pl.nrecv; ++k) {
+        for (int k = 0; k < a.nrecv; ++k) {
             a.recv[k] = recvbuf + roff * Dp; a.off[k] = pl.recv_r0[k] - sh.r0; a.cnt[k] = pl.recv_r1[k] - pl.recv_r0[k];
             roff += a.cnt[k];
         }
@@ -1702,6 +1865,14 @@ int strotss_comm_init(strotss_handle h, int rank, int world, const char* id128) 
     RET(check_handle(h));
     if (world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) { h->err = "comm_init: bad argument"; return STROTSS_ERR_ARG; }
     if (h->nccl_comm) { nccl().CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+    // a peer window belongs to one communicator
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (size_t i = 0; i < h->win_remote.size(); ++i)
+        if (h->win_remote[i] && h->win_remote[i] != h->win_local) cudaIpcCloseMemHandle(h->win_remote[i]);
+    h->win_remote.clear();
+    if (h->win_local) { cudaFree(h->win_local); h->ws_bytes -= h->win_bytes; h->win_local = nullptr; h->win_bytes = 0; }
+    h->win_state = 0;
     h->rank = rank; h->world = world;
     if (world == 1) return 0;
     if (!nccl().ok) { h->err = "NCCL unavailable: " + nccl().why; return STROTSS_ERR_CUDA; }
@@ -2498,6 +2669,25 @@ int strotss_debug_ss_jobs(int N, int world, int rank, int panel, int* jobs6, int
     for (int k = 0; k < pl.nrecv; ++k) { recvs3[3 * k] = pl.recv_peer[k]; recvs3[3 * k + 1] = pl.recv_r0[k]; recvs3[3 * k + 2] = pl.recv_r1[k]; }
     counts3[0] = pl.njobs; counts3[1] = pl.nsend; counts3[2] = pl.nrecv;
     return 1;
+}
+
+int strotss_debug_ss_copies(int N, int world, int rank, int panel, long long* copies8, int capacity, long long* window_elems) {
+    if (!copies8 || !window_elems || capacity < 0) return STROTSS_ERR_ARG;
+    SsPlan pl;
+    if (!ss_make_plan(N, world, rank, panel, pl)) return -1;
+    ss_recv_offset(pl, -1, window_elems);
+    int n = 0;
+    for (int k = 0; k < pl.njobs; ++k) {
+        SsCopy cp[kSsJobsMax];
+        const int ncp = ss_job_copies(N, world, rank, panel, pl, k, cp);
+        if (ncp < 0) return -1;
+        for (int c = 0; c < ncp; ++c, ++n) {
+            if (n >= capacity) return STROTSS_ERR_ARG;
+            const long long v[8] = {k, cp[c].peer, cp[c].dst_off, cp[c].ld, cp[c].i0, cp[c].i1, cp[c].j0, cp[c].j1};
+            for (int e = 0; e < 8; ++e) copies8[8 * n + e] = v[e];
+        }
+    }
+    return n;
 }
 
 }  // extern "C"

@@ -100,4 +100,25 @@ inline long long ss_recv_offset(const SsPlan& pl, int from, long long* total = n
     return found;
 }
 
+// Sign-block copies a rank issues after stage 1 of job `k` when the blocks travel instead of the products: the part of the job
+// that mirrors into rows of rank `peer` -- rows [i0, i1) x columns [j0, j1) of the matrix -- goes to element offset `dst_off`
+// of that rank's window, stored with row length `ld` (= the number of receiver rows of the block).
+struct SsCopy { int peer; long long dst_off; int ld; int i0, i1, j0, j1; };
+inline int ss_job_copies(int N, int world, int rank, int panel, const SsPlan& pl, int k, SsCopy* out /* [kSsJobsMax] */) {
+    const SsJob& jb = pl.job[k];
+    int n = 0;
+    for (int e = 0; e < pl.nsend; ++e) {
+        const int i0 = jb.r0 > pl.send_src_r0[e] ? jb.r0 : pl.send_src_r0[e], i1 = jb.r1 < pl.send_src_r1[e] ? jb.r1 : pl.send_src_r1[e];
+        const int j0 = jb.c0 > pl.send_r0[e] ? jb.c0 : pl.send_r0[e], j1 = jb.c1 < pl.send_r1[e] ? jb.c1 : pl.send_r1[e];
+        if (i0 >= i1 || j0 >= j1) continue;
+        SsPlan pp;
+        if (!ss_make_plan(N, world, pl.send_peer[e], panel, pp)) return -1;
+        const long long off = ss_recv_offset(pp, rank);
+        if (off < 0) return -1;
+        const int ld = pl.send_r1[e] - pl.send_r0[e];
+        out[n++] = SsCopy{pl.send_peer[e], off + static_cast<long long>(i0 - pl.send_src_r0[e]) * ld + (j0 - pl.send_r0[e]), ld, i0, i1, j0, j1};
+    }
+    return n;
+}
+
 }  // namespace sb
