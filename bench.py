@@ -528,6 +528,10 @@ def main():
         barrier()
         ms_shard = max_over_ranks(s0.elapsed_time(s1) / args.steps)
         sphases = hs.profile_read()
+        # every rank's phase times: the step lasts as long as the slowest rank, and a rank's `exchange` includes its wait for it
+        ph_names = sorted(sphases)
+        ph_all = [None] * world
+        dist.all_gather_object(ph_all, [round(sphases[k][0] / args.steps, 4) for k in ph_names])
         hs.profile_enable(False)
         r0s, r1s = hs.shard_rows(N)
         # parity of the sharded evaluation against a single-GPU evaluation of the same inputs on this rank (outside the timed loop)
@@ -548,9 +552,11 @@ def main():
         ok = par[0] <= 1e-4 and par[1] <= 2e-3 and par[2] <= 1e-3 and par[3] <= 1e-3
         shard_info = {"value": 1000.0 / ms_shard, "unit": "evals/s", "ms_per_step": ms_shard, "scaling": "strong",
                       "rows_per_rank": r1s - r0s, "loss": float(sc_s[_lib.S_TOTAL].item()),
+                      "transport": {1: "peer_window", -1: "nccl_sendrecv"}.get(hs.comm_transport(), "none"),
                       "collectives_per_eval": hs.collectives_note(M, D_FEAT) if hasattr(hs, "collectives_note") else
                       f"1 allreduce-max of 2x{M} packed u64 minima + 1 allreduce-sum of {16 + D_FEAT} floats (NCCL)",
                       "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sphases.items()},
+                      "phases_ms_per_step_by_rank": {k: [ph_all[r][i] for r in range(world)] for i, k in enumerate(ph_names)},
                       "parity": {"vs": "single-GPU strotss_eval of the same inputs on every rank; max over ranks",
                                  "scalars_max_rel_diff": par[0], "own_grad_rows_rel_diff": par[1],
                                  "row_argmin_mismatch_frac": par[2], "col_argmin_mismatch_frac": par[3], "ok": ok}}

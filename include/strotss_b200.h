@@ -90,6 +90,13 @@ int strotss_profile_read(strotss_handle h, double* ms_sum, long long* counts);
 int strotss_comm_unique_id(char* out128);
 int strotss_comm_init(strotss_handle h, int rank, int world, const char* id128);
 int strotss_shard_rows(strotss_handle h, int N, int* row_begin, int* row_end);
+/* How the self-similarity term of a sharded evaluation crosses ranks (nn/losses.py:56-68: Xd, Yd are symmetric, so every
+ * 256 x 256 tile is computed by ONE rank and stands for its mirror image as well):
+ *   1  CUDA-IPC peer windows -- the bf16 sign blocks of the mirrored tiles are pushed by copy engine into the owner's
+ *      window while the GEMMs run, and the owner multiplies them itself (no data-path NCCL kernel besides the small allreduces);
+ *  -1  peer windows unavailable (IPC refused, or STROTSS_PEER_WINDOW=0): the fp32 products travel by ncclSend / ncclRecv;
+ *   0  not decided yet (no sharded evaluation has run) or no communicator. */
+int strotss_comm_transport(strotss_handle h);
 
 /* StyleLoss.__init__(target, alpha) (run_strotss.py:28-31): fix the style target for a scale.
  * Caches what the reference recomputes every iteration (nn/losses.py:43,49; run_strotss.py:37):

@@ -34,6 +34,7 @@ SIGNATURES = {
     "strotss_comm_unique_id": (_i, [C.c_char_p]),
     "strotss_comm_init": (_i, [_vp, _i, _i, C.c_char_p]),
     "strotss_shard_rows": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "strotss_comm_transport": (_i, [_vp]),
     "strotss_set_style_target": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "strotss_eval": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _f, _vp, _vp, _ll, _vp, _vp, _vp]),
     "strotss_set_style_targets_grouped": (_i, [_vp, _vp, _ll, C.POINTER(_i), _i, _i, _vp]),

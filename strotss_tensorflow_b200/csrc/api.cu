@@ -88,9 +88,9 @@ __global__ void copy_scalars_kernel(const float* __restrict__ src, int4 idx, int
 
 // Phases timed with CUDA events on the launching stream when profiling is enabled.
 enum Phase { PH_PREP = 0, PH_REMD_GEMM, PH_REMD_MISC, PH_PALETTE, PH_COV_FWD, PH_COV_BWD, PH_MOM_MISC, PH_SS_VEC, PH_SS1, PH_SS2,
-             PH_SS_MISC, PH_FINALIZE, PH_EXCHANGE, PH_COUNT };
+             PH_SS_MISC, PH_FINALIZE, PH_EXCHANGE, PH_COV_OWNER, PH_COPY_WAIT, PH_EXCHANGE2, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"prep", "remd_gemm", "remd_misc", "palette", "cov_fwd_gemm", "cov_bwd_gemm", "moment_misc",
-                                            "ss_vectors", "ss_stage1_gemm", "ss_stage2_gemm", "ss_misc", "finalize", "exchange"};
+                                            "ss_vectors", "ss_stage1_gemm", "ss_stage2_gemm", "ss_misc", "finalize", "exchange", "cov_owner", "copy_wait", "exchange_last"};
 struct PhaseRec { int id; cudaEvent_t a, b; };
 
 // Prepared operands of one (n x D) fp32 feature matrix.
@@ -195,7 +195,8 @@ struct strotss_ctx {
     void* win_local = nullptr; size_t win_bytes = 0;
     std::vector<void*> win_remote;       // [world]; own entry = win_local
     int win_state = 0;                   // 0 untried, 1 usable, -1 unavailable (IPC refused): fall back to the product exchange
-    cudaStream_t comm_st = nullptr;      // copies into peer windows
+    static constexpr int kCommStreams = 4;
+    cudaStream_t comm_st[kCommStreams] = {nullptr, nullptr, nullptr, nullptr};      // copies into peer windows, one stream per destination in flight
     // optional per-phase CUDA-event timing
     bool profiling = false;
     std::vector<PhaseRec> recs;
@@ -229,7 +230,7 @@ struct strotss_ctx {
         for (size_t i = 0; i < win_remote.size(); ++i)
             if (win_remote[i] && win_remote[i] != win_local) cudaIpcCloseMemHandle(win_remote[i]);
         if (win_local) cudaFree(win_local);
-        if (comm_st) cudaStreamDestroy(comm_st);
+        for (auto& cs : comm_st) if (cs) cudaStreamDestroy(cs);
         if (h_scalars) cudaFreeHost(h_scalars);
         for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto& e : pool) cudaEventDestroy(e);
@@ -746,7 +747,7 @@ int cov_store(strotss_ctx* h, const Feat& f, int D, int Dp, float* V, cudaStream
 
 // ---- the three loss terms, each leaving its gradient contribution in workspace buffers --
 // Slots of the float block that is summed over ranks once per evaluation.
-enum { PS_REMD_RY = 0, PS_PAL_RY = 1, PS_SS_LOSS = 2, PS_V = 16 };
+enum { PS_REMD_RY = 0, PS_PAL_RY = 1, PS_SS_LOSS = 2, PS_COV_L1 = 3, PS_V = 16 };
 
 // ---- NCCL through dlopen (the library must not need libnccl to load) ---------------------
 struct NcclApi {
@@ -827,12 +828,13 @@ int peer_window_ensure(strotss_ctx* h, size_t bytes, cudaStream_t st) {
         if (h->win_remote[i] && h->win_remote[i] != h->win_local) cudaIpcCloseMemHandle(h->win_remote[i]);
     h->win_remote.assign(h->world, nullptr);
     if (h->win_local) { cudaFree(h->win_local); h->ws_bytes -= h->win_bytes; h->win_local = nullptr; h->win_bytes = 0; }
-    if (!h->comm_st) CK(cudaStreamCreateWithFlags(&h->comm_st, cudaStreamNonBlocking));
+    for (auto& cs : h->comm_st) if (!cs) CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     const size_t alloc = (bytes + (1u << 21) - 1) >> 21 << 21;
     int good = 1;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     if (cudaMalloc(&h->win_local, alloc) != cudaSuccess) { cudaGetLastError(); h->win_local = nullptr; good = 0; }
+    if (good && cudaMemset(h->win_local, 0, alloc) != cudaSuccess) { cudaGetLastError(); good = 0; }      // Sg keeps its zero padding
     if (good && cudaIpcGetMemHandle(&mine, h->win_local) != cudaSuccess) { cudaGetLastError(); good = 0; }
     // exchange: [world] handles, then a flag
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1032,6 +1034,9 @@ struct MomOut { float* Q = nullptr; long long ldq = 0; float q_scale = 0.f; floa
 // replicated on every rank (3 % of the work); the backward GEMM covers this rank's rows only.
 int mom_nparts(int D) { return (((D + BM - 1) / BM + 1) / 2 * 2) * ((D + 255) / 256) * 4; }
 
+int cov_backward(strotss_ctx* h, const bf16* Sg, const Feat& pred, int N, Shard sh, int D, int Dp, bool want_grad, MomOut& out,
+                 cudaStream_t st);
+
 int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred, int N, Shard sh, int D, int Dp, float* scalars,
             bool want_grad, MomOut& out, cudaStream_t st, float* part_zeroed = nullptr) {
     bf16* Sg; float* part;
@@ -1070,6 +1075,11 @@ int moments(strotss_ctx* h, const float* mu_x, const float* Vx, const Feat& pred
         KL(moment_finish_kernel, 1, 1024, 0, st, pred.mean, mu_x, D, part, npart, out.gmu, scalars);
         CKL();
     }
+    return cov_backward(h, Sg, pred, N, sh, D, Dp, want_grad, out, st);
+}
+
+int cov_backward(strotss_ctx* h, const bf16* Sg, const Feat& pred, int N, Shard sh, int D, int Dp, bool want_grad, MomOut& out,
+                 cudaStream_t st) {
     out.Q = nullptr; out.ldq = 0; out.q_scale = 0.f;
     if (want_grad && sh.n() > 0) {
         // Q = cen . (G + G^T) / N with G = sign(V_y - V_x)/D^2 symmetric  ->  q_scale * (cen . Sg^T)
@@ -1452,28 +1462,112 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
 //   * the stage-2 products ss2[J] += P[I,J]^T x^[I] of the mirrored tiles (point-to-point ncclSend / ncclRecv inside one group:
 //     each rank sends / receives (g - 1) / 2 blocks of N / g rows, 64 MB at N = 16384 on 8 GPUs).
 // Same outputs as self_sim_local.  Returns 1 if the shape cannot use the scheme (the caller then runs self_sim_local).
-int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh, int D, int Dp, float* loss_partial,
-                         float* v_partial, SsOut& out, cudaStream_t st) {
+// ---- row-sharded evaluation over peer windows: what is decided (collectively) before the operands are prepared -----------
+// Window layout (bytes): [ sign blocks of the mirrored self-similarity tiles | partial-Gram slots [world][nslots][256 x 256] fp32 |
+// Sg (Dp x Dp bf16, zero padding kept from the allocation) ].
+struct ShardSym {
+    bool active = false;       // symmetric (circulant) split of the self-similarity triangle
+    bool pwin = false;         // sign blocks through the peer windows (else fp32 products through NCCL)
+    bool cov = false;          // covariance forward row-sharded as well (partial Gram tiles -> owner ranks -> Sg to everyone)
+    SsPlan pl;
+    int panel = 0;
+    size_t off_gram = 0, off_sg = 0;
+    int gram_tiles = 0, gram_slots = 0;
+};
+
+int shard_sym_setup(strotss_ctx* h, int N, int D, int Dp, Shard sh, bool prep3, cudaStream_t st, ShardSym& ss) {
     static const bool off = getenv("STROTSS_SHARD_SYM") && atoi(getenv("STROTSS_SHARD_SYM")) == 0;
     static const bool merged_off = getenv("STROTSS_SS1_MERGED") && atoi(getenv("STROTSS_SS1_MERGED")) == 0;
     static const bool generic_env = (getenv("STROTSS_SS1_GENERIC") != nullptr);
     static const int small_max = getenv("STROTSS_SS1_SMALL_MAX") ? atoi(getenv("STROTSS_SS1_SMALL_MAX")) : 2048;
     static const int panel_rows = getenv("STROTSS_PANEL") ? atoi(getenv("STROTSS_PANEL")) : 4096;
-    if (off || merged_off || generic_env || !pair_enabled() || !x.u || N <= small_max) return 1;
-    SsPlan pl;
-    if (!ss_make_plan(N, h->world, h->rank, round_up(panel_rows < 256 ? 256 : panel_rows, 256), pl)) return 1;
-    if (pl.job[0].r0 != sh.r0 || sh.n() != N / h->world) return 1;
+    static const bool cov_off = getenv("STROTSS_SHARD_COV") && atoi(getenv("STROTSS_SHARD_COV")) == 0;
+    ss = ShardSym{};
+    if (off || merged_off || generic_env || !pair_enabled() || !prep3 || N <= small_max) return 0;
+    ss.panel = round_up(panel_rows < 256 ? 256 : panel_rows, 256);
+    if (!ss_make_plan(N, h->world, h->rank, ss.panel, ss.pl)) return 0;
+    if (ss.pl.job[0].r0 != sh.r0 || sh.n() != N / h->world) return 0;
+    ss.active = true;
+    long long win_elems = 0;
+    ss_recv_offset(ss.pl, -1, &win_elems);
+    ss.gram_tiles = (D + 255) / 256;
+    const int ntri = ss.gram_tiles * (ss.gram_tiles + 1) / 2;
+    ss.gram_slots = (ntri + h->world - 1) / h->world;
+    ss.off_gram = (static_cast<size_t>(win_elems) * sizeof(bf16) + 1023) / 1024 * 1024;
+    const bool want_cov = !cov_off && h->world <= EpiGramScatter<256>::kMaxRanks;
+    const size_t gram_bytes = want_cov ? static_cast<size_t>(h->world) * ss.gram_slots * 65536 * sizeof(float) : 0;
+    ss.off_sg = ss.off_gram + gram_bytes;
+    const size_t total = ss.off_sg + (want_cov ? static_cast<size_t>(Dp) * Dp * sizeof(bf16) : 0);
+    RET(peer_window_ensure(h, total, st));
+    ss.pwin = (h->win_state == 1);
+    ss.cov = ss.pwin && want_cov;
+    return 0;
+}
+
+// Covariance forward, row-sharded (nn/losses.py:43-50 over this rank's rows): partial Gram tiles of the centred rows go straight
+// from the GEMM epilogue into the windows of the ranks that own them.
+int cov_sharded_scatter(strotss_ctx* h, const Feat& pred, Shard sh, int D, int Dp, const ShardSym& ss, cudaStream_t st) {
+    GemmParams<EpiGramScatter<256>> p{};
+    RET(make_tmap_mn(h, &p.tmA[0], pred.cen + static_cast<long long>(sh.r0) * Dp, D, sh.n(), Dp));
+    p.tmB[0] = p.tmA[0];
+    p.nseg = 1; p.seg_kblocks[0] = (sh.n() + BK - 1) / BK; p.seg_acc[0] = 0;
+    p.tiles_m = (D + BM - 1) / BM; p.tiles_n = (D + 255) / 256;
+    p.tri = 1;
+    p.epi.world = h->world; p.epi.tiles = ss.gram_tiles;
+    for (int q = 0; q < h->world; ++q)
+        p.epi.base[q] = reinterpret_cast<float*>(static_cast<unsigned char*>(h->win_remote[q]) + ss.off_gram) +
+                        static_cast<long long>(h->rank) * ss.gram_slots * 65536;
+    PhaseTimer _pt(h, PH_COV_FWD, st);
+    return launch_gemm256<1, 4, 1, 1>(h, p, st);
+}
+
+// ... after a collective every rank entered behind its scatter: this rank adds up the partial tiles it owns, and the sign
+// matrix of those tiles goes to every rank's Sg; the |V - Vx| sum of the owned tiles joins the allreduce-sum block.
+int cov_sharded_owner(strotss_ctx* h, const float* Vx, int N, int D, int Dp, const ShardSym& ss, float* l1_slot, cudaStream_t st) {
+    PhaseTimer _pt(h, PH_COV_OWNER, st);
+    CovOwnArgs a{};
+    a.slots = reinterpret_cast<const float*>(static_cast<unsigned char*>(h->win_local) + ss.off_gram);
+    a.world = h->world; a.rank = h->rank; a.nslots = ss.gram_slots; a.tiles = ss.gram_tiles;
+    a.Vx = Vx; a.ldv = Dp; a.inv_n = 1.f / N; a.D = D; a.lds = Dp;
+    for (int q = 0; q < h->world; ++q) a.sg[q] = reinterpret_cast<bf16*>(static_cast<unsigned char*>(h->win_remote[q]) + ss.off_sg);
+    const int nblk = ss.gram_slots * 16;
+    RET(ensure(h, "mom.ownpart", (size_t)nblk, &a.part));
+    KL(cov_owner_kernel, nblk, 256, 0, st, a);
+    CKL();
+    KL(reduce_sum_kernel, 1, 1024, 0, st, a.part, nblk, 1.f, l1_slot);
+    CKL();
+    return 0;
+}
+
+// ... and after the allreduce-sum (every rank's Sg is complete, the |.| sum is global): mean term, losses, backward GEMM.
+int cov_sharded_finish(strotss_ctx* h, const float* mu_x, const Feat& pred, int N, Shard sh, int D, int Dp, const ShardSym& ss,
+                       const float* l1_slot, float* scalars, bool want_grad, MomOut& out, cudaStream_t st) {
+    RET(ensure(h, "mom.gmu", (size_t)D, &out.gmu));
+    {
+        PhaseTimer _pt(h, PH_MOM_MISC, st);
+        KL(moment_finish_kernel, 1, 1024, 0, st, pred.mean, mu_x, D, l1_slot, 1, out.gmu, scalars);
+        CKL();
+    }
+    const bf16* Sg = reinterpret_cast<const bf16*>(static_cast<unsigned char*>(h->win_local) + ss.off_sg);
+    return cov_backward(h, Sg, pred, N, sh, D, Dp, want_grad, out, st);
+}
+
+// best / nbest: the packed minima of the relaxed-EMD and palette terms, complete on `st` when this is called; their
+// allreduce-max rides in the same NCCL group as the allreduce of r (one launch, one wait for the slowest rank).
+// after_barrier (optional): work that needs every rank to have passed its earlier stream work (the covariance owner step).
+int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh, int D, int Dp, float* loss_partial,
+                         float* v_partial, SsOut& out, cudaStream_t st, unsigned long long* best, size_t nbest, bool* best_reduced,
+                         const ShardSym& ssym, const std::function<int()>& after_barrier) {
+    if (!ssym.active || !x.u) return 1;
+    const SsPlan& pl = ssym.pl;
     const bool amn = (x.xhT == nullptr);
     const int np = x.np;
     float *u = x.u, *w = x.w, *sclamp = x.sclamp, *loss_part, *r_part, *rcol_part, *rowloss, *r_full, *ss2full, *recvbuf = nullptr;
     const int tiles_n_all = N / kSs1BN;
     // Mirrored tiles: either their bf16 sign blocks P[I,J] go to the rank that owns rows J -- copy engine into its peer window,
     // underneath the GEMMs; the owner multiplies them itself -- or, without a usable window, the fp32 products go through NCCL.
-    long long win_elems = 0;
-    ss_recv_offset(pl, -1, &win_elems);
-    RET(peer_window_ensure(h, static_cast<size_t>(win_elems) * sizeof(bf16), st));
-    const bool pwin = (h->win_state == 1);
-    const int panel_arg = round_up(panel_rows < 256 ? 256 : panel_rows, 256);
+    const bool pwin = ssym.pwin;
+    const int panel_arg = ssym.panel;
     RET(ensure(h, "ss.loss_part", (size_t)tiles_n_all * 2 * N, &loss_part));
     RET(ensure(h, "ss.r_part", (size_t)tiles_n_all * 2 * N, &r_part));
     RET(ensure(h, "ss.rcol_part", (size_t)(N / BM) * 4 * N, &rcol_part));
@@ -1483,14 +1577,17 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     RET(ensure(h, "ss.ss2", (size_t)sh.n() * Dp, &out.ss2));
     RET(ensure(h, "ss.ss2full", (size_t)N * Dp, &ss2full));
     out.ld = Dp;
-    size_t pmax = 0, recv_rows = 0;
-    for (int k = 0; k < pl.njobs; ++k) {
-        const size_t e = (size_t)(pl.job[k].r1 - pl.job[k].r0) * (pl.job[k].c1 - pl.job[k].c0);
-        if (e > pmax) pmax = e;
-    }
+    size_t recv_rows = 0;
     for (int k = 0; k < pl.nrecv; ++k) recv_rows += pl.recv_r1[k] - pl.recv_r0[k];
-    bf16* P;
-    RET(ensure(h, "ss.P", pmax, &P));
+    // One sign-matrix buffer per job: all stage-1 launches are issued first, alternating between two streams, so that the
+    // partially filled last round of one persistent launch is filled by the first tiles of the next (a rank of the upper half of
+    // an even world has three jobs -- 164 + 64 + 32 tiles at 8 GPUs: 5 rounds of 74 CTA pairs one after another, 3.5 overlapped);
+    // the copies into the peer windows start behind each job and run under everything that follows.
+    bf16* Pj[kSsJobsMax];
+    for (int k = 0; k < pl.njobs; ++k) {
+        const std::string nm = "ss.P" + std::to_string(k);
+        RET(ensure(h, nm.c_str(), (size_t)(pl.job[k].r1 - pl.job[k].r0) * (pl.job[k].c1 - pl.job[k].c0), &Pj[k]));
+    }
     if (!pwin) RET(ensure(h, "ss.recv", recv_rows * Dp, &recvbuf));
     static PerDeviceOnce configured;
     if (configured.needed(h->device)) {
@@ -1502,9 +1599,16 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     // first product written into a row range of ss2full stores, later ones accumulate; the ranges of the three job kinds are
     // disjoint and every kind sweeps its range panel after panel
     bool fresh_main = true, fresh_wrap = true, fresh_half = true;
-    bool copy_pending = false;
-    cudaEvent_t ev_copied = nullptr;
-    if (pwin) RET(seq_event(h, 39, &ev_copied));
+    // copies of one job go to different peers: each on its own stream / copy engine, all of them awaited together
+    int copy_pending = 0;
+    cudaEvent_t ev_copied[strotss_ctx::kCommStreams] = {};
+    if (pwin) for (int c = 0; c < strotss_ctx::kCommStreams; ++c) RET(seq_event(h, 30 + c, &ev_copied[c]));
+    auto await_copies = [&]() -> int {
+        PhaseTimer _pe(h, PH_COPY_WAIT, st);
+        for (int c = 0; c < copy_pending; ++c) CK(cudaStreamWaitEvent(st, ev_copied[c], 0));
+        copy_pending = 0;
+        return 0;
+    };
     // 256 x 512 tiles only where they do not leave half of the CTA pairs without a tile (a wide tile costs ~1.8 narrow ones)
     const int tm256 = (D + 255) / 256;
     auto wide_pays = [&](int out_rows) {
@@ -1514,9 +1618,20 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     };
     bool own_rows_in_full = false;
     int full_row0 = sh.n();
+    static const bool two_streams = !(getenv("STROTSS_SHARD_SS1_STREAMS") && atoi(getenv("STROTSS_SHARD_SS1_STREAMS")) == 1);
+    const bool alt = two_streams && pl.njobs > 1;
+    cudaEvent_t ev_job[kSsJobsMax] = {};
+    if (alt) {
+        cudaEvent_t ev_fork;
+        RET(seq_event(h, 38, &ev_fork));
+        CK(cudaEventRecord(ev_fork, st));
+        CK(cudaStreamWaitEvent(h->aux, ev_fork, 0));
+    }
     for (int k = 0; k < pl.njobs; ++k) {
         const SsJob jb = pl.job[k];
         const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
+        bf16* P = Pj[k];
+        cudaStream_t sk = (alt && (k & 1)) ? h->aux : st;
         {   // ---- stage 1: P[rows][cw] (bf16), loss / r partials
             Ss1Params sp{};
             RET(make_tmap(h, &sp.tmA[0], y.xh, N, Dp, Dp, BM)); RET(make_tmap(h, &sp.tmB[0], y.xh, N, Dp, Dp, 128));      // y^ . y^T
@@ -1534,35 +1649,37 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
             if (gn > sp.tiles_n) gn = sp.tiles_n;
             sp.group_n = static_cast<int>(gn);
             const int tiles = ss1_num_tiles(sp);
-            if (copy_pending) {      // the copy engine still reads the previous job's blocks out of P
-                PhaseTimer _pe(h, PH_EXCHANGE, st);
-                CK(cudaStreamWaitEvent(st, ev_copied, 0));
-                copy_pending = false;
-            }
-            PhaseTimer _pt(h, PH_SS1, st);
-            KL(ss1_pair_merged_kernel, 2 * (tiles < max_pairs ? tiles : max_pairs), kSs1Threads, kSs1MergedSmemBytes, st, sp);
+            PhaseTimer _pt(h, PH_SS1, sk);
+            KL(ss1_pair_merged_kernel, 2 * (tiles < max_pairs ? tiles : max_pairs), kSs1Threads, kSs1MergedSmemBytes, sk, sp);
             CKL();
         }
-        if (pwin) {      // blocks of this job that mirror into other ranks' rows: [source rows][receiver rows] in the owner's window
-            SsCopy cp[kSsJobsMax];
-            const int ncp = ss_job_copies(N, h->world, h->rank, panel_arg, pl, k, cp);
-            if (ncp < 0) { h->err = "internal: sign-block copy plan"; return STROTSS_ERR_STATE; }
-            if (ncp > 0) {
-                cudaEvent_t ev_s1;
-                RET(seq_event(h, 40 + k, &ev_s1));
-                CK(cudaEventRecord(ev_s1, st));
-                CK(cudaStreamWaitEvent(h->comm_st, ev_s1, 0));
-                for (int c = 0; c < ncp; ++c) {
-                    bf16* dst = static_cast<bf16*>(h->win_remote[cp[c].peer]) + cp[c].dst_off;
-                    const bf16* src = P + static_cast<long long>(cp[c].i0 - jb.r0) * cw + (cp[c].j0 - jb.c0);
-                    CK(cudaMemcpy2DAsync(dst, static_cast<size_t>(cp[c].ld) * sizeof(bf16), src, static_cast<size_t>(cw) * sizeof(bf16),
-                                         static_cast<size_t>(cp[c].j1 - cp[c].j0) * sizeof(bf16), cp[c].i1 - cp[c].i0,
-                                         cudaMemcpyDeviceToDevice, h->comm_st));
-                }
-                CK(cudaEventRecord(ev_copied, h->comm_st));
-                copy_pending = true;
-            }
+        SsCopy cp[kSsJobsMax];
+        const int ncp = pwin ? ss_job_copies(N, h->world, h->rank, panel_arg, pl, k, cp) : 0;
+        if (ncp < 0) { h->err = "internal: sign-block copy plan"; return STROTSS_ERR_STATE; }
+        if (ncp > 0 || sk != st) {
+            RET(seq_event(h, 40 + k, &ev_job[k]));
+            CK(cudaEventRecord(ev_job[k], sk));
         }
+        if (ncp > 0) {      // blocks of this job that mirror into other ranks' rows: [source rows][receiver rows] in the owner's window
+            const int nst = ncp < strotss_ctx::kCommStreams ? ncp : strotss_ctx::kCommStreams;
+            for (int c = 0; c < nst; ++c) CK(cudaStreamWaitEvent(h->comm_st[c], ev_job[k], 0));
+            for (int c = 0; c < ncp; ++c) {
+                bf16* dst = static_cast<bf16*>(h->win_remote[cp[c].peer]) + cp[c].dst_off;
+                const bf16* src = P + static_cast<long long>(cp[c].i0 - jb.r0) * cw + (cp[c].j0 - jb.c0);
+                CK(cudaMemcpy2DAsync(dst, static_cast<size_t>(cp[c].ld) * sizeof(bf16), src, static_cast<size_t>(cw) * sizeof(bf16),
+                                     static_cast<size_t>(cp[c].j1 - cp[c].j0) * sizeof(bf16), cp[c].i1 - cp[c].i0,
+                                     cudaMemcpyDeviceToDevice, h->comm_st[c % nst]));
+            }
+            if (nst > copy_pending) copy_pending = nst;
+        }
+    }
+    for (int c = 0; c < copy_pending; ++c) CK(cudaEventRecord(ev_copied[c], h->comm_st[c]));
+    if (alt)
+        for (int k = 1; k < pl.njobs; k += 2) CK(cudaStreamWaitEvent(st, ev_job[k], 0));
+    for (int k = 0; k < pl.njobs; ++k) {
+        const SsJob jb = pl.job[k];
+        const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
+        const bf16* P = Pj[k];
         PhaseTimer _pt(h, PH_SS2, st);
         {   // ---- stage 2a: ss2[job rows] (+)= P . x^[job columns]  (+ for a trapezoid the transposed part left of the diagonal)
             GemmParams<EpiStoreTr<256>> q{};
@@ -1633,8 +1750,15 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
         // A rank enters this collective only after its copies into the peers' windows have completed, so leaving it means every
         // block destined for this rank has landed.  (The window is not overwritten early either: a peer starts the copies of its
         // next evaluation after this evaluation's last collective, which this rank enters after it has consumed the window.)
-        if (copy_pending) { CK(cudaStreamWaitEvent(st, ev_copied, 0)); copy_pending = false; }
+        if (copy_pending) RET(await_copies());
+        NCK(nccl().GroupStart());
         NCK(nccl().AllReduce(r_full, r_full, (size_t)N, kNcclFloat32, kNcclSum, h->nccl_comm, st));
+        if (best && nbest) {
+            NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
+            *best_reduced = true;
+        }
+        NCK(nccl().GroupEnd());
+        if (after_barrier) RET(after_barrier());
         if (!pwin) {
             NCK(nccl().GroupStart());
             size_t roff = 0;
@@ -1724,8 +1848,8 @@ int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) 
 //   allreduce-sum over the float block (partial column sums, self-similarity loss, v vector)
 int exchange(strotss_ctx* h, unsigned long long* best, size_t nbest, float* partials, size_t npartials, cudaStream_t st) {
     if (h->world <= 1 || !h->nccl_comm) return 0;
-    PhaseTimer _pt(h, PH_EXCHANGE, st);      // includes the wait for the slowest rank to arrive
-    NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
+    PhaseTimer _pt(h, (best && nbest) ? PH_EXCHANGE : PH_EXCHANGE2, st);      // includes the wait for the slowest rank to arrive
+    if (best && nbest) NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
     NCK(nccl().AllReduce(partials, partials, npartials, kNcclFloat32, kNcclSum, h->nccl_comm, st));
     return 0;
 }
@@ -1883,6 +2007,8 @@ int strotss_comm_init(strotss_handle h, int rank, int world, const char* id128) 
     return 0;
 }
 
+int strotss_comm_transport(strotss_handle h) { return (h && h->world > 1 && h->nccl_comm) ? h->win_state : 0; }
+
 int strotss_shard_rows(strotss_handle h, int N, int* row_begin, int* row_end) {
     RET(check_handle(h));
     if (N <= 0 || !row_begin || !row_end) { h->err = "shard_rows: bad argument"; return STROTSS_ERR_ARG; }
@@ -1967,7 +2093,10 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaEventRecord(h->ev_join, s_pal));
     }
 
-    if (with_content && prep3_usable(pred, ld_pred, content, ld_content, D, Dp)) {
+    const bool prep3 = with_content && prep3_usable(pred, ld_pred, content, ld_content, D, Dp);
+    ShardSym ssym;
+    if (exch && want_grad && with_content) RET(shard_sym_setup(h, N, D, Dp, sh, prep3, st, ssym));
+    if (prep3) {
         RET(prep_pred_content3(h, fp, fc, pred, content, N, D, Dp, Shard{0, N}, st));
     } else if (with_content && Dp <= 2560) {
         RET(prep_pred_content(h, fp, fc, pred, ld_pred, content, ld_content, N, D, Dp, want_grad, st));
@@ -1994,12 +2123,17 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         RET(remd_finish(h, h->style, M, N, sh, D, rs, ry_remd, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, s_aux));
     if (par) CK(cudaEventRecord(h->ev_join2, s_aux));
-    RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_mom, mom_part));
+    if (ssym.cov) RET(cov_sharded_scatter(h, fp, sh, D, Dp, ssym, st));
+    else RET(moments(h, h->style.mean, h->Vx, fp, N, sh, D, Dp, scalars, want_grad, mo, s_mom, mom_part));
     if (par) CK(cudaEventRecord(h->ev_join3, s_mom));
+    bool best_reduced = false;
     if (with_content) {
         int rc = 1;
         if (exch && want_grad) {
-            rc = self_sim_sharded_sym(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, so, st);
+            std::function<int()> owner_step;
+            if (ssym.cov) owner_step = [&]() { return cov_sharded_owner(h, h->Vx, N, D, Dp, ssym, partials + PS_COV_L1, st); };
+            rc = self_sim_sharded_sym(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, so, st, best, (size_t)2 * M,
+                                      &best_reduced, ssym, owner_step);
             if (rc < 0) return rc;
         }
         if (rc == 1) RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
@@ -2009,7 +2143,8 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
         CK(cudaStreamWaitEvent(st, h->ev_join3, 0));
     } else {
-        if (sharded) RET(exchange(h, best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
+        if (sharded) RET(exchange(h, best_reduced ? nullptr : best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
+        if (ssym.cov) RET(cov_sharded_finish(h, h->style.mean, fp, N, sh, D, Dp, ssym, partials + PS_COV_L1, scalars, want_grad, mo, st));
         RET(remd_finish(h, h->style, M, N, sh, D, rs, ry_remd, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, st));
         RET(pal_finish(h, h->style.rec, M, fp.rec, N, sh, STROTSS_DIST_BOTH, 1, ps, ry_pal, scalars, S_LPAL, S_PAL_RX,

@@ -326,6 +326,40 @@ struct EpiStoreTr {
     }
 };
 
+// ---- partial Gram tile -> the window slot of the rank that owns the tile (row-sharded covariance) ----------
+// Symmetric product over THIS rank's rows only (triangular tile walk): tile number lt of the upper block triangle belongs to
+// rank lt % world and is stored whole -- 256 x 256 fp32, transposed, phantom rows/columns are zeros -- as slot lt / world of
+// this sender's slot array in the owner's peer window (base[owner]; plain stores to a CUDA-IPC mapped pointer, NVLink for a
+// remote owner).
+template <int BN>
+struct EpiGramScatter {
+    static constexpr int SMEM_BYTES = 0;
+    static constexpr int kMaxRanks = 16;
+    struct Params { float* base[kMaxRanks]; int world; int tiles; };      // tiles: 256-wide tiles per side of the matrix
+    struct State {};
+    __device__ static void init(State&, const Params&, int, int) {}
+    __device__ static void prologue(State&, const Params&, const TileInfo&, uint8_t*) {}
+    __device__ static void finish(State&, const Params&, int, int) {}
+    __device__ static void run(State&, const Params& P, const TileInfo& ti, uint8_t*) {
+        static_assert(BN == 256, "256 x 256 tiles");
+        const int tm2 = ti.tm >> 1;                                    // ti.tm counts 128-row blocks
+        const int lt = tm2 * P.tiles - tm2 * (tm2 - 1) / 2 + (ti.tn - tm2);
+        const int owner = lt % P.world, slot = lt / P.world;
+        // the slot holds the tile TRANSPOSED (slot[col][row]; the matrix is symmetric, so that is its mirror tile): for a fixed
+        // accumulator column the 32 lanes of a warp -- 32 consecutive rows -- then write one full 128-byte line, which is what a
+        // remote (NVLink) store wants; row-major slots would send 32 partial sectors per instruction
+        float* dst = P.base[owner] + static_cast<long long>(slot) * (256 * 256) + ((ti.tm & 1) * 128 + ti.q * 32 + ti.lane);
+#pragma unroll 1
+        for (int c = ti.c0; c < ti.c1; ++c) {
+            uint32_t r[32];
+            tmem_ld32(ti.taddr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dst[(c * 32 + e) * 256] = __uint_as_float(r[e]);
+        }
+    }
+};
+
 // ---- relaxed EMD: best (max dot = min cosine distance) per A row and per B row ---------
 // A rows = target/style samples i (M of them), B rows = prediction samples j (N of them).
 // rowbest[i] = max_j (dot_ij, lowest j on ties);  colbest[j] = max_i (dot_ij, lowest i on ties).

@@ -892,6 +892,99 @@ __global__ void __launch_bounds__(256) ss2_add_kernel(const Ss2AddArgs a) {
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Row-sharded covariance, owner side: tile number lt = j * world + rank of the upper block triangle belongs to this rank.
+// Its g partial sums (one per sender, written by EpiGramScatter into this rank's window) are added in rank order, turned into
+// V - Vx, |.| partial sums (off-diagonal tiles count twice) and the sign matrix, which is stored -- the tile and, right of the
+// diagonal, its mirror image -- into the Sg buffer of EVERY rank (peer-mapped pointers).  One block per 64 x 64 sub-tile.
+// --------------------------------------------------------------------------------------
+constexpr int kCovMaxRanks = 16;
+struct CovOwnArgs {
+    const float* slots;                    // [world][nslots][256 * 256]
+    int world, rank, nslots, tiles;        // tiles: 256-wide tiles per side
+    const float* Vx; long long ldv; float inv_n; int D;
+    __nv_bfloat16* sg[kCovMaxRanks]; long long lds;
+    float* part;                           // [gridDim.x]
+};
+__global__ void __launch_bounds__(256) cov_owner_kernel(const CovOwnArgs a) {
+    pdl_wait();
+    __shared__ __nv_bfloat16 sgn[64][72];
+    __shared__ float red[8];
+    const int j = blockIdx.x >> 4, sub = blockIdx.x & 15;
+    int lt = j * a.world + a.rank;
+    const int ntri = a.tiles * (a.tiles + 1) / 2;
+    if (lt >= ntri) { if (threadIdx.x == 0) a.part[blockIdx.x] = 0.f; return; }
+    // upper-triangle tile (ut, ut + lt); its slot holds the TRANSPOSED tile, i.e. the lower-triangle tile (tm, tn) = (ut + lt, ut)
+    // of the symmetric matrix, row-major -- that is the tile this block works on; `mirror` below then writes the upper one
+    int ut = 0;
+    while (lt >= a.tiles - ut) { lt -= a.tiles - ut; ++ut; }
+    const int tm = ut + lt, tn = ut;
+    const int sr = sub >> 2, sc = sub & 3;
+    const int c4 = (threadIdx.x & 15) * 4;
+    float l1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = (threadIdx.x >> 4) + 16 * i;
+        const long long off = static_cast<long long>(j) * 65536 + (sr * 64 + r) * 256 + sc * 64 + c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < a.world; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(a.slots + static_cast<long long>(s) * a.nslots * 65536 + off);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const int grow = tm * 256 + sr * 64 + r, gcol = tn * 256 + sc * 64 + c4;
+        const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float sv = 0.f;
+            if (grow < a.D && gcol + e < a.D) {
+                const float d = fmaf(av[e], a.inv_n, -a.Vx[static_cast<long long>(grow) * a.ldv + gcol + e]);
+                l1 += fabsf(d);
+                sv = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+            }
+            sgn[r][c4 + e] = __float2bfloat16(sv);
+        }
+    }
+    __syncthreads();
+    const bool mirror = tn != tm;
+    for (int q = 0; q < a.world; ++q) {
+        __nv_bfloat16* S = a.sg[q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = (threadIdx.x >> 4) + 16 * i;
+            {   // the tile itself: row grow, columns gcol .. gcol + 3
+                const int grow = tm * 256 + sr * 64 + r, gcol = tn * 256 + sc * 64 + c4;
+                if (grow < a.D) {
+                    __nv_bfloat16* dst = S + static_cast<long long>(grow) * a.lds + gcol;
+                    if (gcol + 3 < a.D) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(&sgn[r][c4]);
+                    else for (int e = 0; e < 4; ++e) if (gcol + e < a.D) dst[e] = sgn[r][c4 + e];
+                }
+            }
+            if (mirror) {   // mirror image: row = a column of the tile, 4 consecutive tile rows along it
+                const int mrow = tn * 256 + sc * 64 + r, mcol = tm * 256 + sr * 64 + c4;
+                if (mrow < a.D) {
+                    __nv_bfloat16* dst = S + static_cast<long long>(mrow) * a.lds + mcol;
+                    if (mcol + 3 < a.D) {
+                        __nv_bfloat16 v[4] = {sgn[c4][r], sgn[c4 + 1][r], sgn[c4 + 2][r], sgn[c4 + 3][r]};
+                        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(v);
+                    } else {
+                        for (int e = 0; e < 4; ++e) if (mcol + e < a.D) dst[e] = sgn[c4 + e][r];
+                    }
+                }
+            }
+        }
+    }
+    if (mirror) l1 *= 2.f;
+    l1 = warp_sum(l1);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k];
+        a.part[blockIdx.x] = t;
+    }
+}
+
 // out[slot] = scale * sum_i in[i]      (single block, fixed order)
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out) {
     pdl_wait();

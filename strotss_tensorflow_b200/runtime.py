@@ -98,6 +98,20 @@ class Handle:
         self._ck(self.lib.strotss_shard_rows(self._h, int(N), C.byref(r0), C.byref(r1)), "strotss_shard_rows")
         return r0.value, r1.value
 
+    def comm_transport(self) -> int:
+        """1: sign blocks through CUDA-IPC peer windows, -1: fp32 products through ncclSend/ncclRecv, 0: undecided / single GPU."""
+        return int(self.lib.strotss_comm_transport(self._h))
+
+    def collectives_note(self, M: int, D: int) -> str:
+        t = self.comm_transport()
+        small = (f"NCCL per evaluation: one group of allreduce-sum over N floats (r) + allreduce-max over 2x{M} packed u64 minima, "
+                 f"one allreduce-sum of {16 + D} floats")
+        if t == 1:
+            return small + "; mirrored self-similarity tiles: bf16 sign blocks by copy engine into CUDA-IPC peer windows (no NCCL)"
+        if t == -1:
+            return small + "; mirrored self-similarity tiles: fp32 products by ncclSend/ncclRecv (peer windows unavailable)"
+        return small
+
     def profile_enable(self, on: bool = True):
         self._ck(self.lib.strotss_profile_enable(self._h, 1 if on else 0), "strotss_profile_enable")
 
