@@ -1676,12 +1676,13 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     for (int c = 0; c < copy_pending; ++c) CK(cudaEventRecord(ev_copied[c], h->comm_st[c]));
     if (alt)
         for (int k = 1; k < pl.njobs; k += 2) CK(cudaStreamWaitEvent(st, ev_job[k], 0));
+    bool merged2a[kSsJobsMax] = {};      // rectangular jobs over the same rows as a trapezoid job ride in its stage-2a launch
     for (int k = 0; k < pl.njobs; ++k) {
         const SsJob jb = pl.job[k];
         const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
         const bf16* P = Pj[k];
         PhaseTimer _pt(h, PH_SS2, st);
-        {   // ---- stage 2a: ss2[job rows] (+)= P . x^[job columns]  (+ for a trapezoid the transposed part left of the diagonal)
+        if (!merged2a[k]) {   // ---- stage 2a: ss2[job rows] (+)= P . x^[job columns]  (+ for a trapezoid the transposed part left of the diagonal)
             GemmParams<EpiStoreTr<256>> q{};
             if (amn) RET(make_tmap_mn(h, &q.tmA[0], x.xh + static_cast<long long>(jb.c0) * Dp, D, cw, Dp));
             else RET(make_tmap(h, &q.tmA[0], x.xhT + jb.c0, D, cw, np, BM));
@@ -1698,6 +1699,17 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
                 RET(make_tmap_mn(h, &q.tmB[1], P, rows, rows, cw));
                 q.nseg = 2; q.seg_kblocks[1] = (rows + BK - 1) / BK; q.seg_acc[1] = 0;
                 q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
+                for (int j = k + 1; j < pl.njobs && q.nseg < kMaxSeg; ++j) {
+                    const SsJob o = pl.job[j];
+                    if (o.diag || o.r0 != jb.r0 || o.r1 != jb.r1) continue;
+                    const int ocw = o.c1 - o.c0;
+                    if (amn) RET(make_tmap_mn(h, &q.tmA[q.nseg], x.xh + static_cast<long long>(o.c0) * Dp, D, ocw, Dp));
+                    else RET(make_tmap(h, &q.tmA[q.nseg], x.xhT + o.c0, D, ocw, np, BM));
+                    RET(make_tmap(h, &q.tmB[q.nseg], Pj[j], rows, ocw, ocw, 128));
+                    q.seg_kblocks[q.nseg] = ocw / BK; q.seg_acc[q.nseg] = 0;
+                    ++q.nseg;
+                    merged2a[j] = true;
+                }
                 if (wide) {
                     q.tiles_n = (rows + 511) / 512;
                     if (amn) RET((launch_gemm256w<2, 1>(h, q, st))); else RET((launch_gemm256w<2>(h, q, st)));
@@ -2097,7 +2109,8 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     ShardSym ssym;
     if (exch && want_grad && with_content) RET(shard_sym_setup(h, N, D, Dp, sh, prep3, st, ssym));
     if (prep3) {
-        RET(prep_pred_content3(h, fp, fc, pred, content, N, D, Dp, Shard{0, N}, st));
+        // the centred operand is only read for this rank's rows once the covariance forward is row-sharded as well
+        RET(prep_pred_content3(h, fp, fc, pred, content, N, D, Dp, ssym.cov ? sh : Shard{0, N}, st));
     } else if (with_content && Dp <= 2560) {
         RET(prep_pred_content(h, fp, fc, pred, ld_pred, content, ld_content, N, D, Dp, want_grad, st));
     } else if (with_content) {
