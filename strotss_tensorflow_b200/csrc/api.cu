@@ -195,6 +195,7 @@ struct strotss_ctx {
     void* win_local = nullptr; size_t win_bytes = 0;
     std::vector<void*> win_remote;       // [world]; own entry = win_local
     int win_state = 0;                   // 0 untried, 1 usable, -1 unavailable (IPC refused): fall back to the product exchange
+    unsigned long long ar_epoch = 0;     // collectives done through the windows (peer_allreduce); the same on every rank
     static constexpr int kCommStreams = 4;
     cudaStream_t comm_st[kCommStreams] = {nullptr, nullptr, nullptr, nullptr};      // copies into peer windows, one stream per destination in flight
     // optional per-phase CUDA-event timing
@@ -1473,6 +1474,8 @@ struct ShardSym {
     int panel = 0;
     size_t off_gram = 0, off_sg = 0;
     int gram_tiles = 0, gram_slots = 0;
+    bool ar = false;           // small allreduces through the windows as well (peer_allreduce) instead of NCCL
+    size_t off_ar = 0, ar_slot = 0, off_flags = 0;
 };
 
 int shard_sym_setup(strotss_ctx* h, int N, int D, int Dp, Shard sh, bool prep3, cudaStream_t st, ShardSym& ss) {
@@ -1497,10 +1500,47 @@ int shard_sym_setup(strotss_ctx* h, int N, int D, int Dp, Shard sh, bool prep3, 
     const bool want_cov = !cov_off && h->world <= EpiGramScatter<256>::kMaxRanks;
     const size_t gram_bytes = want_cov ? static_cast<size_t>(h->world) * ss.gram_slots * 65536 * sizeof(float) : 0;
     ss.off_sg = ss.off_gram + gram_bytes;
-    const size_t total = ss.off_sg + (want_cov ? static_cast<size_t>(Dp) * Dp * sizeof(bf16) : 0);
+    static const bool ar_off = getenv("STROTSS_PEER_AR") && atoi(getenv("STROTSS_PEER_AR")) == 0;
+    const bool want_ar = !ar_off && h->world <= kArMaxRanks;
+    ss.off_ar = (ss.off_sg + (want_cov ? static_cast<size_t>(Dp) * Dp * sizeof(bf16) : 0) + 1023) / 1024 * 1024;
+    // largest payload: r (N floats) + the packed minima (2 M u64); the (16 + D)-float block is smaller
+    size_t pay = (static_cast<size_t>(N) * 4 + 15) / 16 * 16 + static_cast<size_t>(2) * h->M * 8;
+    const size_t pay2 = static_cast<size_t>(PS_V + D) * 4 + 16;
+    if (pay2 > pay) pay = pay2;
+    ss.ar_slot = (pay + 255) / 256 * 256;
+    ss.off_flags = ss.off_ar + (want_ar ? 2 * static_cast<size_t>(h->world) * ss.ar_slot : 0);
+    const size_t total = ss.off_flags + (want_ar ? 256 : 0);
     RET(peer_window_ensure(h, total, st));
     ss.pwin = (h->win_state == 1);
     ss.cov = ss.pwin && want_cov;
+    ss.ar = ss.pwin && want_ar;
+    return 0;
+}
+
+// One-shot allreduce through the windows (peer_allreduce_kernel): f[nf] summed, u[nu] maximised, in place, identical on all ranks.
+// Like an NCCL collective it is a barrier in stream order: a rank's flags go out after its earlier work on `st`, and it returns
+// after every rank's flags have arrived.
+int peer_allreduce(strotss_ctx* h, const ShardSym& ss, float* f, size_t nf, unsigned long long* u, size_t nu, cudaStream_t st) {
+    unsigned int* counter;
+    RET(ensure(h, "comm.arcnt", (size_t)1, &counter, /*zero_on_alloc=*/true));
+    const unsigned long long epoch = ++h->ar_epoch;
+    const size_t parity_off = ss.off_ar + (epoch & 1) * static_cast<size_t>(h->world) * ss.ar_slot;
+    PeerArArgs a{};
+    for (int q = 0; q < h->world; ++q) {
+        unsigned char* base = static_cast<unsigned char*>(h->win_remote[q]);
+        a.push[q] = base + parity_off + static_cast<size_t>(h->rank) * ss.ar_slot;
+        a.flag_out[q] = reinterpret_cast<unsigned long long*>(base + ss.off_flags) + h->rank;
+    }
+    a.slots = static_cast<unsigned char*>(h->win_local) + parity_off;
+    a.flags_in = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(h->win_local) + ss.off_flags);
+    a.slot_bytes = static_cast<long long>(ss.ar_slot); a.world = h->world; a.rank = h->rank; a.epoch = epoch;
+    a.f = f; a.nf = static_cast<long long>(nf); a.u = u; a.nu = static_cast<long long>(nu); a.counter = counter;
+    const size_t bytes = nf * 4 + nu * 8;
+    int grid = static_cast<int>((bytes + 16 * 256 - 1) / (16 * 256));
+    if (grid < 1) grid = 1;
+    if (grid > 64) grid = 64;                 // all blocks must be resident at once: they wait for each other's flags
+    KL(peer_allreduce_kernel, grid, 256, 0, st, a);
+    CKL();
     return 0;
 }
 
@@ -1583,10 +1623,19 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     // partially filled last round of one persistent launch is filled by the first tiles of the next (a rank of the upper half of
     // an even world has three jobs -- 164 + 64 + 32 tiles at 8 GPUs: 5 rounds of 74 CTA pairs one after another, 3.5 overlapped);
     // the copies into the peer windows start behind each job and run under everything that follows.
+    // A rectangular job over the LOWER part of a trapezoid job's rows (the half block of an upper-half rank) gets a buffer as tall
+    // as the trapezoid job, its missing top rows zeroed: it then rides in that job's stage-2a launch like the other rectangles
+    // (a few K blocks of zeros cost less than one more launch).  pad[k] = rows above the job inside its buffer.
     bf16* Pj[kSsJobsMax];
+    int pad[kSsJobsMax] = {};
     for (int k = 0; k < pl.njobs; ++k) {
+        const SsJob& jb = pl.job[k];
+        if (pwin && !jb.diag)
+            for (int d = 0; d < k; ++d)
+                if (pl.job[d].diag && pl.job[d].r1 == jb.r1 && pl.job[d].r0 < jb.r0) pad[k] = jb.r0 - pl.job[d].r0;
         const std::string nm = "ss.P" + std::to_string(k);
-        RET(ensure(h, nm.c_str(), (size_t)(pl.job[k].r1 - pl.job[k].r0) * (pl.job[k].c1 - pl.job[k].c0), &Pj[k]));
+        RET(ensure(h, nm.c_str(), (size_t)(jb.r1 - jb.r0 + pad[k]) * (jb.c1 - jb.c0), &Pj[k]));
+        if (pad[k]) CK(cudaMemsetAsync(Pj[k], 0, (size_t)pad[k] * (jb.c1 - jb.c0) * sizeof(bf16), st));
     }
     if (!pwin) RET(ensure(h, "ss.recv", recv_rows * Dp, &recvbuf));
     static PerDeviceOnce configured;
@@ -1630,7 +1679,7 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     for (int k = 0; k < pl.njobs; ++k) {
         const SsJob jb = pl.job[k];
         const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
-        bf16* P = Pj[k];
+        bf16* P = Pj[k] + static_cast<long long>(pad[k]) * cw;
         cudaStream_t sk = (alt && (k & 1)) ? h->aux : st;
         {   // ---- stage 1: P[rows][cw] (bf16), loss / r partials
             Ss1Params sp{};
@@ -1680,7 +1729,7 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     for (int k = 0; k < pl.njobs; ++k) {
         const SsJob jb = pl.job[k];
         const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
-        const bf16* P = Pj[k];
+        const bf16* P = Pj[k] + static_cast<long long>(pad[k]) * cw;
         PhaseTimer _pt(h, PH_SS2, st);
         if (!merged2a[k]) {   // ---- stage 2a: ss2[job rows] (+)= P . x^[job columns]  (+ for a trapezoid the transposed part left of the diagonal)
             GemmParams<EpiStoreTr<256>> q{};
@@ -1701,7 +1750,7 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
                 q.kb_hi_mul[1] = 256 / BK; q.seg_bmn[1] = 1;
                 for (int j = k + 1; j < pl.njobs && q.nseg < kMaxSeg; ++j) {
                     const SsJob o = pl.job[j];
-                    if (o.diag || o.r0 != jb.r0 || o.r1 != jb.r1) continue;
+                    if (o.diag || o.r0 - pad[j] != jb.r0 || o.r1 != jb.r1) continue;
                     const int ocw = o.c1 - o.c0;
                     if (amn) RET(make_tmap_mn(h, &q.tmA[q.nseg], x.xh + static_cast<long long>(o.c0) * Dp, D, ocw, Dp));
                     else RET(make_tmap(h, &q.tmA[q.nseg], x.xhT + o.c0, D, ocw, np, BM));
@@ -1763,13 +1812,18 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
         // block destined for this rank has landed.  (The window is not overwritten early either: a peer starts the copies of its
         // next evaluation after this evaluation's last collective, which this rank enters after it has consumed the window.)
         if (copy_pending) RET(await_copies());
-        NCK(nccl().GroupStart());
-        NCK(nccl().AllReduce(r_full, r_full, (size_t)N, kNcclFloat32, kNcclSum, h->nccl_comm, st));
-        if (best && nbest) {
-            NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
-            *best_reduced = true;
+        if (ssym.ar) {
+            RET(peer_allreduce(h, ssym, r_full, (size_t)N, best, best ? nbest : 0, st));
+            if (best && nbest) *best_reduced = true;
+        } else {
+            NCK(nccl().GroupStart());
+            NCK(nccl().AllReduce(r_full, r_full, (size_t)N, kNcclFloat32, kNcclSum, h->nccl_comm, st));
+            if (best && nbest) {
+                NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
+                *best_reduced = true;
+            }
+            NCK(nccl().GroupEnd());
         }
-        NCK(nccl().GroupEnd());
         if (after_barrier) RET(after_barrier());
         if (!pwin) {
             NCK(nccl().GroupStart());
@@ -1858,9 +1912,11 @@ int finalize(strotss_ctx* h, const FinalizeArgs& a, int nrows, cudaStream_t st) 
 // One exchange per evaluation when the handle is attached to a communicator:
 //   allreduce-max over the packed (value, ~index) bests of the target rows (relaxed EMD + palette, 2*M u64)
 //   allreduce-sum over the float block (partial column sums, self-similarity loss, v vector)
-int exchange(strotss_ctx* h, unsigned long long* best, size_t nbest, float* partials, size_t npartials, cudaStream_t st) {
+int exchange(strotss_ctx* h, unsigned long long* best, size_t nbest, float* partials, size_t npartials, cudaStream_t st,
+             const ShardSym* ss = nullptr) {
     if (h->world <= 1 || !h->nccl_comm) return 0;
     PhaseTimer _pt(h, (best && nbest) ? PH_EXCHANGE : PH_EXCHANGE2, st);      // includes the wait for the slowest rank to arrive
+    if (ss && ss->ar) return peer_allreduce(h, *ss, partials, npartials, best, best ? nbest : 0, st);
     if (best && nbest) NCK(nccl().AllReduce(best, best, nbest, kNcclUint64, kNcclMax, h->nccl_comm, st));
     NCK(nccl().AllReduce(partials, partials, npartials, kNcclFloat32, kNcclSum, h->nccl_comm, st));
     return 0;
@@ -2156,7 +2212,7 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
         CK(cudaStreamWaitEvent(st, h->ev_join3, 0));
     } else {
-        if (sharded) RET(exchange(h, best_reduced ? nullptr : best, (size_t)2 * M, partials, (size_t)PS_V + D, st));
+        if (sharded) RET(exchange(h, best_reduced ? nullptr : best, (size_t)2 * M, partials, (size_t)PS_V + D, st, &ssym));
         if (ssym.cov) RET(cov_sharded_finish(h, h->style.mean, fp, N, sh, D, Dp, ssym, partials + PS_COV_L1, scalars, want_grad, mo, st));
         RET(remd_finish(h, h->style, M, N, sh, D, rs, ry_remd, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, st));

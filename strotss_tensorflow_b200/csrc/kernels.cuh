@@ -985,6 +985,87 @@ __global__ void __launch_bounds__(256) cov_owner_kernel(const CovOwnArgs a) {
     }
 }
 
+// --------------------------------------------------------------------------------------
+// One-shot allreduce over the peer windows (row-sharded evaluation; replaces the small NCCL allreduces).  Every rank pushes its
+// payload -- nf floats to be summed, nu packed u64 keys to be maximised -- into ITS slot of every rank's window (plain 16-byte
+// stores to CUDA-IPC mapped pointers: NVLink for remote ranks), publishes a per-sender flag = epoch in every window
+// (st.release.sys after a system-scope fence), waits until all senders' flags in its own window have reached the epoch
+// (ld.acquire.sys, bounded spin -> trap, never a hang) and reduces the world slots in rank order -- the sum is bit-identical on
+// all ranks and from run to run.  Slots are double-buffered by epoch parity: a sender can only be one collective ahead of the
+// slowest rank, because finishing collective e needs every rank's flag e.
+// --------------------------------------------------------------------------------------
+constexpr int kArMaxRanks = 16;
+struct PeerArArgs {
+    unsigned char* push[kArMaxRanks];             // this rank's slot in rank q's window (current parity)
+    unsigned long long* flag_out[kArMaxRanks];    // this rank's flag in rank q's window
+    const unsigned char* slots;                   // own window: [world] slots of the current parity
+    const unsigned long long* flags_in;           // own window: [world] flags
+    long long slot_bytes;
+    int world, rank;
+    unsigned long long epoch;
+    float* f; long long nf;                       // summed in place
+    unsigned long long* u; long long nu;          // maximised in place
+    unsigned int* counter;                        // zero between calls
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const PeerArArgs a) {
+    pdl_wait();
+    __shared__ bool last;
+    const long long fbytes = (a.nf * 4 + 15) / 16 * 16;              // the u64 part starts 16-byte aligned
+    const long long nf4 = a.nf / 4, nu2 = a.nu / 2;
+    const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+    // ---- push
+    for (int q = 0; q < a.world; ++q) {
+        float4* df = reinterpret_cast<float4*>(a.push[q]);
+        const float4* sf = reinterpret_cast<const float4*>(a.f);
+        for (long long i = gtid; i < nf4; i += gsz) df[i] = sf[i];
+        for (long long i = nf4 * 4 + gtid; i < a.nf; i += gsz) reinterpret_cast<float*>(a.push[q])[i] = a.f[i];
+        ulonglong2* du = reinterpret_cast<ulonglong2*>(a.push[q] + fbytes);
+        const ulonglong2* su = reinterpret_cast<const ulonglong2*>(a.u);
+        for (long long i = gtid; i < nu2; i += gsz) du[i] = su[i];
+        for (long long i = nu2 * 2 + gtid; i < a.nu; i += gsz) reinterpret_cast<unsigned long long*>(a.push[q] + fbytes)[i] = a.u[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < a.world) st_release_sys(a.flag_out[threadIdx.x], a.epoch);
+        if (threadIdx.x == 0) *a.counter = 0;
+    }
+    // ---- wait for every sender
+    if (threadIdx.x < a.world) {
+        unsigned int spins = 0;
+        while (ld_acquire_sys(a.flags_in + threadIdx.x) < a.epoch) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();                      // ~ seconds: a rank died or the protocol is broken
+        }
+    }
+    __syncthreads();
+    // ---- reduce in rank order
+    for (long long i = gtid; i < a.nf; i += gsz) {
+        float acc = 0.f;
+        for (int q = 0; q < a.world; ++q) acc += reinterpret_cast<const float*>(a.slots + q * a.slot_bytes)[i];
+        a.f[i] = acc;
+    }
+    for (long long i = gtid; i < a.nu; i += gsz) {
+        unsigned long long m = 0;
+        for (int q = 0; q < a.world; ++q) {
+            const unsigned long long v = reinterpret_cast<const unsigned long long*>(a.slots + q * a.slot_bytes + fbytes)[i];
+            m = v > m ? v : m;
+        }
+        a.u[i] = m;
+    }
+}
+
 // out[slot] = scale * sum_i in[i]      (single block, fixed order)
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ in, int n, float scale, float* __restrict__ out) {
     pdl_wait();
