@@ -1264,7 +1264,9 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
         p.a_row0 = r0; p.b_row0 = c0;
         p.epi.u = u; p.epi.w = w; p.epi.P = P; p.epi.ldp = np; p.epi.panel_row0 = r0;
         p.epi.loss_part = loss_part; p.epi.r_part = r_part; p.epi.N = N; p.epi.row_end = sh.r1;
-        p.epi.write_p = (want_grad ? 1 : 0);
+        // STROTSS_P_STREAM=1 (experiment): the panel leaves with st.global.cs so that it is the first thing the L2 evicts
+        static const int p_stream = (getenv("STROTSS_P_STREAM") && atoi(getenv("STROTSS_P_STREAM")) != 0) ? 2 : 1;
+        p.epi.write_p = (want_grad ? p_stream : 0);
         p.epi.sym = sym ? 1 : 0; p.epi.panel_end = r0 + panel; p.epi.rcol_part = rcol_part;
         if (small) {
             RET(ss1_small(h, x, y, N, Dp, r0, c0, rows, p.epi, st));
@@ -1441,7 +1443,7 @@ int self_sim_local(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh
             // v = sum_i coef_i x^_i: from the bf16 x^ rows (half the bytes of x; the rounding errors of 16384 rows average out)
             static const bool v_fp32 = (getenv("STROTSS_V_FP32") != nullptr);
             if (x.xh && !v_fp32)
-                KL(weighted_colsum_bf16_kernel, nblk, 256, 0, st, x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
+                KL(weighted_colsum_bf16_kernel, dim3(nblk, (D + 1023) / 1024), 256, 0, st, x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
             else
                 KL(weighted_colsum_kernel, nblk, 256, 0, st, x.x + static_cast<long long>(sh.r0) * x.ld, x.ld, sh.n(), D, x.inv + sh.r0,
                                                              out.coef + sh.r0, vpart, rpb);
@@ -1892,7 +1894,7 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
     const int nblk = (sh.n() + rpb - 1) / rpb;
     float* vpart;
     RET(ensure(h, "ss.vpart", (size_t)nblk * D, &vpart));
-    KL(weighted_colsum_bf16_kernel, nblk, 256, 0, st, x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
+    KL(weighted_colsum_bf16_kernel, dim3(nblk, (D + 1023) / 1024), 256, 0, st, x.xh + static_cast<long long>(sh.r0) * Dp, Dp, sh.n(), D, out.coef + sh.r0, vpart, rpb);
     CKL();
     KL(colsum_finish_kernel, (D + 31) / 32, 256, 0, st, vpart, nblk, D, 1.f, v_partial);
     CKL();

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __res
     }
 }
 
-// the same from the normalised bf16 rows: part[b][d] = sum_{r in block b} coef[r] * xh[r][d]   (two columns per thread)
+// the same from the normalised bf16 rows: part[b][d] = sum_{r in block b} coef[r] * xh[r][d].  Four columns per thread (8-byte
+// loads, eight rows in flight), blockIdx.y picks a chunk of 1024 columns; the rows hold Dp >= D zero-padded columns (Dp % 4 == 0).
 __global__ void __launch_bounds__(256) weighted_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ xh, long long ld, int n, int D,
                                                                    const float* __restrict__ coef, float* __restrict__ part, int rpb) {
     pdl_wait();
@@ -94,17 +95,24 @@ __global__ void __launch_bounds__(256) weighted_colsum_bf16_kernel(const __nv_bf
     }
     __syncthreads();
     const int rows = min(rpb, n - r0);
-    for (int d = 2 * threadIdx.x; d < D; d += 2 * blockDim.x) {
-        float a0 = 0.f, a1 = 0.f;
+    const int d = blockIdx.y * 1024 + 4 * threadIdx.x;
+    if (d >= D) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const __nv_bfloat16* src = xh + static_cast<long long>(r0) * ld + d;
 #pragma unroll 8
-        for (int rr = 0; rr < rows; ++rr) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xh + static_cast<long long>(r0 + rr) * ld + d);
-            a0 = fmaf(__low2float(v), s_w[rr], a0);
-            a1 = fmaf(__high2float(v), s_w[rr], a1);
-        }
-        part[static_cast<long long>(blockIdx.x) * D + d] = a0;
-        if (d + 1 < D) part[static_cast<long long>(blockIdx.x) * D + d + 1] = a1;
+    for (int rr = 0; rr < rows; ++rr) {
+        const uint2 v = *reinterpret_cast<const uint2*>(src + static_cast<long long>(rr) * ld);
+        const float w = s_w[rr];
+        a0 = fmaf(__uint_as_float(v.x << 16), w, a0);
+        a1 = fmaf(__uint_as_float(v.x & 0xffff0000u), w, a1);
+        a2 = fmaf(__uint_as_float(v.y << 16), w, a2);
+        a3 = fmaf(__uint_as_float(v.y & 0xffff0000u), w, a3);
     }
+    float* dst = part + static_cast<long long>(blockIdx.x) * D + d;
+    dst[0] = a0;
+    if (d + 1 < D) dst[1] = a1;
+    if (d + 2 < D) dst[2] = a2;
+    if (d + 3 < D) dst[3] = a3;
 }
 
 // out[d] = scale * sum_b part[b][d]   (fixed order: 8 interleaved block groups, then a fixed tree)

@@ -348,8 +348,12 @@ __device__ __forceinline__ void ss1_body(const Ss1Params& p) {
                         }
                         packed[e2 >> 1] = pack_bf16x2(pv[0], pv[1]);
                     }
-                    if (pwrite)
-                        *reinterpret_cast<uint4*>(prow + (colbase - P.p_col0) + e8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    if (pwrite) {
+                        uint4* pdst = reinterpret_cast<uint4*>(prow + (colbase - P.p_col0) + e8);
+                        const uint4 pval = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        if (P.write_p == 2) __stcs(pdst, pval);      // experiment: streaming (evict-first) stores for the panel
+                        else *pdst = pval;
+                    }
                 }
                 if (both) {
                     // transpose-reduce: lane l ends with the sum over the warp's 32 rows of column l
