@@ -83,9 +83,12 @@ int strotss_profile_read(strotss_handle h, double* ms_sum, long long* counts);
  * Rank 0 creates an id with strotss_comm_unique_id (ncclGetUniqueId) and ships the 128 bytes to the
  * other ranks by any means (bench.py uses torch.distributed); every rank then calls strotss_comm_init.
  * Afterwards strotss_eval / strotss_eval_host compute rows [row_begin, row_end) of the prediction on
- * this rank (strotss_shard_rows), exchange ONE allreduce-max of the packed (value, index) minima of the
- * M style rows and ONE allreduce-sum of a (16 + D)-float block per evaluation over NCCL, write
- * identical scalars on every rank and only this rank's rows of grad_pred.  Inputs are replicated.
+ * this rank (strotss_shard_rows), write identical scalars on every rank and only this rank's rows of
+ * grad_pred.  Inputs are replicated.  Per evaluation the ranks exchange the packed (value, index) minima
+ * of the M style rows (max), N + 16 + D floats (sum) and -- for the symmetric self-similarity matrices
+ * (nn/losses.py:56-68) and the covariance (nn/losses.py:43-50), whose tiles are dealt out over the ranks --
+ * bf16 sign blocks and partial covariance tiles; with CUDA IPC available all of it moves through peer
+ * windows over NVLink (strotss_comm_transport), otherwise through NCCL allreduce / send / recv.
  * NCCL is loaded with dlopen("libnccl.so.2") at first use; the library itself does not link it. */
 int strotss_comm_unique_id(char* out128);
 int strotss_comm_init(strotss_handle h, int rank, int world, const char* id128);

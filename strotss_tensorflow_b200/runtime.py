@@ -104,13 +104,15 @@ class Handle:
 
     def collectives_note(self, M: int, D: int) -> str:
         t = self.comm_transport()
-        small = (f"NCCL per evaluation: one group of allreduce-sum over N floats (r) + allreduce-max over 2x{M} packed u64 minima, "
-                 f"one allreduce-sum of {16 + D} floats")
+        small = (f"two small collectives per evaluation: {{sum over N floats (r), max over 2x{M} packed u64 minima}} and a sum of "
+                 f"{16 + D} floats")
         if t == 1:
-            return small + "; mirrored self-similarity tiles: bf16 sign blocks by copy engine into CUDA-IPC peer windows (no NCCL)"
+            return (small + " -- one-shot allreduces through CUDA-IPC peer windows (peer stores + epoch flags over NVLink; "
+                    "STROTSS_PEER_AR=0: NCCL); mirrored self-similarity tiles: bf16 sign blocks by copy engine into the owners' "
+                    "windows; covariance forward: partial Gram tiles by epilogue peer stores, sign tiles back to every rank")
         if t == -1:
-            return small + "; mirrored self-similarity tiles: fp32 products by ncclSend/ncclRecv (peer windows unavailable)"
-        return small
+            return small + " (NCCL); mirrored self-similarity tiles: fp32 products by ncclSend/ncclRecv (peer windows unavailable)"
+        return small + " (NCCL)"
 
     def profile_enable(self, on: bool = True):
         self._ck(self.lib.strotss_profile_enable(self._h, 1 if on else 0), "strotss_profile_enable")
