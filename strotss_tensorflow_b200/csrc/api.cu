@@ -1599,7 +1599,8 @@ int cov_sharded_finish(strotss_ctx* h, const float* mu_x, const Feat& pred, int 
 // after_barrier (optional): work that needs every rank to have passed its earlier stream work (the covariance owner step).
 int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Shard sh, int D, int Dp, float* loss_partial,
                          float* v_partial, SsOut& out, cudaStream_t st, unsigned long long* best, size_t nbest, bool* best_reduced,
-                         const ShardSym& ssym, const std::function<int()>& after_barrier) {
+                         const ShardSym& ssym, const std::function<int()>& after_barrier, cudaEvent_t best_ready = nullptr,
+                         cudaEvent_t best_ready2 = nullptr) {
     if (!ssym.active || !x.u) return 1;
     const SsPlan& pl = ssym.pl;
     const bool amn = (x.xhT == nullptr);
@@ -1678,11 +1679,25 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
         CK(cudaEventRecord(ev_fork, st));
         CK(cudaStreamWaitEvent(h->aux, ev_fork, 0));
     }
-    for (int k = 0; k < pl.njobs; ++k) {
+    // launch order: largest job first, so that the short ones fill the CTA pairs its last round leaves idle
+    int order[kSsJobsMax];
+    auto job_tiles = [&](int k) {
+        const SsJob& j = pl.job[k];
+        const int tm = (j.r1 - j.r0) / 256, tn = (j.c1 - j.c0) / 256;
+        return j.diag ? tm * tn - tm * (tm - 1) / 2 : tm * tn;
+    };
+    for (int k = 0; k < pl.njobs; ++k) order[k] = k;
+    if (alt)
+        for (int a = 1; a < pl.njobs; ++a)
+            for (int b = a; b > 0 && job_tiles(order[b]) > job_tiles(order[b - 1]); --b) { const int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+    bool on_aux[kSsJobsMax] = {};
+    for (int pos = 0; pos < pl.njobs; ++pos) {
+        const int k = order[pos];
         const SsJob jb = pl.job[k];
         const int rows = jb.r1 - jb.r0, cw = jb.c1 - jb.c0;
         bf16* P = Pj[k] + static_cast<long long>(pad[k]) * cw;
-        cudaStream_t sk = (alt && (k & 1)) ? h->aux : st;
+        cudaStream_t sk = (alt && (pos & 1)) ? h->aux : st;
+        on_aux[k] = (sk != st);
         {   // ---- stage 1: P[rows][cw] (bf16), loss / r partials
             Ss1Params sp{};
             RET(make_tmap(h, &sp.tmA[0], y.xh, N, Dp, Dp, BM)); RET(make_tmap(h, &sp.tmB[0], y.xh, N, Dp, Dp, 128));      // y^ . y^T
@@ -1725,8 +1740,8 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
         }
     }
     for (int c = 0; c < copy_pending; ++c) CK(cudaEventRecord(ev_copied[c], h->comm_st[c]));
-    if (alt)
-        for (int k = 1; k < pl.njobs; k += 2) CK(cudaStreamWaitEvent(st, ev_job[k], 0));
+    for (int k = 0; k < pl.njobs; ++k)
+        if (on_aux[k]) CK(cudaStreamWaitEvent(st, ev_job[k], 0));
     bool merged2a[kSsJobsMax] = {};      // rectangular jobs over the same rows as a trapezoid job ride in its stage-2a launch
     for (int k = 0; k < pl.njobs; ++k) {
         const SsJob jb = pl.job[k];
@@ -1814,6 +1829,8 @@ int self_sim_sharded_sym(strotss_ctx* h, const Feat& x, const Feat& y, int N, Sh
         // block destined for this rank has landed.  (The window is not overwritten early either: a peer starts the copies of its
         // next evaluation after this evaluation's last collective, which this rank enters after it has consumed the window.)
         if (copy_pending) RET(await_copies());
+        if (best_ready) CK(cudaStreamWaitEvent(st, best_ready, 0));      // the relaxed-EMD GEMM / the palette search ran on side streams
+        if (best_ready2) CK(cudaStreamWaitEvent(st, best_ready2, 0));
         if (ssym.ar) {
             RET(peer_allreduce(h, ssym, r_full, (size_t)N, best, best ? nbest : 0, st));
             if (best && nbest) *best_reduced = true;
@@ -2152,20 +2169,30 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
     float* ry_remd = exch ? partials + PS_REMD_RY : nullptr;
     float* ry_pal = exch ? partials + PS_PAL_RY : nullptr;
     cudaStream_t s_pal = par ? h->side : st, s_aux = par ? h->aux : st, s_mom = par ? h->aux2 : st;
-    if (par) {
+    const bool prep3 = with_content && prep3_usable(pred, ld_pred, content, ld_content, D, Dp);
+    ShardSym ssym;
+    if (exch && want_grad && with_content) RET(shard_sym_setup(h, N, D, Dp, sh, prep3, st, ssym));
+    // Row-sharded symmetric path: the palette search (CUDA cores) and the relaxed-EMD GEMM run on side streams.  A shard's
+    // launches are short -- a few rounds of the 74 CTA pairs, the last one partially filled -- so what runs beside them fills
+    // SMs that would idle: the palette search hides under the HBM-bound row preparation, the relaxed-EMD CTA pairs start
+    // wherever a stage-1 launch runs out of tiles (8 GPUs: 924 -> 985 evals/s with the GEMM alone).  STROTSS_SHARD_SIDE=0: off.
+    static const bool shard_side_off = getenv("STROTSS_SHARD_SIDE") && atoi(getenv("STROTSS_SHARD_SIDE")) == 0;
+    // STROTSS_SIDE=1 (experiment): the same on a single GPU / unsharded large problems
+    static const bool solo_side = getenv("STROTSS_SIDE") && atoi(getenv("STROTSS_SIDE")) != 0;
+    const bool shard_side = !par && ((!shard_side_off && exch && ssym.active) || (solo_side && !exch && with_content && st != h->side && st != h->aux2));
+    if (shard_side) s_pal = h->aux2;
+    if (par || shard_side) {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(s_pal, h->ev_fork, 0));
     }
     RET(pal_local(h, h->style.srec, M, pal_srec, N, sh, STROTSS_DIST_BOTH, ps, ry_pal, s_pal, true));
+    if (shard_side) CK(cudaEventRecord(h->ev_join, s_pal));
     if (par) {
         RET(pal_finish(h, h->style.rec, M, pal_rec, N, sh, STROTSS_DIST_BOTH, 1, ps, ry_pal, scalars, S_LPAL, S_PAL_RX,
                        S_PAL_RY, S_PAL_BRANCH, want_grad, nullptr, nullptr, s_pal, pal_g));
         CK(cudaEventRecord(h->ev_join, s_pal));
     }
 
-    const bool prep3 = with_content && prep3_usable(pred, ld_pred, content, ld_content, D, Dp);
-    ShardSym ssym;
-    if (exch && want_grad && with_content) RET(shard_sym_setup(h, N, D, Dp, sh, prep3, st, ssym));
     if (prep3) {
         // the centred operand is only read for this rank's rows once the covariance forward is row-sharded as well
         RET(prep_pred_content3(h, fp, fc, pred, content, N, D, Dp, ssym.cov ? sh : Shard{0, N}, st));
@@ -2189,7 +2216,15 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
         CK(cudaStreamWaitEvent(s_aux, h->ev_fork2, 0));
         CK(cudaStreamWaitEvent(s_mom, h->ev_fork2, 0));
     }
+    // row-sharded symmetric path: the relaxed-EMD GEMM goes to a side stream (see shard_side above)
+    const bool remd_on_side = shard_side;
+    if (remd_on_side) {
+        CK(cudaEventRecord(h->ev_fork2, st));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork2, 0));
+        s_aux = h->side;
+    }
     RET(remd_local(h, h->style, M, fp, N, sh, Dp, rs, ry_remd, s_aux, true, D));
+    if (remd_on_side) CK(cudaEventRecord(h->ev_join2, h->side));
     if (par)
         RET(remd_finish(h, h->style, M, N, sh, D, rs, ry_remd, scalars, S_LREMD, S_REMD_RX, S_REMD_RY, S_REMD_BRANCH,
                         want_grad, row_arg, col_arg, s_aux));
@@ -2204,11 +2239,14 @@ static int eval_impl(strotss_handle h, const float* pred, long long ld_pred, con
             std::function<int()> owner_step;
             if (ssym.cov) owner_step = [&]() { return cov_sharded_owner(h, h->Vx, N, D, Dp, ssym, partials + PS_COV_L1, st); };
             rc = self_sim_sharded_sym(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, so, st, best, (size_t)2 * M,
-                                      &best_reduced, ssym, owner_step);
+                                      &best_reduced, ssym, owner_step, remd_on_side ? h->ev_join2 : nullptr,
+                                      shard_side ? h->ev_join : nullptr);
             if (rc < 0) return rc;
         }
         if (rc == 1) RET(self_sim_local(h, fp, fc, N, sh, D, Dp, partials + PS_SS_LOSS, partials + PS_V, want_grad, so, st));
     }
+    if (remd_on_side) CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
+    if (shard_side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
     if (par) {
         CK(cudaStreamWaitEvent(st, h->ev_join, 0));
         CK(cudaStreamWaitEvent(st, h->ev_join2, 0));
