@@ -1,11 +1,13 @@
 """Row-sharded multi-GPU evaluation: host-side plumbing (one process per GPU).
 
-The data path has exactly one exchange per evaluation (inside the C library, over NCCL): an
-allreduce-max of the packed (value, ~index) minima of the M style rows and an allreduce-sum of a
-(16 + D)-float block.  This module only (a) mirrors the library's row partition, (b) ships the NCCL
-unique id from rank 0 to the other ranks with torch.distributed (any backend: nccl on GPUs, gloo in
-the CPU tests) and (c) optionally all-gathers the per-rank gradient rows for callers that want the
-full (N, D) gradient on every rank.
+The whole exchange of an evaluation happens inside the C library (csrc/api.cu): two small allreduces
+-- {sum of N floats, max of the packed (value, ~index) minima of the M style rows} and a sum of a
+(16 + D)-float block -- plus, for the symmetric self-similarity and covariance tiles that are dealt out
+over the ranks, bf16 sign blocks and partial covariance tiles.  With CUDA IPC available everything moves
+through peer windows over NVLink (`Handle.comm_transport() == 1`), otherwise over NCCL.  This module
+only (a) mirrors the library's row partition, (b) ships the NCCL unique id from rank 0 to the other
+ranks with torch.distributed (any backend: nccl on GPUs, gloo in the CPU tests) and (c) optionally
+all-gathers the per-rank gradient rows for callers that want the full (N, D) gradient on every rank.
 """
 from __future__ import annotations
 
