@@ -312,6 +312,20 @@ def extra_workloads(args, dev, S, _lib, torch, world, rank, barrier, max_over_ra
         ms_m, _ = timed_events(torch, lambda: hm.eval_grouped(preds, contents, ALPHA, True), steps, 5)
         out["masked_ms_per_step"] = {"grouped": round(ms_m, 4), "workload": f"R=3 regions {MASKED_REGIONS}, one strotss_eval_grouped call"}
         del hm
+        # ---- SURVEY 8d sweep below the headline size (the same loop as tools/size_sweep.py); never fatal for the line
+        try:
+            sweep = {}
+            hs = S.Handle(dev)
+            for n in (2048, 4096, 8192):
+                style, content, pred = synth_torch(n, n, D_FEAT, args.eps, 0, dev)
+                hs.set_style_target(style)
+                ms_n, _ = timed_events(torch, lambda: hs.eval(pred, content, ALPHA, True, False), 20, 3)
+                sweep[f"N=M={n}"] = {"ms_per_step": round(ms_n, 4), "tflops_alg": round(f_alg(n, n) / (ms_n * 1e-3) / 1e12, 1)}
+            out["size_sweep"] = sweep
+            del hs, style, content, pred
+        except Exception as e:  # noqa: BLE001
+            out["size_sweep"] = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
     barrier()
     if not args.no_image:
         import bench_e2e
