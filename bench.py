@@ -13,7 +13,8 @@ Besides the contract's keys the line carries (all measured in this run, outside 
              block (scalars, argmins and this rank's gradient rows against a single-GPU evaluation of the same
              inputs on the same rank; the run FAILS on a mismatch)
   extra      the other BASELINE workloads in short form: default sample count (N=M=1024, direct and CUDA-graph
-             replay), masked transfer (R=3 regions), seconds per stylised 512-px image and images/s at 1024 px
+             replay), masked transfer (R=3 regions), the size sweep N=M=2048/4096/8192, seconds per stylised 512-px image and
+             images/s at 1024 px
              (bench_e2e.py; one job per GPU)
 """
 from __future__ import annotations
@@ -287,6 +288,21 @@ def run_masked(args, dev, S, _lib):
     print(json.dumps(line), flush=True)
 
 
+def size_sweep_extra(dev, S, torch, eps, sizes=(2048, 4096, 8192), steps=20):
+    """SURVEY 8d sweep below the headline size (the same loop as tools/size_sweep.py).  Never fatal for the bench line."""
+    try:
+        sweep = {}
+        hs = S.Handle(dev)
+        for n in sizes:
+            style, content, pred = synth_torch(n, n, D_FEAT, eps, 0, dev)
+            hs.set_style_target(style)
+            ms_n, _ = timed_events(torch, lambda: hs.eval(pred, content, ALPHA, True, False), steps, 3)
+            sweep[f"N=M={n}"] = {"ms_per_step": round(ms_n, 4), "tflops_alg": round(f_alg(n, n) / (ms_n * 1e-3) / 1e12, 1)}
+        return sweep
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
 def extra_workloads(args, dev, S, _lib, torch, world, rank, barrier, max_over_ranks):
     """Short forms of the other BASELINE workloads, so that the driver's BENCH / SCALE records carry them:
     default sample count (configs[1]'s per-iteration loss), masked transfer (configs[2]), seconds per stylised image
@@ -312,19 +328,8 @@ def extra_workloads(args, dev, S, _lib, torch, world, rank, barrier, max_over_ra
         ms_m, _ = timed_events(torch, lambda: hm.eval_grouped(preds, contents, ALPHA, True), steps, 5)
         out["masked_ms_per_step"] = {"grouped": round(ms_m, 4), "workload": f"R=3 regions {MASKED_REGIONS}, one strotss_eval_grouped call"}
         del hm
-        # ---- SURVEY 8d sweep below the headline size (the same loop as tools/size_sweep.py); never fatal for the line
-        try:
-            sweep = {}
-            hs = S.Handle(dev)
-            for n in (2048, 4096, 8192):
-                style, content, pred = synth_torch(n, n, D_FEAT, args.eps, 0, dev)
-                hs.set_style_target(style)
-                ms_n, _ = timed_events(torch, lambda: hs.eval(pred, content, ALPHA, True, False), 20, 3)
-                sweep[f"N=M={n}"] = {"ms_per_step": round(ms_n, 4), "tflops_alg": round(f_alg(n, n) / (ms_n * 1e-3) / 1e12, 1)}
-            out["size_sweep"] = sweep
-            del hs, style, content, pred
-        except Exception as e:  # noqa: BLE001
-            out["size_sweep"] = {"error": str(e)[:200]}
+        del style, content, pred
+        out["size_sweep"] = size_sweep_extra(dev, S, torch, args.eps)
         torch.cuda.empty_cache()
     barrier()
     if not args.no_image:

@@ -105,3 +105,38 @@ def test_peaks_come_from_the_measured_file_or_the_stated_fallback():
     else:
         assert p["source"].startswith("fallback")
     assert 4000 < p["hbm"] < 8000 and 1000 < p["tf_sust"] <= p["tf_burst"] < 2300
+
+
+def test_size_sweep_extra_over_a_stand_in_handle(monkeypatch):
+    """The sweep that rides in the default line's extras, executed over a stand-in handle (logic only): one entry per size with the
+    SURVEY 8d FLOP count, and an error entry instead of an exception when the handle fails."""
+    import types
+
+    import torch
+
+    calls = []
+
+    class _Handle:
+        def __init__(self, dev):
+            self.n = None
+
+        def set_style_target(self, style):
+            self.n = style.shape[0]
+
+        def eval(self, pred, content, alpha, want_grad, want_arg):
+            assert pred.shape == content.shape == (self.n, 8) and alpha == bench.ALPHA and want_grad and not want_arg
+            calls.append(self.n)
+            return None
+
+    monkeypatch.setattr(bench, "synth_torch", lambda N, M, D, eps, seed, dev: tuple(torch.zeros(n, 8) for n in (M, N, N)))
+    monkeypatch.setattr(bench, "timed_events", lambda torch_, fn, steps, warmup: ([fn() for _ in range(steps + warmup)], 2.0)[1:] + (None,))
+    got = bench.size_sweep_extra("cpu", types.SimpleNamespace(Handle=_Handle), torch, 1.0, sizes=(256, 512), steps=2)
+    assert list(got) == ["N=M=256", "N=M=512"] and calls == [256] * 5 + [512] * 5
+    assert got["N=M=512"]["ms_per_step"] == 2.0
+    assert got["N=M=512"]["tflops_alg"] == pytest.approx(bench.f_alg(512, 512) / 2e-3 / 1e12, abs=0.06)
+
+    class _Broken(_Handle):
+        def set_style_target(self, style):
+            raise RuntimeError("boom")
+
+    assert bench.size_sweep_extra("cpu", types.SimpleNamespace(Handle=_Broken), torch, 1.0) == {"error": "boom"}
