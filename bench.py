@@ -328,9 +328,7 @@ def extra_workloads(args, dev, S, _lib, torch, world, rank, barrier, max_over_ra
         ms_m, _ = timed_events(torch, lambda: hm.eval_grouped(preds, contents, ALPHA, True), steps, 5)
         out["masked_ms_per_step"] = {"grouped": round(ms_m, 4), "workload": f"R=3 regions {MASKED_REGIONS}, one strotss_eval_grouped call"}
         del hm
-        del style, content, pred
         out["size_sweep"] = size_sweep_extra(dev, S, torch, args.eps)
-        torch.cuda.empty_cache()
     barrier()
     if not args.no_image:
         import bench_e2e
